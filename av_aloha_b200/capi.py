@@ -1,0 +1,205 @@
+"""ctypes binding of libavsim.so (include/avsim.h) + thin torch-tensor helpers.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in the hand-written sm_100a kernels
+behind the C-ABI.  There is no CPU fallback: importing this module without the built library, or creating a
+batch without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libavsim.so")
+
+# avsim_field
+QPOS, QVEL, CTRL, WARMSTART, AGENT_POS, REWARD, SUCCESS, NCON, CONTACTS, STATUS, LATCH, QACC, XPOS, QFRC_BIAS, \
+    QACC_SMOOTH, MASS_DIAG = range(16)
+MAX_CONTACTS = 40
+
+SYMBOLS = [
+    "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
+    "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
+    "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error",
+]
+
+
+class DiffIKParams(C.Structure):
+    _fields_ = [("k_pos", C.c_float), ("k_ori", C.c_float), ("damping", C.c_float), ("max_angvel", C.c_float),
+                ("integration_dt", C.c_float), ("k_null", C.c_float * 7), ("q0", C.c_float * 7),
+                ("iterations", C.c_int)]
+
+
+class GradIKParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("min_cost_delta", C.c_float), ("position_weight", C.c_float),
+                ("rotation_weight", C.c_float), ("position_threshold", C.c_float), ("rotation_threshold", C.c_float),
+                ("max_pos_diff", C.c_float), ("max_rot_diff", C.c_float), ("joint_p", C.c_float),
+                ("joint_center_weight", C.c_float * 7), ("joint_displacement_weight", C.c_float * 7),
+                ("max_iterations", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libavsim.so (fails loudly when it has not been built: run ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension has not been built (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    vp, cp, i32, u64 = C.c_void_p, C.c_char_p, C.c_int, C.c_uint64
+    L.avsim_model_load.restype = vp; L.avsim_model_load.argtypes = [cp, i32]
+    L.avsim_model_free.argtypes = [vp]
+    L.avsim_model_dim.argtypes = [vp, cp]
+    L.avsim_create.restype = vp; L.avsim_create.argtypes = [vp, i32, u64, vp]
+    L.avsim_destroy.argtypes = [vp]
+    L.avsim_set_options.argtypes = [vp, i32, i32, i32]
+    L.avsim_reset.argtypes = [vp, vp, vp]
+    L.avsim_step.argtypes = [vp, vp, i32]
+    L.avsim_forward.argtypes = [vp]
+    L.avsim_get.argtypes = [vp, i32, vp]
+    L.avsim_set.argtypes = [vp, i32, vp]
+    L.avsim_step_host.argtypes = [vp, vp, i32, vp, vp]
+    L.avsim_launch_count.restype = C.c_int64; L.avsim_launch_count.argtypes = [vp]
+    L.avsim_diffik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(DiffIKParams), vp, vp]
+    L.avsim_gradik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(GradIKParams), vp, vp]
+    L.avsim_fk.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.avsim_last_error.restype = cp
+    _lib = L
+    return L
+
+
+class AvsimError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise AvsimError(f"avsim error {rc}: {load_library().avsim_last_error().decode()}")
+
+
+class Model:
+    """Compiled model resident on one CUDA device (replaces mjcf.from_path + Physics.from_mjcf_model, env.py:53-56)."""
+
+    def __init__(self, avm_path, device=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("av_aloha_b200 needs a CUDA device; there is no CPU path")
+        self.lib = load_library()
+        self.device = int(device)
+        self.ptr = self.lib.avsim_model_load(os.fsencode(avm_path), self.device)
+        if not self.ptr:
+            raise AvsimError(self.lib.avsim_last_error().decode())
+        d = lambda n: self.lib.avsim_model_dim(self.ptr, n.encode())
+        self.nq, self.nv, self.nu, self.nbody, self.ngeom = d("nq"), d("nv"), d("nu"), d("nbody"), d("ngeom")
+        self.njoints, self.nfree, self.max_reward, self.task_id, self.num_arms = (
+            d("njoints"), d("nfree"), d("max_reward"), d("task_id"), d("num_arms"))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.avsim_model_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Batch:
+    """B environments in lockstep on one GPU (replaces B GuidedVisionEnv instances under SyncVectorEnv)."""
+
+    def __init__(self, model: Model, num_envs: int, seed: int = 0, stream=None):
+        import torch
+
+        self.torch = torch
+        self.model = model
+        self.lib = model.lib
+        self.num_envs = int(num_envs)
+        self.dev = torch.device("cuda", model.device)
+        self.stream = stream
+        sp = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        self.ptr = self.lib.avsim_create(model.ptr, self.num_envs, C.c_uint64(seed), sp)
+        if not self.ptr:
+            raise AvsimError(self.lib.avsim_last_error().decode())
+        m = model
+        self._shape = {
+            QPOS: (m.nq, torch.float32), QVEL: (m.nv, torch.float32), CTRL: (m.nu, torch.float32),
+            WARMSTART: (m.nv, torch.float32), AGENT_POS: (m.njoints, torch.float32), REWARD: (None, torch.int32),
+            SUCCESS: (None, torch.int32), NCON: (None, torch.int32), CONTACTS: ((MAX_CONTACTS, 16), torch.float32),
+            STATUS: (None, torch.int32), LATCH: (None, torch.int32), QACC: (m.nv, torch.float32),
+            XPOS: ((m.nbody, 3), torch.float32), QFRC_BIAS: (m.nv, torch.float32), QACC_SMOOTH: (m.nv, torch.float32),
+            MASS_DIAG: (m.nv, torch.float32),
+        }
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.lib.avsim_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_options(self, solver_iters=20, noslip_iters=-1, multiccd=-1):
+        check(self.lib.avsim_set_options(self.ptr, solver_iters, noslip_iters, multiccd))
+
+    def reset(self, mask=None, free_pos=None):
+        t = self.torch
+        mp = fp = None
+        if mask is not None:
+            self._mask = t.as_tensor(mask, dtype=t.uint8, device=self.dev).contiguous()
+            mp = C.c_void_p(self._mask.data_ptr())
+        if free_pos is not None:
+            self._fp = t.as_tensor(np.asarray(free_pos, dtype=np.float32), device=self.dev).contiguous()
+            assert self._fp.shape == (self.num_envs, self.model.nfree, 3), self._fp.shape
+            fp = C.c_void_p(self._fp.data_ptr())
+        check(self.lib.avsim_reset(self.ptr, mp, fp))
+
+    def step(self, action, nsubsteps=20):
+        """action: float32 CUDA tensor [B, njoints] (stays on the device)."""
+        assert action.is_cuda and action.dtype == self.torch.float32 and action.is_contiguous()
+        assert tuple(action.shape) == (self.num_envs, self.model.njoints), action.shape
+        check(self.lib.avsim_step(self.ptr, C.c_void_p(action.data_ptr()), nsubsteps))
+
+    def step_host(self, action_np, nsubsteps=20, agent_pos_out=None, reward_out=None):
+        """Host-buffer path: numpy float32 [B, njoints] in, numpy agent_pos / reward out (copies inside the call)."""
+        a = np.ascontiguousarray(action_np, dtype=np.float32)
+        assert a.shape == (self.num_envs, self.model.njoints), a.shape
+        if agent_pos_out is None:
+            agent_pos_out = np.empty((self.num_envs, self.model.njoints), np.float32)
+        if reward_out is None:
+            reward_out = np.empty((self.num_envs,), np.int32)
+        check(self.lib.avsim_step_host(self.ptr, a.ctypes.data_as(C.c_void_p), nsubsteps,
+                                       agent_pos_out.ctypes.data_as(C.c_void_p), reward_out.ctypes.data_as(C.c_void_p)))
+        return agent_pos_out, reward_out
+
+    def forward(self):
+        check(self.lib.avsim_forward(self.ptr))
+
+    def get(self, field, out=None):
+        t = self.torch
+        w, dt = self._shape[field]
+        shape = (self.num_envs,) if w is None else (self.num_envs,) + (w if isinstance(w, tuple) else (w,))
+        if out is None:
+            out = t.empty(shape, dtype=dt, device=self.dev)
+        check(self.lib.avsim_get(self.ptr, field, C.c_void_p(out.data_ptr())))
+        return out
+
+    def set(self, field, value):
+        t = self.torch
+        w, dt = self._shape[field]
+        shape = (self.num_envs,) if w is None else (self.num_envs, w)
+        v = t.as_tensor(value, dtype=dt, device=self.dev).contiguous()
+        assert tuple(v.shape) == shape, (v.shape, shape)
+        self._keep = v
+        check(self.lib.avsim_set(self.ptr, field, C.c_void_p(v.data_ptr())))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.avsim_launch_count(self.ptr))

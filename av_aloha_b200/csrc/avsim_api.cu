@@ -1,0 +1,317 @@
+// avsim_api.cu -- C-ABI of libavsim.so (include/avsim.h): model upload, batch state, kernel launches.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/avsim.h"
+#include "avsim_ik.cuh"
+#include "avsim_kernels.cuh"
+#include "avsim_model_pack.h"
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return fail(AVSIM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CUP(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) { fail(AVSIM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); return nullptr; } \
+    } while (0)
+
+// ------------------------------------------------------------------ model
+struct avsim_model {
+    DevModel dm;
+    avpack::PackedModel pk;
+    int device;
+    float *fblob = nullptr;
+    int *iblob = nullptr;
+    float *hull = nullptr;
+    float *home_dev = nullptr;
+};
+
+extern "C" const char *avsim_last_error(void) { return g_err; }
+
+extern "C" avsim_model *avsim_model_load(const char *avm_path, int device) {
+    avsim_model *M = new avsim_model();
+    if (!avpack::pack_model(avm_path, M->pk)) {
+        fail(AVSIM_ERR_IO, "avsim_model_load('%s'): %s", avm_path ? avm_path : "(null)", M->pk.error.c_str());
+        delete M;
+        return nullptr;
+    }
+    CUP(cudaSetDevice(device));
+    M->device = device;
+    avpack::Packer &P = M->pk.P;
+    CUP(cudaMalloc(&M->fblob, P.fdata.size() * sizeof(float)));
+    CUP(cudaMalloc(&M->iblob, P.idata.size() * sizeof(int)));
+    CUP(cudaMalloc(&M->hull, M->pk.hull4.size() * sizeof(float)));
+    CUP(cudaMemcpy(M->fblob, P.fdata.data(), P.fdata.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUP(cudaMemcpy(M->iblob, P.idata.data(), P.idata.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUP(cudaMemcpy(M->hull, M->pk.hull4.data(), M->pk.hull4.size() * sizeof(float), cudaMemcpyHostToDevice));
+    M->pk.relocate(M->fblob, M->iblob, M->hull);
+    M->dm = M->pk.dm;
+    CUP(cudaMalloc(&M->home_dev, sizeof AV_HOME));
+    CUP(cudaMemcpy(M->home_dev, AV_HOME, sizeof AV_HOME, cudaMemcpyHostToDevice));
+    return M;
+}
+
+extern "C" void avsim_model_free(avsim_model *m) {
+    if (!m) return;
+    cudaFree(m->fblob); cudaFree(m->iblob); cudaFree(m->hull); cudaFree(m->home_dev);
+    delete m;
+}
+
+extern "C" int avsim_model_dim(const avsim_model *m, const char *what) {
+    if (!m || !what) return fail(AVSIM_ERR_ARG, "avsim_model_dim: null argument");
+    const DevModel &d = m->dm;
+    std::string w(what);
+    if (w == "nq") return d.nq;
+    if (w == "nv") return d.nv;
+    if (w == "nu") return d.nu;
+    if (w == "nbody") return d.nbody;
+    if (w == "ngeom") return d.ngeom;
+    if (w == "njoints") return d.nj_obs;
+    if (w == "nfree") return d.nfree;
+    if (w == "max_reward") return d.max_reward;
+    if (w == "task_id") return d.task_id;
+    if (w == "num_arms") return d.num_arms;
+    return fail(AVSIM_ERR_ARG, "avsim_model_dim: unknown dimension '%s'", what);
+}
+
+// ------------------------------------------------------------------ batch
+struct avsim_batch {
+    const avsim_model *model;
+    BatchState st;
+    cudaStream_t stream;
+    int grid;
+    int64_t launches = 0;
+    std::vector<void *> allocs;
+    float *h_action = nullptr, *h_agent = nullptr;   // pinned staging for the host-buffer path
+    int32_t *h_reward = nullptr;
+    float *d_action = nullptr;
+};
+
+template <typename T>
+static bool dalloc(avsim_batch *b, T **p, size_t n) {
+    if (cudaMalloc(p, n * sizeof(T)) != cudaSuccess) return false;
+    cudaMemset(*p, 0, n * sizeof(T));
+    b->allocs.push_back(*p);
+    return true;
+}
+
+extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_t seed, void *stream) {
+    if (!m || num_envs <= 0) { fail(AVSIM_ERR_ARG, "avsim_create: bad arguments"); return nullptr; }
+    CUP(cudaSetDevice(m->device));
+    avsim_batch *b = new avsim_batch();
+    b->model = m;
+    b->stream = (cudaStream_t)stream;
+    const DevModel &d = m->dm;
+    BatchState &s = b->st;
+    memset(&s, 0, sizeof s);
+    s.num_envs = num_envs; s.seed = seed;
+    s.solver_iters = 20; s.noslip_iters = d.noslip_iterations; s.multiccd = d.multiccd;
+    size_t B = num_envs;
+    bool ok = dalloc(b, &s.qpos, B * d.nq) && dalloc(b, &s.qvel, B * d.nv) && dalloc(b, &s.ctrl, B * d.nu) &&
+              dalloc(b, &s.warm, B * d.nv) && dalloc(b, &s.agent_pos, B * d.nj_obs) && dalloc(b, &s.reward, B) &&
+              dalloc(b, &s.status, B) && dalloc(b, &s.latch, B) && dalloc(b, &s.ncon, B) && dalloc(b, &s.episode, B) &&
+              dalloc(b, &s.contacts, B * AV_NCON * 16) && dalloc(b, &s.qacc, B * d.nv) && dalloc(b, &s.xpos, B * 3 * d.nbody) &&
+              dalloc(b, &s.qfrc_bias, B * d.nv) && dalloc(b, &s.qacc_smooth, B * d.nv) && dalloc(b, &s.mass_diag, B * d.nv) &&
+              dalloc(b, &s.scratch, B * AV_SCRATCH_FLOATS) && dalloc(b, &b->d_action, B * d.nj_obs);
+    if (!ok) { fail(AVSIM_ERR_CUDA, "avsim_create: device allocation failed"); avsim_destroy(b); return nullptr; }
+    if (cudaMallocHost(&b->h_action, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
+        cudaMallocHost(&b->h_agent, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
+        cudaMallocHost(&b->h_reward, B * sizeof(int32_t)) != cudaSuccess) {
+        fail(AVSIM_ERR_CUDA, "avsim_create: pinned allocation failed");
+        avsim_destroy(b);
+        return nullptr;
+    }
+    int smem = (int)sizeof(EnvS);
+    CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0, sms = 0;
+    CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, avsim_step_kernel, 32, smem));
+    CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+    if (per_sm < 1) { fail(AVSIM_ERR_CUDA, "avsim_create: step kernel does not fit on an SM"); avsim_destroy(b); return nullptr; }
+    b->grid = std::min(num_envs, per_sm * sms);   // persistent: a multiple of the SM count, looping over envs
+    if (avsim_reset(b, nullptr, nullptr) != 0) { avsim_destroy(b); return nullptr; }
+    return b;
+}
+
+extern "C" void avsim_destroy(avsim_batch *b) {
+    if (!b) return;
+    cudaStreamSynchronize(b->stream);
+    for (void *p : b->allocs) cudaFree(p);
+    if (b->h_action) cudaFreeHost(b->h_action);
+    if (b->h_agent) cudaFreeHost(b->h_agent);
+    if (b->h_reward) cudaFreeHost(b->h_reward);
+    delete b;
+}
+
+extern "C" int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_iters, int multiccd) {
+    if (!b || solver_iters < 0) return fail(AVSIM_ERR_ARG, "avsim_set_options: bad arguments");
+    b->st.solver_iters = solver_iters;
+    b->st.noslip_iters = noslip_iters >= 0 ? noslip_iters : b->model->dm.noslip_iterations;
+    b->st.multiccd = multiccd >= 0 ? multiccd : b->model->dm.multiccd;
+    return AVSIM_OK;
+}
+
+static int launch_forward(avsim_batch *b) {
+    avsim_forward_kernel<<<b->grid, 32, sizeof(EnvS), b->stream>>>(b->model->dm, b->st);
+    b->launches++;
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}
+
+extern "C" int avsim_reset(avsim_batch *b, const uint8_t *mask_dev, const float *free_pos_dev) {
+    if (!b) return fail(AVSIM_ERR_ARG, "avsim_reset: null batch");
+    CU(cudaSetDevice(b->model->device));
+    int n = b->st.num_envs;
+    avsim_reset_kernel<<<(n + 127) / 128, 128, 0, b->stream>>>(b->model->dm, b->st, mask_dev, free_pos_dev, b->model->home_dev);
+    b->launches++;
+    CU(cudaGetLastError());
+    return launch_forward(b);   // physics.forward() + first observation (reference env.py:244-246)
+}
+
+extern "C" int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps) {
+    if (!b || nsubsteps < 0) return fail(AVSIM_ERR_ARG, "avsim_step: bad arguments");
+    CU(cudaSetDevice(b->model->device));
+    avsim_step_kernel<<<b->grid, 32, sizeof(EnvS), b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
+    b->launches++;
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}
+
+extern "C" int avsim_forward(avsim_batch *b) {
+    if (!b) return fail(AVSIM_ERR_ARG, "avsim_forward: null batch");
+    CU(cudaSetDevice(b->model->device));
+    return launch_forward(b);
+}
+
+static int field_ptr(avsim_batch *b, int field, void **p, size_t *bytes) {
+    const DevModel &d = b->model->dm;
+    BatchState &s = b->st;
+    size_t B = s.num_envs;
+    switch (field) {
+    case AVSIM_QPOS: *p = s.qpos; *bytes = B * d.nq * 4; break;
+    case AVSIM_QVEL: *p = s.qvel; *bytes = B * d.nv * 4; break;
+    case AVSIM_CTRL: *p = s.ctrl; *bytes = B * d.nu * 4; break;
+    case AVSIM_WARMSTART: *p = s.warm; *bytes = B * d.nv * 4; break;
+    case AVSIM_AGENT_POS: *p = s.agent_pos; *bytes = B * d.nj_obs * 4; break;
+    case AVSIM_REWARD: *p = s.reward; *bytes = B * 4; break;
+    case AVSIM_NCON: *p = s.ncon; *bytes = B * 4; break;
+    case AVSIM_CONTACTS: *p = s.contacts; *bytes = B * AV_NCON * 16 * 4; break;
+    case AVSIM_STATUS: *p = s.status; *bytes = B * 4; break;
+    case AVSIM_LATCH: *p = s.latch; *bytes = B * 4; break;
+    case AVSIM_QACC: *p = s.qacc; *bytes = B * d.nv * 4; break;
+    case AVSIM_XPOS: *p = s.xpos; *bytes = B * 3 * d.nbody * 4; break;
+    case AVSIM_QFRC_BIAS: *p = s.qfrc_bias; *bytes = B * d.nv * 4; break;
+    case AVSIM_QACC_SMOOTH: *p = s.qacc_smooth; *bytes = B * d.nv * 4; break;
+    case AVSIM_MASS_DIAG: *p = s.mass_diag; *bytes = B * d.nv * 4; break;
+    default: return fail(AVSIM_ERR_ARG, "unknown field");
+    }
+    return AVSIM_OK;
+}
+
+__global__ void avsim_success_kernel(const int *reward, int max_reward, int *out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = reward[i] == max_reward;
+}
+
+extern "C" int avsim_get(avsim_batch *b, int field, void *dst_dev) {
+    if (!b || !dst_dev) return fail(AVSIM_ERR_ARG, "avsim_get: null argument");
+    CU(cudaSetDevice(b->model->device));
+    if (field == AVSIM_SUCCESS) {
+        int n = b->st.num_envs;
+        avsim_success_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->st.reward, b->model->dm.max_reward, (int *)dst_dev, n);
+        b->launches++;
+        CU(cudaGetLastError());
+        return AVSIM_OK;
+    }
+    void *p;
+    size_t bytes;
+    int rc = field_ptr(b, field, &p, &bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst_dev, p, bytes, cudaMemcpyDeviceToDevice, b->stream));
+    return AVSIM_OK;
+}
+
+extern "C" int avsim_set(avsim_batch *b, int field, const void *src_dev) {
+    if (!b || !src_dev) return fail(AVSIM_ERR_ARG, "avsim_set: null argument");
+    if (field != AVSIM_QPOS && field != AVSIM_QVEL && field != AVSIM_CTRL && field != AVSIM_WARMSTART && field != AVSIM_LATCH)
+        return fail(AVSIM_ERR_ARG, "avsim_set: field is read-only");
+    CU(cudaSetDevice(b->model->device));
+    void *p;
+    size_t bytes;
+    int rc = field_ptr(b, field, &p, &bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(p, src_dev, bytes, cudaMemcpyDeviceToDevice, b->stream));
+    return AVSIM_OK;
+}
+
+extern "C" int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host) {
+    if (!b || !action_host) return fail(AVSIM_ERR_ARG, "avsim_step_host: null argument");
+    CU(cudaSetDevice(b->model->device));
+    const DevModel &d = b->model->dm;
+    size_t na = (size_t)b->st.num_envs * d.nj_obs;
+    memcpy(b->h_action, action_host, na * sizeof(float));
+    CU(cudaMemcpyAsync(b->d_action, b->h_action, na * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    int rc = avsim_step(b, b->d_action, nsubsteps);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(b->h_agent, b->st.agent_pos, na * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(b->h_reward, b->st.reward, b->st.num_envs * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    if (agent_pos_host) memcpy(agent_pos_host, b->h_agent, na * sizeof(float));
+    if (reward_host) memcpy(reward_host, b->h_reward, b->st.num_envs * sizeof(int32_t));
+    return AVSIM_OK;
+}
+
+extern "C" int64_t avsim_launch_count(const avsim_batch *b) { return b ? b->launches : 0; }
+
+// ------------------------------------------------------------------ IK entry points
+extern "C" int avsim_diffik(const avsim_model *m, int arm, const float *q, const float *pos, const float *quat, int n,
+                            const avsim_diffik_params *p, float *q_out, void *stream) {
+    if (!m || !q || !pos || !quat || !p || !q_out || arm < 0 || arm > 2 || n < 0) return fail(AVSIM_ERR_ARG, "avsim_diffik: bad arguments");
+    CU(cudaSetDevice(m->device));
+    if (n == 0) return AVSIM_OK;
+    DiffIKParams dp;
+    dp.k_pos = p->k_pos; dp.k_ori = p->k_ori; dp.damping = p->damping; dp.max_angvel = p->max_angvel;
+    dp.dt = p->integration_dt; dp.iterations = p->iterations;
+    for (int k = 0; k < 7; k++) { dp.k_null[k] = p->k_null[k]; dp.q0[k] = p->q0[k]; }
+    avsim_diffik_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(m->dm, arm, q, pos, quat, n, dp, q_out);
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}
+extern "C" int avsim_gradik(const avsim_model *m, int arm, const float *q, const float *pos, const float *quat, int n,
+                            const avsim_gradik_params *p, float *q_out, void *stream) {
+    if (!m || !q || !pos || !quat || !p || !q_out || arm < 0 || arm > 2 || n < 0) return fail(AVSIM_ERR_ARG, "avsim_gradik: bad arguments");
+    CU(cudaSetDevice(m->device));
+    if (n == 0) return AVSIM_OK;
+    GradIKParams gp;
+    gp.step_size = p->step_size; gp.min_cost_delta = p->min_cost_delta; gp.position_weight = p->position_weight;
+    gp.rotation_weight = p->rotation_weight; gp.position_threshold = p->position_threshold;
+    gp.rotation_threshold = p->rotation_threshold; gp.max_pos_diff = p->max_pos_diff; gp.max_rot_diff = p->max_rot_diff;
+    gp.joint_p = p->joint_p; gp.max_iterations = p->max_iterations;
+    for (int k = 0; k < 7; k++) { gp.center_w[k] = p->joint_center_weight[k]; gp.disp_w[k] = p->joint_displacement_weight[k]; }
+    avsim_gradik_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(m->dm, arm, q, pos, quat, n, gp, q_out);
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}
+extern "C" int avsim_fk(const avsim_model *m, int arm, const float *q, int n, float *T_out, void *stream) {
+    if (!m || !q || !T_out || arm < 0 || arm > 2 || n < 0) return fail(AVSIM_ERR_ARG, "avsim_fk: bad arguments");
+    CU(cudaSetDevice(m->device));
+    if (n == 0) return AVSIM_OK;
+    avsim_fk_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(m->dm, arm, q, n, T_out);
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}

@@ -1,0 +1,392 @@
+// avsim_collide.cuh -- fp32 narrowphase for the warp-per-environment step kernel.
+//
+// Replaces MuJoCo's mj_collision narrowphase [third-party; reached through Physics.step, reference env.py:218].
+// Primitive pairs (sphere-sphere, sphere-box, box-box) run one candidate pair per lane; every other convex pair
+// (mesh hulls, cylinder) runs Minkowski Portal Refinement cooperatively on the whole warp: control flow is
+// warp-uniform and the hull support map is an exhaustive arg-max strided over the 32 lanes (hull vertices are
+// float4 in L2-resident model memory, so one support query is ceil(nvert/32) coalesced 512-byte reads).
+// Contact convention: normal from geom1 to geom2, dist < 0 is penetration, pos is the mid-surface point.
+#pragma once
+#include "avsim_dev.h"
+#include "avsim_math.cuh"
+
+#define AV_MPR_TOL 1e-6f
+#define AV_MPR_ITERS 50
+
+struct Shape {
+    int type, nvert;
+    V3 pos, size;
+    M3 mat;
+    const float4 *vert;
+};
+
+struct PrimOut {   // <= 8 points sharing one normal
+    int n;
+    V3 nrm;
+    float dist[8];
+    V3 pos[8];
+};
+
+__device__ __forceinline__ void make_frame(V3 n, V3 &t1, V3 &t2) {
+    V3 e = fabsf(n.y) < 0.5f ? v3(0, 1, 0) : v3(0, 0, 1);
+    t1 = normalized(e - n * dot(e, n));
+    t2 = cross(n, t1);
+}
+
+// ------------------------------------------------------------------ closed forms (one pair per lane)
+__device__ inline void collide_sphere_sphere(const Shape &A, const Shape &B, PrimOut &o) {
+    V3 d = B.pos - A.pos;
+    float len = norm(d), dist = len - A.size.x - B.size.x;
+    o.n = 0;
+    if (dist >= 0) return;
+    d = len < AV_MINVAL ? v3(0, 0, 1) : d * (1.0f / len);
+    o.n = 1; o.nrm = d; o.dist[0] = dist;
+    o.pos[0] = A.pos + d * (A.size.x + 0.5f * dist);
+}
+
+// A sphere, B box; normal from the sphere to the box
+__device__ inline void collide_sphere_box(const Shape &A, const Shape &B, PrimOut &o) {
+    V3 c = mulT(B.mat, A.pos - B.pos);
+    V3 q = v3(fminf(fmaxf(c.x, -B.size.x), B.size.x), fminf(fmaxf(c.y, -B.size.y), B.size.y),
+              fminf(fmaxf(c.z, -B.size.z), B.size.z));
+    bool inside = (q.x == c.x) && (q.y == c.y) && (q.z == c.z);
+    float r = A.size.x, dist;
+    V3 nl;
+    o.n = 0;
+    if (!inside) {
+        V3 dv = c - q;
+        float len = norm(dv);
+        dist = len - r;
+        if (dist >= 0) return;
+        nl = dv * (-1.0f / len);
+    } else {
+        float dx = B.size.x - fabsf(c.x), dy = B.size.y - fabsf(c.y), dz = B.size.z - fabsf(c.z);
+        nl = v3(0, 0, 0);
+        float bd;
+        if (dx <= dy && dx <= dz) { bd = dx; nl.x = c.x >= 0 ? -1.f : 1.f; q.x = c.x >= 0 ? B.size.x : -B.size.x; }
+        else if (dy <= dz) { bd = dy; nl.y = c.y >= 0 ? -1.f : 1.f; q.y = c.y >= 0 ? B.size.y : -B.size.y; }
+        else { bd = dz; nl.z = c.z >= 0 ? -1.f : 1.f; q.z = c.z >= 0 ? B.size.z : -B.size.z; }
+        dist = -bd - r;
+    }
+    V3 nw = mul(B.mat, nl), qw = mul(B.mat, q) + B.pos;
+    o.n = 1; o.nrm = nw; o.dist[0] = dist;
+    o.pos[0] = qw + nw * (0.5f * dist);
+}
+
+// ------------------------------------------------------------------ box-box: 15-axis SAT + face clipping / edge-edge
+__device__ inline int clip_poly(float (*poly)[3], int n, int axis, float lim) {
+    for (int pass = 0; pass < 2; pass++) {
+        float sgn = pass ? -1.f : 1.f, outp[16][3];
+        int no = 0;
+        for (int i = 0; i < n; i++) {
+            const float *a = poly[i], *b = poly[(i + 1) % n];
+            float da = sgn * a[axis] - lim, db = sgn * b[axis] - lim;
+            if (da <= 0) { outp[no][0] = a[0]; outp[no][1] = a[1]; outp[no][2] = a[2]; no++; }
+            if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
+                float t = da / (da - db);
+                for (int k = 0; k < 3; k++) outp[no][k] = a[k] + t * (b[k] - a[k]);
+                no++;
+            }
+        }
+        n = no;
+        for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) poly[i][k] = outp[i][k];
+        if (!n) break;
+    }
+    return n;
+}
+
+__device__ inline void collide_box_box(const Shape &A, const Shape &B, PrimOut &o) {
+    V3 a[3], b[3];
+    float R[3][3], Q[3][3], dA[3], dB[3];
+    float hA[3] = {A.size.x, A.size.y, A.size.z}, hB[3] = {B.size.x, B.size.y, B.size.z};
+    for (int k = 0; k < 3; k++) { a[k] = colm(A.mat, k); b[k] = colm(B.mat, k); }
+    V3 d = B.pos - A.pos;
+    for (int i = 0; i < 3; i++) {
+        dA[i] = dot(d, a[i]); dB[i] = dot(d, b[i]);
+        for (int j = 0; j < 3; j++) { R[i][j] = dot(a[i], b[j]); Q[i][j] = fabsf(R[i][j]); }
+    }
+    o.n = 0;
+    float best = -1e30f;
+    int code = -1;
+    for (int i = 0; i < 3; i++) {
+        float s = fabsf(dA[i]) - (hA[i] + hB[0] * Q[i][0] + hB[1] * Q[i][1] + hB[2] * Q[i][2]);
+        if (s > 0) return;
+        if (s > best) { best = s; code = i; }
+    }
+    for (int j = 0; j < 3; j++) {
+        float s = fabsf(dB[j]) - (hB[j] + hA[0] * Q[0][j] + hA[1] * Q[1][j] + hA[2] * Q[2][j]);
+        if (s > 0) return;
+        if (s > best) { best = s; code = 3 + j; }
+    }
+    float ebest = -1e30f;
+    int ecode = -1;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float len2 = 1.f - R[i][j] * R[i][j];
+            if (len2 < 1e-8f) continue;
+            int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            float il = rsqrtf(len2);
+            float s = (fabsf(dA[i2] * R[i1][j] - dA[i1] * R[i2][j]) -
+                       (hA[i1] * Q[i2][j] + hA[i2] * Q[i1][j] + hB[j1] * Q[i][j2] + hB[j2] * Q[i][j1])) * il;
+            if (s > 0) return;
+            if (s > ebest) { ebest = s; ecode = 3 * i + j; }
+        }
+    if (ecode >= 0 && ebest > 0.95f * best + 1e-9f) {
+        int i = ecode / 3, j = ecode % 3;
+        V3 L = normalized(cross(a[i], b[j]));
+        if (dot(L, d) < 0) L = -L;
+        V3 pa = A.pos, pb = B.pos;
+        for (int k = 0; k < 3; k++) {
+            if (k != i) pa = pa + a[k] * ((dot(L, a[k]) > 0 ? 1.f : -1.f) * hA[k]);
+            if (k != j) pb = pb + b[k] * ((dot(L, b[k]) > 0 ? -1.f : 1.f) * hB[k]);
+        }
+        V3 w = pa - pb;
+        float ab = R[i][j], wa = dot(w, a[i]), wb = dot(w, b[j]), den = 1.f - ab * ab;
+        float s = (ab * wb - wa) / den, t = (wb - ab * wa) / den;
+        o.n = 1; o.nrm = L; o.dist[0] = ebest;
+        o.pos[0] = ((pa + a[i] * s) + (pb + b[j] * t)) * 0.5f;
+        return;
+    }
+    bool refA = code < 3;
+    const Shape &Rf = refA ? A : B;
+    const Shape &In = refA ? B : A;
+    const V3 *ra = refA ? a : b, *ia = refA ? b : a;
+    const float *hR = refA ? hA : hB, *hI = refA ? hB : hA;
+    int ri = code % 3;
+    V3 dref = In.pos - Rf.pos;
+    float sgn = dot(dref, ra[ri]) >= 0 ? 1.f : -1.f;
+    V3 nref = ra[ri] * sgn;
+    int ij = 0;
+    float bestdot = -1.f;
+    for (int k = 0; k < 3; k++) {
+        float dt = fabsf(dot(nref, ia[k]));
+        if (dt > bestdot) { bestdot = dt; ij = k; }
+    }
+    float isgn = dot(nref, ia[ij]) > 0 ? -1.f : 1.f;
+    int iu = (ij + 1) % 3, iv = (ij + 2) % 3, ru = (ri + 1) % 3, rv = (ri + 2) % 3;
+    float poly[16][3];
+    for (int c = 0; c < 4; c++) {
+        float su = (c == 0 || c == 3) ? 1.f : -1.f, sv = (c < 2) ? 1.f : -1.f;
+        V3 p = dref + ia[ij] * (isgn * hI[ij]) + ia[iu] * (su * hI[iu]) + ia[iv] * (sv * hI[iv]);
+        poly[c][0] = dot(p, ra[ru]); poly[c][1] = dot(p, ra[rv]); poly[c][2] = dot(p, nref);
+    }
+    int n = clip_poly(poly, 4, 0, hR[ru]);
+    if (n) n = clip_poly(poly, n, 1, hR[rv]);
+    int nc = 0;
+    for (int c = 0; c < n && nc < 8; c++) {
+        float sep = poly[c][2] - hR[ri];
+        if (sep > 0) continue;
+        o.dist[nc] = sep;
+        o.pos[nc] = Rf.pos + ra[ru] * poly[c][0] + ra[rv] * poly[c][1] + nref * (poly[c][2] - 0.5f * sep);
+        nc++;
+    }
+    o.n = nc;
+    o.nrm = refA ? nref : -nref;
+}
+
+// ------------------------------------------------------------------ warp-cooperative MPR
+struct Sup {
+    V3 v, v1, v2;
+};
+
+// support point of S in world direction dir; uniform across the warp
+__device__ inline V3 support_world(const Shape &S, V3 dir, int lane) {
+    V3 dl = mulT(S.mat, dir), pl;
+    if (S.type == AV_GEOM_MESH) {
+        float bd = -3.0e38f;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < S.nvert; i += 32) {
+            float4 p = S.vert[i];
+            float dt = p.x * dl.x + p.y * dl.y + p.z * dl.z;
+            if (dt > bd) { bd = dt; bi = i; }
+        }
+        warp_argmax(bd, bi);
+        float4 p = S.vert[bi];
+        pl = v3(p.x, p.y, p.z);
+    } else if (S.type == AV_GEOM_BOX) {
+        pl = v3(dl.x >= 0 ? S.size.x : -S.size.x, dl.y >= 0 ? S.size.y : -S.size.y, dl.z >= 0 ? S.size.z : -S.size.z);
+    } else if (S.type == AV_GEOM_SPHERE) {
+        float n = norm(dl);
+        pl = n < AV_MINVAL ? v3(0, 0, 0) : dl * (S.size.x / n);
+    } else {  // cylinder: radius size.x, half height size.y along local z
+        float n = sqrtf(dl.x * dl.x + dl.y * dl.y);
+        pl = n > AV_MINVAL ? v3(dl.x / n * S.size.x, dl.y / n * S.size.x, 0) : v3(0, 0, 0);
+        pl.z = dl.z >= 0 ? S.size.y : -S.size.y;
+    }
+    return mul(S.mat, pl) + S.pos;
+}
+__device__ inline Sup mpr_support(const Shape &A, const Shape &B, V3 dir, int lane) {
+    Sup s;
+    s.v1 = support_world(A, dir, lane);
+    s.v2 = support_world(B, -dir, lane);
+    s.v = s.v1 - s.v2;
+    return s;
+}
+__device__ __forceinline__ V3 portal_dir(const Sup *p) { return normalized(cross(p[2].v - p[1].v, p[3].v - p[1].v)); }
+__device__ __forceinline__ void expand_portal(Sup *p, const Sup &v4) {
+    V3 v4v0 = cross(v4.v, p[0].v);
+    if (dot(p[1].v, v4v0) > 0) {
+        if (dot(p[2].v, v4v0) > 0) p[1] = v4; else p[3] = v4;
+    } else {
+        if (dot(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4;
+    }
+}
+__device__ __forceinline__ bool reach_tolerance(const Sup *p, const Sup &v4, V3 dir) {
+    float dv4 = dot(v4.v, dir);
+    float dt = fminf(fminf(dv4 - dot(p[1].v, dir), dv4 - dot(p[2].v, dir)), dv4 - dot(p[3].v, dir));
+    return dt <= AV_MPR_TOL;
+}
+__device__ inline float origin_tri_dist2(V3 a, V3 b, V3 c, V3 &wit) {
+    V3 ab = b - a, ac = c - a, ap = -a;
+    float d1 = dot(ab, ap), d2 = dot(ac, ap), s, t;
+    if (d1 <= 0 && d2 <= 0) { s = 0; t = 0; }
+    else {
+        float d3 = dot(ab, -b), d4 = dot(ac, -b);
+        if (d3 >= 0 && d4 <= d3) { s = 1; t = 0; }
+        else {
+            float vc = d1 * d4 - d3 * d2;
+            if (vc <= 0 && d1 >= 0 && d3 <= 0) { s = d1 / (d1 - d3); t = 0; }
+            else {
+                float d5 = dot(ab, -c), d6 = dot(ac, -c);
+                if (d6 >= 0 && d5 <= d6) { s = 0; t = 1; }
+                else {
+                    float vb = d5 * d2 - d1 * d6;
+                    if (vb <= 0 && d2 >= 0 && d6 <= 0) { s = 0; t = d2 / (d2 - d6); }
+                    else {
+                        float va = d3 * d6 - d5 * d4;
+                        if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { t = (d4 - d3) / ((d4 - d3) + (d5 - d6)); s = 1 - t; }
+                        else { float den = 1.0f / (va + vb + vc); s = vb * den; t = vc * den; }
+                    }
+                }
+            }
+        }
+    }
+    wit = a + ab * s + ac * t;
+    return dot(wit, wit);
+}
+__device__ inline V3 find_pos(const Sup *p) {
+    V3 dir = portal_dir(p);
+    float b[4];
+    b[0] = dot(cross(p[1].v, p[2].v), p[3].v);
+    b[1] = dot(cross(p[3].v, p[2].v), p[0].v);
+    b[2] = dot(cross(p[0].v, p[1].v), p[3].v);
+    b[3] = dot(cross(p[2].v, p[1].v), p[0].v);
+    float sum = b[0] + b[1] + b[2] + b[3];
+    if (sum <= 0) {
+        b[0] = 0;
+        b[1] = dot(cross(p[2].v, p[3].v), dir);
+        b[2] = dot(cross(p[3].v, p[1].v), dir);
+        b[3] = dot(cross(p[1].v, p[2].v), dir);
+        sum = b[1] + b[2] + b[3];
+    }
+    float inv = 1.0f / sum;
+    V3 p1 = v3(0, 0, 0), p2 = v3(0, 0, 0);
+    for (int i = 0; i < 4; i++) { p1 = p1 + p[i].v1 * b[i]; p2 = p2 + p[i].v2 * b[i]; }
+    return (p1 + p2) * (0.5f * inv);
+}
+
+// returns true (warp-uniform) and depth / direction A->B / position when the shapes intersect
+__device__ inline bool mpr_penetration(const Shape &A, const Shape &B, int lane, float &depth, V3 &dir, V3 &pos) {
+    Sup p[4], v4;
+    p[0].v1 = A.pos; p[0].v2 = B.pos; p[0].v = A.pos - B.pos;
+    if (norm(p[0].v) < 1e-9f) p[0].v.x += 1e-6f;
+    dir = normalized(-p[0].v);
+    p[1] = mpr_support(A, B, dir, lane);
+    if (dot(p[1].v, dir) <= 0) return false;
+    dir = cross(p[0].v, p[1].v);
+    if (norm(dir) < 1e-12f) {
+        pos = (p[1].v1 + p[1].v2) * 0.5f;
+        if (norm(p[1].v) < 1e-9f) { depth = 0; dir = v3(0, 0, 0); return true; }
+        depth = norm(p[1].v);
+        dir = normalized(p[1].v);
+        return true;
+    }
+    dir = normalized(dir);
+    p[2] = mpr_support(A, B, dir, lane);
+    if (dot(p[2].v, dir) <= 0) return false;
+    dir = normalized(cross(p[1].v - p[0].v, p[2].v - p[0].v));
+    if (dot(dir, p[0].v) > 0) { Sup t = p[1]; p[1] = p[2]; p[2] = t; dir = -dir; }
+    for (int it = 0;; it++) {
+        if (it > 100) return false;
+        p[3] = mpr_support(A, B, dir, lane);
+        if (dot(p[3].v, dir) <= 0) return false;
+        bool cont = false;
+        if (dot(cross(p[1].v, p[3].v), p[0].v) < 0) { p[2] = p[3]; cont = true; }
+        if (!cont && dot(cross(p[3].v, p[2].v), p[0].v) < 0) { p[1] = p[3]; cont = true; }
+        if (!cont) break;
+        dir = normalized(cross(p[1].v - p[0].v, p[2].v - p[0].v));
+    }
+    for (int it = 0;; it++) {
+        dir = portal_dir(p);
+        if (dot(dir, p[1].v) >= 0) break;
+        v4 = mpr_support(A, B, dir, lane);
+        if (dot(v4.v, dir) < 0 || reach_tolerance(p, v4, dir) || it > 100) return false;
+        expand_portal(p, v4);
+    }
+    for (int it = 0;; it++) {
+        dir = portal_dir(p);
+        v4 = mpr_support(A, B, dir, lane);
+        if (reach_tolerance(p, v4, dir) || it > AV_MPR_ITERS) {
+            V3 wit;
+            float d2 = origin_tri_dist2(p[1].v, p[2].v, p[3].v, wit);
+            depth = sqrtf(d2);
+            if (depth >= 1e-9f) dir = normalized(wit);
+            pos = find_pos(p);
+            return true;
+        }
+        expand_portal(p, v4);
+    }
+}
+
+__device__ inline M3 rot_axis_angle(V3 ax, float ang) {
+    float c = cosf(ang), s = sinf(ang), t = 1 - c, x = ax.x, y = ax.y, z = ax.z;
+    M3 R;
+    R.m[0] = t * x * x + c; R.m[1] = t * x * y - s * z; R.m[2] = t * x * z + s * y;
+    R.m[3] = t * x * y + s * z; R.m[4] = t * y * y + c; R.m[5] = t * y * z - s * x;
+    R.m[6] = t * x * z - s * y; R.m[7] = t * y * z + s * x; R.m[8] = t * z * z + c;
+    return R;
+}
+
+// warp-cooperative convex pair: up to 5 points (multiccd) sharing the unperturbed normal
+__device__ inline void collide_convex(const Shape &A, const Shape &B, bool multiccd, int lane, PrimOut &o) {
+    float depth;
+    V3 dir, pos;
+    o.n = 0;
+    if (!mpr_penetration(A, B, lane, depth, dir, pos)) return;
+    if (norm(dir) < 0.5f) return;
+    o.n = 1; o.nrm = dir; o.dist[0] = -depth; o.pos[0] = pos;
+    if (!multiccd) return;
+    V3 t1, t2;
+    make_frame(dir, t1, t2);
+    for (int q = 0; q < 4; q++) {
+        V3 ax = q < 2 ? t1 : t2;
+        float ang = (q & 1) ? -1e-3f : 1e-3f;
+        M3 Rp = rot_axis_angle(ax, ang), Rm = rot_axis_angle(ax, -ang);
+        Shape A2 = A, B2 = B;
+        A2.mat = mul(Rp, A.mat); A2.pos = pos + mul(Rp, A.pos - pos);
+        B2.mat = mul(Rm, B.mat); B2.pos = pos + mul(Rm, B.pos - pos);
+        float dp;
+        V3 dr, ps;
+        if (!mpr_penetration(A2, B2, lane, dp, dr, ps) || norm(dr) < 0.5f) continue;
+        bool dup = false;
+        for (int c = 0; c < o.n; c++) dup = dup || norm(ps - o.pos[c]) < 1e-4f;
+        if (dup) continue;
+        o.dist[o.n] = -dp; o.pos[o.n] = ps; o.n++;
+    }
+}
+
+// conservative oriented-box test on the 6 face axes of the two local bounding boxes
+__device__ inline bool obb_separated(V3 hA, const Shape &A, V3 hB, const Shape &B) {
+    V3 d = B.pos - A.pos;
+    for (int i = 0; i < 3; i++) {
+        V3 ai = colm(A.mat, i);
+        float rb = hB.x * fabsf(dot(ai, colm(B.mat, 0))) + hB.y * fabsf(dot(ai, colm(B.mat, 1))) + hB.z * fabsf(dot(ai, colm(B.mat, 2)));
+        if (fabsf(dot(d, ai)) > comp(hA, i) + rb) return true;
+    }
+    for (int j = 0; j < 3; j++) {
+        V3 bj = colm(B.mat, j);
+        float ra = hA.x * fabsf(dot(bj, colm(A.mat, 0))) + hA.y * fabsf(dot(bj, colm(A.mat, 1))) + hA.z * fabsf(dot(bj, colm(A.mat, 2)));
+        if (fabsf(dot(d, bj)) > comp(hB, j) + ra) return true;
+    }
+    return false;
+}

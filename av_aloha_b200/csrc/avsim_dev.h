@@ -1,0 +1,82 @@
+// avsim_dev.h -- device-side model tables and batch state shared by the kernels and the host API.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   * model constants: one fp32 blob + one int32 blob per loaded model, read-only, shared by all environments
+//     (hull vertices 18 014 x float4 = 288 KB dominate; everything is L2-resident after the first substep);
+//   * per-environment persistent state, environment-major rows: qpos[nq] qvel[nv] ctrl[nu] warmstart[nv]
+//     (+ latch, reward, status, agent_pos) -- the 1 032 B/env-step algorithmic traffic of SURVEY.md 8(d);
+//   * per-environment solver scratch (contact Jacobian blocks), written and re-read inside one launch only.
+#pragma once
+#include <stdint.h>
+
+#define AV_NB 32        // max bodies
+#define AV_NV 41        // max dofs (TubeTransfer)
+#define AV_NVP 44       // padded
+#define AV_NQ 44
+#define AV_NU 21
+#define AV_NG 96        // max collidable geoms
+#define AV_NTREE 6
+#define AV_TD 8         // max dofs per kinematic tree
+#define AV_MBLK (AV_NTREE * AV_TD * AV_TD)
+#define AV_NCON 40      // max contacts per environment (== AVSIM_MAX_CONTACTS)
+#define AV_NSC 20       // max scalar constraint rows (equality + friction loss + joint limits)
+#define AV_NCAND 64     // broadphase survivors per class
+#define AV_JW 16        // columns of a contact Jacobian block: 8 dofs of tree1 | 8 dofs of tree2
+
+enum { AV_JNT_FREE = 0, AV_JNT_SLIDE = 2, AV_JNT_HINGE = 3 };
+enum { AV_GEOM_SPHERE = 2, AV_GEOM_CYLINDER = 5, AV_GEOM_BOX = 6, AV_GEOM_MESH = 7 };
+enum { AV_PAIR_SS = 0, AV_PAIR_SB = 1, AV_PAIR_BS = 2, AV_PAIR_BB = 3, AV_PAIR_CONVEX = 4 };
+
+struct DevModel {
+    int nbody, njnt, nv, nq, ngeom, npair, nu, neq, ntree, nfree, nj_obs;
+    int task_id, max_reward, num_arms, noslip_iterations, multiccd;
+    float timestep, impratio, gravity[3];
+    // bodies
+    const int *body_parent, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_tree, *body_lastdof;
+    const float *body_pos, *body_quat, *body_mass, *body_ipos, *body_inertia, *body_invweight0;
+    const float *body_xpos0, *body_xquat0;   // world pose at qpos0 (exact for world-welded bodies)
+    // trees (bodies and dofs of a tree are contiguous)
+    const int *tree_bodyadr, *tree_bodynum, *tree_dofadr, *tree_dofnum;
+    // joints / dofs
+    const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
+    const float *jnt_axis, *jnt_pos, *jnt_range, *jnt_solref, *jnt_solimp;
+    const int *dof_body, *dof_jnt, *dof_parent, *dof_tree, *dof_frc_limited;
+    const float *dof_armature, *dof_damping, *dof_frictionloss, *dof_frc_lo, *dof_frc_hi, *dof_invweight0,
+        *dof_solref, *dof_solimp;
+    const float *qpos0;
+    // geoms
+    const int *geom_type, *geom_body, *geom_condim, *geom_hull, *geom_class, *geom_static;
+    const float *geom_pos, *geom_mat, *geom_size, *geom_rbound, *geom_aabb, *geom_friction, *geom_solref,
+        *geom_solimp, *geom_gap, *geom_margin;
+    const float *geom_xpos0, *geom_xmat0, *geom_xaabb0;   // world pose / world AABB half extents of world-welded geoms
+    const int *hull_adr, *hull_num;
+    const float4 *hull_vert;
+    const int *pair_geom;                    // packed g1 | g2 << 8 | type << 16
+    const float *pair_rsum;                  // rbound1 + rbound2
+    // equality / actuators / env tables
+    const int *eq_dof1, *eq_dof2, *eq_qadr1, *eq_qadr2;
+    const float *eq_polycoef, *eq_solref, *eq_solimp, *eq_invweight0;
+    const int *act_dof, *act_qadr;
+    const float *act_kp, *act_kv, *act_ctrl_lo, *act_ctrl_hi;
+    const int *obs_qadr, *finger_qadr, *free_qadr;
+    const float *reset_lo, *reset_hi;        // [nfree*3] uniform ranges of the task reset
+    const int *reset_draw;                   // Philox stream layout (which draw feeds which coordinate)
+    // IK tables
+    const int *ik_ndof;
+    const float *ik_w0, *ik_p0, *ik_site0, *ik_range;
+};
+
+struct BatchState {
+    int num_envs;
+    float *qpos, *qvel, *ctrl, *warm, *agent_pos;   // [B][nq|nv|nu|nv|nj]
+    int *reward, *status, *latch, *ncon, *episode;  // [B]
+    float *contacts;                                // [B][AV_NCON][16]
+    float *qacc, *xpos, *qfrc_bias, *qacc_smooth, *mass_diag;  // debug dumps of the last forward pass
+    float *scratch;                                 // [B][AV_SCRATCH_FLOATS]
+    uint64_t seed;
+    int solver_iters, noslip_iters, multiccd;
+};
+
+// per-contact solver block in global scratch: J[6][16], MinvJT[6][16], AR (21, packed lower), Ainv (15, packed)
+#define AV_CBLK (6 * AV_JW * 2 + 21 + 15)
+#define AV_SCRATCH_FLOATS (AV_NCON * AV_CBLK)

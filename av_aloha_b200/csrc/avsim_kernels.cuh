@@ -1,0 +1,169 @@
+// avsim_kernels.cuh -- __global__ entry points: env step (nsub substeps + trailing position pass + reward),
+// forward (stage dumps for parity tests) and reset.  One warp (= one 32-thread block) per environment;
+// the grid is a persistent multiple of the SM count and loops over environments.
+#pragma once
+#include "avsim_step.cuh"
+
+extern __shared__ float4 av_smem_raw[];
+
+__device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane) {
+    for (int i = lane; i < m.nq; i += 32) S.qpos[i] = B.qpos[(size_t)env * m.nq + i];
+    for (int i = lane; i < m.nv; i += 32) { S.qvel[i] = B.qvel[(size_t)env * m.nv + i]; S.warm[i] = B.warm[(size_t)env * m.nv + i]; }
+    for (int i = lane; i < m.nu; i += 32) S.ctrl[i] = B.ctrl[(size_t)env * m.nu + i];
+    // world-welded bodies keep their compile-time pose
+    for (int b = lane; b < m.nbody; b += 32)
+        if (m.body_tree[b] < 0) {
+            st3(S.xpos + 3 * b, ld3(m.body_xpos0 + 3 * b));
+            Q4 q = ldq(m.body_xquat0 + 4 * b);
+            stq(S.xquat + 4 * b, q);
+            stm3(S.xmat + 9 * b, q2m(q));
+        }
+    for (int g = lane; g < m.ngeom; g += 32)
+        if (m.geom_static[g]) {
+            st3(S.gpos + 3 * g, ld3(m.geom_xpos0 + 3 * g));
+            st3(S.gaabb + 3 * g, ld3(m.geom_xaabb0 + 3 * g));
+        }
+    if (lane == 0) { S.status = 0; S.ncon = 0; S.nsc = 0; }
+    __syncwarp();
+}
+__device__ inline void env_store(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane) {
+    for (int i = lane; i < m.nq; i += 32) B.qpos[(size_t)env * m.nq + i] = S.qpos[i];
+    for (int i = lane; i < m.nv; i += 32) { B.qvel[(size_t)env * m.nv + i] = S.qvel[i]; B.warm[(size_t)env * m.nv + i] = S.warm[i]; }
+    for (int i = lane; i < m.nu; i += 32) B.ctrl[(size_t)env * m.nu + i] = S.ctrl[i];
+}
+
+__device__ inline void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane) {
+    stage_kinematics(m, S, lane);
+    stage_inertia(m, S, lane);
+    stage_collision(m, S, lane, B.multiccd != 0);
+    stage_smooth(m, S, lane);
+    stage_rows_scalar(m, S, lane);
+    stage_rows_contact(m, S, scratch, lane);
+    stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters);
+}
+
+__device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane, bool with_reward) {
+    int latch = B.latch[env];
+    int r = stage_reward(m, S, lane, latch);
+    if (!with_reward) { r = B.reward[env]; latch = B.latch[env]; }
+    for (int k = lane; k < m.nj_obs; k += 32) {
+        float q = S.qpos[m.obs_qadr[k]];
+        if (k == 6 || k == 13) q = (q - m.act_ctrl_lo[k]) / (m.act_ctrl_hi[k] - m.act_ctrl_lo[k]);
+        B.agent_pos[(size_t)env * m.nj_obs + k] = q;
+    }
+    // numerical blow-up guard: flag and leave the state for the host-side auto-reset
+    int bad = 0;
+    for (int i = lane; i < m.nq; i += 32) bad |= !(fabsf(S.qpos[i]) < 1e6f);
+    bad = __any_sync(AV_FULL, bad);
+    if (lane == 0) {
+        B.reward[env] = r;
+        B.latch[env] = latch;
+        B.ncon[env] = S.ncon;
+        B.status[env] = S.status | (bad ? 1 : 0);
+    }
+    for (int c = lane; c < S.ncon; c += 32) {
+        float *o = B.contacts + ((size_t)env * AV_NCON + c) * 16;
+        int info = S.c_info[c];
+        o[0] = S.c_dist[c];
+        o[1] = S.c_pos[3 * c]; o[2] = S.c_pos[3 * c + 1]; o[3] = S.c_pos[3 * c + 2];
+        o[4] = S.c_frame[9 * c]; o[5] = S.c_frame[9 * c + 1]; o[6] = S.c_frame[9 * c + 2];
+        o[7] = (float)(info & 0xff); o[8] = (float)((info >> 8) & 0xff); o[9] = (float)((info >> 16) & 0xf);
+        o[10] = (float)((info >> 20) & 1); o[11] = S.c_f[6 * c];
+        o[12] = o[13] = o[14] = o[15] = 0.f;
+    }
+}
+
+// env.step: ctrl write (reference env.py:204-215), nsub x mj_step (env.py:218), trailing position pass, reward
+__global__ void __launch_bounds__(32) avsim_step_kernel(DevModel m, BatchState B, const float *__restrict__ action, int nsub) {
+    EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
+    int lane = threadIdx.x;
+    for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
+        env_load(m, B, S, env, lane);
+        if (action && lane < m.nj_obs) {
+            float a = action[(size_t)env * m.nj_obs + lane];
+            if (lane == 6 || lane == 13) a = a * (m.act_ctrl_hi[lane] - m.act_ctrl_lo[lane]) + m.act_ctrl_lo[lane];
+            S.ctrl[lane] = a;
+        }
+        __syncwarp();
+        float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
+        for (int s = 0; s < nsub; s++) {
+            env_forward(m, B, S, scratch, lane);
+            stage_integrate(m, S, lane);
+        }
+        stage_kinematics(m, S, lane);
+        stage_collision(m, S, lane, B.multiccd != 0);
+        env_store(m, B, S, env, lane);
+        env_outputs(m, B, S, env, lane, true);
+        __syncwarp();
+    }
+}
+
+// physics.forward(): all stages, no integration; dumps stage outputs for the parity tests
+__global__ void __launch_bounds__(32) avsim_forward_kernel(DevModel m, BatchState B) {
+    EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
+    int lane = threadIdx.x;
+    for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
+        env_load(m, B, S, env, lane);
+        float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
+        env_forward(m, B, S, scratch, lane);
+        for (int i = lane; i < m.nv; i += 32) {
+            B.qacc[(size_t)env * m.nv + i] = S.qacc_smooth[i] + S.acc[i];
+            B.qacc_smooth[(size_t)env * m.nv + i] = S.qacc_smooth[i];
+            B.qfrc_bias[(size_t)env * m.nv + i] = S.qfrc_bias[i];
+            int t = m.dof_tree[i], dl = i - m.tree_dofadr[t];
+            B.mass_diag[(size_t)env * m.nv + i] = S.M[t * AV_TD * AV_TD + dl * AV_TD + dl];
+        }
+        for (int i = lane; i < 3 * m.nbody; i += 32) B.xpos[(size_t)env * 3 * m.nbody + i] = S.xpos[i];
+        env_outputs(m, B, S, env, lane, false);
+        __syncwarp();
+    }
+}
+
+// ---- Philox4x32-10 counter RNG for device-side reset draws
+__device__ inline void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// reset: home pose, open fingers, ctrl = home, object placement (reference env.py:228-249 + task resets); thread = env
+__global__ void avsim_reset_kernel(DevModel m, BatchState B, const uint8_t *__restrict__ mask, const float *__restrict__ free_pos,
+                                   const float *__restrict__ home /*[21]*/) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= B.num_envs) return;
+    if (mask && !mask[env]) return;
+    float *qpos = B.qpos + (size_t)env * m.nq, *qvel = B.qvel + (size_t)env * m.nv, *ctrl = B.ctrl + (size_t)env * m.nu,
+          *warm = B.warm + (size_t)env * m.nv;
+    for (int i = 0; i < m.nq; i++) qpos[i] = m.qpos0[i];
+    for (int i = 0; i < m.nv; i++) { qvel[i] = 0.f; warm[i] = 0.f; }
+    for (int k = 0; k < 21; k++) { qpos[m.obs_qadr[k]] = home[k]; ctrl[k] = home[k]; }
+    float open_l = m.act_ctrl_hi[6], open_r = m.act_ctrl_hi[13];
+    qpos[m.finger_qadr[0]] = qpos[m.finger_qadr[1]] = open_l;
+    qpos[m.finger_qadr[2]] = qpos[m.finger_qadr[3]] = open_r;
+    ctrl[6] = open_l; ctrl[13] = open_r;
+    int episode = B.episode[env];
+    for (int k = 0; k < m.nfree; k++) {
+        int qa = m.free_qadr[k];
+        float p[3];
+        if (free_pos) {
+            for (int a = 0; a < 3; a++) p[a] = free_pos[((size_t)env * m.nfree + k) * 3 + a];
+        } else {
+            int src = m.reset_draw[k];   // TubeTransfer's tube1 re-uses the ball's draw (env.py:713-716)
+            uint32_t c[4] = {(uint32_t)env, (uint32_t)episode, (uint32_t)src, 0x41564c4fu};
+            philox4x32(c, (uint32_t)B.seed, (uint32_t)(B.seed >> 32));
+            for (int a = 0; a < 3; a++) {
+                float u = (c[a] >> 8) * (1.0f / 16777216.0f);
+                p[a] = m.reset_lo[3 * k + a] + u * (m.reset_hi[3 * k + a] - m.reset_lo[3 * k + a]);
+            }
+        }
+        qpos[qa] = p[0]; qpos[qa + 1] = p[1]; qpos[qa + 2] = p[2];
+        qpos[qa + 3] = 1.f; qpos[qa + 4] = qpos[qa + 5] = qpos[qa + 6] = 0.f;
+    }
+    B.latch[env] = 0;
+    B.reward[env] = 0;
+    B.status[env] = 0;
+    B.episode[env] = episode + 1;
+}

@@ -1,0 +1,131 @@
+// avsim_math.cuh -- small fp32 vector helpers + warp collectives used by the step kernel.
+#pragma once
+
+#define AV_FULL 0xffffffffu
+#define AV_MINVAL 1e-15f
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
+__device__ __forceinline__ V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(float *p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float norm(V3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ V3 normalized(V3 a) {
+    float n = norm(a);
+    return n > AV_MINVAL ? a * (1.0f / n) : a;
+}
+__device__ __forceinline__ float comp(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+// row-major 3x3
+struct M3 {
+    float m[9];
+};
+__device__ __forceinline__ M3 ldm3(const float *p) {
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.m[i] = p[i];
+    return r;
+}
+__device__ __forceinline__ void stm3(float *p, const M3 &a) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) p[i] = a.m[i];
+}
+__device__ __forceinline__ V3 mul(const M3 &a, V3 v) {
+    return v3(a.m[0] * v.x + a.m[1] * v.y + a.m[2] * v.z, a.m[3] * v.x + a.m[4] * v.y + a.m[5] * v.z,
+              a.m[6] * v.x + a.m[7] * v.y + a.m[8] * v.z);
+}
+__device__ __forceinline__ V3 mulT(const M3 &a, V3 v) {
+    return v3(a.m[0] * v.x + a.m[3] * v.y + a.m[6] * v.z, a.m[1] * v.x + a.m[4] * v.y + a.m[7] * v.z,
+              a.m[2] * v.x + a.m[5] * v.y + a.m[8] * v.z);
+}
+__device__ __forceinline__ M3 mul(const M3 &a, const M3 &b) {
+    M3 r;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+    return r;
+}
+__device__ __forceinline__ V3 colm(const M3 &a, int k) { return v3(a.m[k], a.m[3 + k], a.m[6 + k]); }
+
+struct Q4 {
+    float w, x, y, z;
+};
+__device__ __forceinline__ Q4 ldq(const float *p) { Q4 q = {p[0], p[1], p[2], p[3]}; return q; }
+__device__ __forceinline__ void stq(float *p, Q4 q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; }
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+    Q4 r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+    r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+    return r;
+}
+__device__ __forceinline__ Q4 qnormalize(Q4 q) {
+    float n = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    if (n < AV_MINVAL) { Q4 i = {1, 0, 0, 0}; return i; }
+    float s = 1.0f / n;
+    Q4 r = {q.w * s, q.x * s, q.y * s, q.z * s};
+    return r;
+}
+__device__ __forceinline__ M3 q2m(Q4 q) {
+    M3 r;
+    float w = q.w, x = q.x, y = q.y, z = q.z;
+    r.m[0] = 1 - 2 * (y * y + z * z); r.m[1] = 2 * (x * y - w * z); r.m[2] = 2 * (x * z + w * y);
+    r.m[3] = 2 * (x * y + w * z); r.m[4] = 1 - 2 * (x * x + z * z); r.m[5] = 2 * (y * z - w * x);
+    r.m[6] = 2 * (x * z - w * y); r.m[7] = 2 * (y * z + w * x); r.m[8] = 1 - 2 * (x * x + y * y);
+    return r;
+}
+
+// 6-vectors: [angular; linear]
+struct S6 {
+    V3 a, l;
+};
+__device__ __forceinline__ S6 ld6(const float *p) { S6 r = {ld3(p), ld3(p + 3)}; return r; }
+__device__ __forceinline__ void st6(float *p, S6 s) { st3(p, s.a); st3(p + 3, s.l); }
+__device__ __forceinline__ S6 operator+(S6 a, S6 b) { S6 r = {a.a + b.a, a.l + b.l}; return r; }
+__device__ __forceinline__ S6 operator*(S6 a, float s) { S6 r = {a.a * s, a.l * s}; return r; }
+__device__ __forceinline__ float dot6(S6 a, S6 b) { return dot(a.a, b.a) + dot(a.l, b.l); }
+__device__ __forceinline__ S6 cross_motion(S6 v, S6 s) {
+    S6 r = {cross(v.a, s.a), cross(v.a, s.l) + cross(v.l, s.a)};
+    return r;
+}
+__device__ __forceinline__ S6 cross_force(S6 v, S6 f) {
+    S6 r = {cross(v.a, f.a) + cross(v.l, f.l), cross(v.a, f.l)};
+    return r;
+}
+// spatial inertia {Ixx Iyy Izz Ixy Ixz Iyz, m*c (3), m} about the tree origin, times a motion vector
+__device__ __forceinline__ S6 inert_mul(const float *I, S6 v) {
+    V3 mc = v3(I[6], I[7], I[8]);
+    S6 f;
+    f.a = v3(I[0] * v.a.x + I[3] * v.a.y + I[4] * v.a.z, I[3] * v.a.x + I[1] * v.a.y + I[5] * v.a.z,
+             I[4] * v.a.x + I[5] * v.a.y + I[2] * v.a.z) + cross(mc, v.l);
+    f.l = v.l * I[9] - cross(mc, v.a);
+    return f;
+}
+
+// ---- warp collectives (one warp == one environment)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(AV_FULL, v, o);
+    return v;
+}
+// argmax with lowest-index tie break; returns the winning (value, index) in every lane
+__device__ __forceinline__ void warp_argmax(float &v, int &i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(AV_FULL, v, o);
+        int oi = __shfl_xor_sync(AV_FULL, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}

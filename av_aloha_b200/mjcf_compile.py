@@ -742,10 +742,33 @@ def _finish(m, names):
     m["finger_qadr"] = np.array([qa("left_left_finger"), qa("left_right_finger"),
                                  qa("right_left_finger"), qa("right_right_finger")], np.int32)
     free = [j for j, t in enumerate(m["jnt_type"]) if t == JNT_FREE]
+    # task reset ranges (reference env.py:478-493,517-533,608-624,709-723,796-808); uniform(lo, hi) per coordinate
+    lo, hi, src = [], [], []
+    fnames = [names["joint"][j] for j in free]
+    for k, n in enumerate(fnames):
+        rl, rh, sname = RESET_RANGES[int(m["task_id"])][n]
+        lo.append(rl); hi.append(rh); src.append(fnames.index(sname) if sname else k)
+    m["reset_lo"], m["reset_hi"], m["reset_draw"] = np.array(lo, np.float64), np.array(hi, np.float64), np.array(src, np.int32)
     m["free_qadr"] = np.array([m["jnt_qposadr"][j] for j in free], np.int32)
     m["free_names"] = names["free_joint"] = [names["joint"][j] for j in free]
     del m["free_names"]
 
+
+# free joint -> (low[3], high[3], name of the free joint whose draw is re-used or None).  Note the reference passes
+# low > high for the hole's x range (env.py:485): numpy's uniform then samples low + (high-low)*u, kept as is.
+RESET_RANGES = {
+    0: {"peg_joint": ([0.1, -0.1, 0.01], [0.2, 0.1, 0.01], None),
+        "hole_joint": ([-0.1, -0.1, 0.021], [-0.2, 0.1, 0.021], None)},
+    1: {"slot_joint": ([-0.05, 0.1, 0.0], [0.05, 0.15, 0.0], None),
+        "stick_joint": ([-0.08, -0.1, 0.0], [0.08, 0.0, 0.0], None)},
+    2: {"wall_joint": ([-0.025, -0.025, 0.0], [0.025, 0.1, 0.0], None),
+        "needle_joint": ([0.15, -0.025, 0.0], [0.2, 0.1, 0.0], None)},
+    3: {"ball_joint": ([0.05, -0.05, 0.0], [0.1, 0.05, 0.0], None),
+        "tube1_joint": ([0.05, -0.05, 0.0], [0.1, 0.05, 0.0], "ball_joint"),
+        "tube2_joint": ([-0.1, -0.05, 0.0], [-0.05, 0.05, 0.0], None)},
+    4: {"hook_joint": ([-0.1, 0.3, 0.2], [0.1, 0.3, 0.3], None),
+        "package_joint": ([-0.1, 0.0, 0.0], [0.1, 0.15, 0.0], None)},
+}
 
 # class bits shared by all tasks
 CLS_LEFT, CLS_RIGHT, CLS_TABLE = 1, 2, 4

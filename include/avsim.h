@@ -1,0 +1,113 @@
+/*
+ * avsim.h -- C-ABI of the B200-native batched simulator behind gym_guided_vision's env.step()/reset()
+ * and the diff_ik / grad_ik controllers.
+ *
+ * The reference has no native boundary of its own (it calls MuJoCo through dm_control and numba-JITs its IK);
+ * each entry point below names the reference call it replaces so a maintainer can bind it (INTEGRATION.md
+ * shows the ctypes stub).  Plain pointers and sizes only; all *_dev pointers are CUDA device pointers owned by
+ * the caller (e.g. torch tensors), contiguous, environment-major.  Every function returns 0 on success or a
+ * negative code; the message is available from avsim_last_error() (thread-local).  Nothing throws across the ABI.
+ * Calls on one avsim_batch must be serialised by the caller; work is enqueued on the batch's stream and is
+ * asynchronous with respect to the host.
+ */
+#ifndef AVSIM_H
+#define AVSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct avsim_model avsim_model;
+typedef struct avsim_batch avsim_batch;
+
+#define AVSIM_OK 0
+#define AVSIM_ERR_ARG -1
+#define AVSIM_ERR_IO -2
+#define AVSIM_ERR_CUDA -3
+#define AVSIM_ERR_LIMIT -4
+
+/* fields of avsim_get / avsim_set  (dtype, per-env length) */
+enum avsim_field {
+    AVSIM_QPOS = 0,        /* f32 [nq]      physics.data.qpos            (reference env.py:251-253)           */
+    AVSIM_QVEL = 1,        /* f32 [nv]      physics.data.qvel                                                */
+    AVSIM_CTRL = 2,        /* f32 [nu]      physics.data.ctrl            (env.py:208-215)                     */
+    AVSIM_WARMSTART = 3,   /* f32 [nv]      data.qacc_warmstart                                               */
+    AVSIM_AGENT_POS = 4,   /* f32 [14|21]   get_obs()['agent_pos']       (env.py:169-178)                     */
+    AVSIM_REWARD = 5,      /* i32 [1]       get_reward()                 (env.py:425-472,546-589,640-690,...)  */
+    AVSIM_SUCCESS = 6,     /* i32 [1]       reward == max_reward         (env.py:224)                          */
+    AVSIM_NCON = 7,        /* i32 [1]       data.ncon                                                          */
+    AVSIM_CONTACTS = 8,    /* f32 [AVSIM_MAX_CONTACTS][16]: dist,pos3,normal3,geom1,geom2,dim,excluded,force_n,pad4 */
+    AVSIM_STATUS = 9,      /* i32 [1]       bit0 = numerical blow-up (auto-reset), bit1 = contact overflow     */
+    AVSIM_LATCH = 10,      /* i32 [1]       SewNeedle _threaded_needle   (env.py:602,631,673)                  */
+    AVSIM_QACC = 11,       /* f32 [nv]      data.qacc of the last forward pass                                 */
+    AVSIM_XPOS = 12,       /* f32 [nbody*3] data.xpos of the last forward pass                                 */
+    AVSIM_QFRC_BIAS = 13,  /* f32 [nv]                                                                          */
+    AVSIM_QACC_SMOOTH = 14,/* f32 [nv]                                                                          */
+    AVSIM_MASS_DIAG = 15   /* f32 [nv]      diagonal of the joint-space inertia                                */
+};
+#define AVSIM_MAX_CONTACTS 40
+
+/* ---- model: replaces mjcf.from_path + Physics.from_mjcf_model (reference env.py:53-56).
+ * `avm_path` is a compiled model table produced by av_aloha_b200/mjcf_compile.py from the reference's MJCF. */
+avsim_model *avsim_model_load(const char *avm_path, int device);
+void avsim_model_free(avsim_model *m);
+int avsim_model_dim(const avsim_model *m, const char *what); /* "nq","nv","nu","nbody","ngeom","njoints","max_reward","task_id","num_arms" */
+
+/* ---- batch of environments in lockstep: replaces B x GuidedVisionEnv instances under SyncVectorEnv
+ * (reference lerobot/common/envs/factory.py:50-56).  `stream` is a cudaStream_t (0 = default stream). */
+avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_t seed, void *stream);
+void avsim_destroy(avsim_batch *b);
+
+/* solver_iters: PGS sweeps per substep; noslip_iters < 0 takes the model's value (aloha_sim.xml:4);
+ * multiccd < 0 takes the model's flag (aloha_sim.xml:5). */
+int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_iters, int multiccd);
+
+/* reset: replaces GuidedVisionEnv.reset + task reset (env.py:228-249, 474-501, 513-543, 604-637, 705-735, 792-818).
+ * mask_dev: u8[B] nullable (null = all envs).  free_pos_dev: f32[B][nfree][3] object positions drawn by the host
+ * in the reference's np.random order, nullable (null = Philox draw on the device from (seed, env, episode)). */
+int avsim_reset(avsim_batch *b, const uint8_t *mask_dev, const float *free_pos_dev);
+
+/* step: replaces GuidedVisionEnv.step / step_action (env.py:203-226, 255-269): ctrl write with gripper
+ * un-normalisation, nsubsteps x mj_step, trailing position pass, reward, agent_pos.  action_dev: f32[B][14|21]. */
+int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps);
+
+/* forward: replaces physics.forward() (env.py:244,253): position + velocity + acceleration stages, no integration. */
+int avsim_forward(avsim_batch *b);
+
+int avsim_get(avsim_batch *b, int field, void *dst_dev);
+int avsim_set(avsim_batch *b, int field, const void *src_dev);
+
+/* host-buffer convenience path used by the gym-facing wrapper (e2e metric): copies happen inside the call. */
+int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host);
+
+/* number of kernel launches issued by this batch so far (bench.py's gpu_launches) */
+int64_t avsim_launch_count(const avsim_batch *b);
+
+/* ---- IK controllers (reference data_collection_scripts/diff_ik.py:51-90, grad_ik.py:8-99).
+ * arm: 0 left, 1 right, 2 middle.  q/pos/quat_wxyz/q_out are device f32 arrays of n rows. */
+typedef struct {
+    float k_pos, k_ori, damping, max_angvel, integration_dt;
+    float k_null[7], q0[7];
+    int iterations;
+} avsim_diffik_params;
+typedef struct {
+    float step_size, min_cost_delta, position_weight, rotation_weight, position_threshold, rotation_threshold,
+        max_pos_diff, max_rot_diff, joint_p;
+    float joint_center_weight[7], joint_displacement_weight[7];
+    int max_iterations;
+} avsim_gradik_params;
+int avsim_diffik(const avsim_model *m, int arm, const float *q_dev, const float *pos_dev, const float *quat_wxyz_dev,
+                 int n, const avsim_diffik_params *p, float *q_out_dev, void *stream);
+int avsim_gradik(const avsim_model *m, int arm, const float *q_dev, const float *pos_dev, const float *quat_wxyz_dev,
+                 int n, const avsim_gradik_params *p, float *q_out_dev, void *stream);
+/* product-of-exponentials forward kinematics of an arm's end-effector site (kinematics.py:7-26): out f32[n][16] */
+int avsim_fk(const avsim_model *m, int arm, const float *q_dev, int n, float *T_out_dev, void *stream);
+
+const char *avsim_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSIM_H */

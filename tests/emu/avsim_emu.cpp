@@ -1,0 +1,110 @@
+// avsim_emu.cpp -- TEST/DEBUG HARNESS ONLY (see cuda_emu.h): the step / forward / reset kernels of
+// av_aloha_b200/csrc compiled for the host and driven lane-by-lane through 32 cooperative fibers, exposed through
+// a tiny C interface that tests/test_emu_parity.py loads with ctypes.  It exists so the kernel *source* can be
+// checked against the oracle in the GPU-less build container; it is never loaded by the package.
+#include "cuda_emu.h"
+
+namespace emu {
+Warp W;
+dim3_emu g_blockIdx = {0, 0, 0}, g_gridDim = {1, 1, 1}, g_blockDim = {32, 1, 1};
+static void trampoline() {
+    W.body();
+    W.done[W.cur] = true;
+    swapcontext(&W.ctx[W.cur], &W.main);
+}
+void run_block(int block, int grid, const std::function<void()> &body) {
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 32; i++) W.stack[i] = (char *)malloc(1 << 20);
+        init = true;
+    }
+    g_blockIdx.x = block; g_gridDim.x = grid;
+    W.body = body; W.arrived = 0; W.gen = 0;
+    for (int i = 0; i < 32; i++) {
+        W.done[i] = false;
+        getcontext(&W.ctx[i]);
+        W.ctx[i].uc_stack.ss_sp = W.stack[i];
+        W.ctx[i].uc_stack.ss_size = 1 << 20;
+        W.ctx[i].uc_link = &W.main;
+        makecontext(&W.ctx[i], trampoline, 0);
+    }
+    for (;;) {
+        bool all = true;
+        for (int i = 0; i < 32; i++)
+            if (!W.done[i]) {
+                all = false;
+                W.cur = i;
+                swapcontext(&W.main, &W.ctx[i]);
+            }
+        if (all) break;
+    }
+}
+}  // namespace emu
+
+#include "../../av_aloha_b200/csrc/avsim_kernels.cuh"
+#include "../../av_aloha_b200/csrc/avsim_model_pack.h"
+
+float4 av_smem_raw[(sizeof(EnvS) + 15) / 16 + 1];
+
+struct EmuBatch {
+    avpack::PackedModel pk;
+    BatchState st;
+    std::vector<float> f[16];
+    std::vector<int> iv[8];
+};
+
+extern "C" {
+EmuBatch *emu_create(const char *path, int num_envs) {
+    EmuBatch *b = new EmuBatch();
+    if (!avpack::pack_model(path, b->pk)) { fprintf(stderr, "emu_create: %s\n", b->pk.error.c_str()); delete b; return nullptr; }
+    b->pk.relocate(b->pk.P.fdata.data(), b->pk.P.idata.data(), b->pk.hull4.data());
+    const DevModel &d = b->pk.dm;
+    BatchState &s = b->st;
+    memset(&s, 0, sizeof s);
+    size_t B = num_envs;
+    s.num_envs = num_envs; s.seed = 1234; s.solver_iters = 50; s.noslip_iters = d.noslip_iterations; s.multiccd = d.multiccd;
+    auto F = [&](int k, size_t n) { b->f[k].assign(n, 0.f); return b->f[k].data(); };
+    auto I = [&](int k, size_t n) { b->iv[k].assign(n, 0); return b->iv[k].data(); };
+    s.qpos = F(0, B * d.nq); s.qvel = F(1, B * d.nv); s.ctrl = F(2, B * d.nu); s.warm = F(3, B * d.nv);
+    s.agent_pos = F(4, B * d.nj_obs); s.contacts = F(5, B * AV_NCON * 16); s.qacc = F(6, B * d.nv);
+    s.xpos = F(7, B * 3 * d.nbody); s.qfrc_bias = F(8, B * d.nv); s.qacc_smooth = F(9, B * d.nv);
+    s.mass_diag = F(10, B * d.nv); s.scratch = F(11, B * AV_SCRATCH_FLOATS);
+    s.reward = I(0, B); s.status = I(1, B); s.latch = I(2, B); s.ncon = I(3, B); s.episode = I(4, B);
+    return b;
+}
+void emu_destroy(EmuBatch *b) { delete b; }
+void emu_set_options(EmuBatch *b, int iters, int noslip, int multiccd) {
+    b->st.solver_iters = iters;
+    b->st.noslip_iters = noslip >= 0 ? noslip : b->pk.dm.noslip_iterations;
+    b->st.multiccd = multiccd >= 0 ? multiccd : b->pk.dm.multiccd;
+}
+int emu_dim(EmuBatch *b, int what) {
+    const DevModel &d = b->pk.dm;
+    switch (what) { case 0: return d.nq; case 1: return d.nv; case 2: return d.nu; case 3: return d.nbody; case 4: return d.nj_obs; case 5: return d.nfree; }
+    return -1;
+}
+float *emu_f(EmuBatch *b, int k) {
+    BatchState &s = b->st;
+    float *p[] = {s.qpos, s.qvel, s.ctrl, s.warm, s.agent_pos, s.contacts, s.qacc, s.xpos, s.qfrc_bias, s.qacc_smooth, s.mass_diag};
+    return p[k];
+}
+int *emu_i(EmuBatch *b, int k) {
+    BatchState &s = b->st;
+    int *p[] = {s.reward, s.status, s.latch, s.ncon, s.episode};
+    return p[k];
+}
+void emu_forward(EmuBatch *b) {
+    for (int e = 0; e < b->st.num_envs; e++)
+        emu::run_block(e, b->st.num_envs, [&]() { avsim_forward_kernel(b->pk.dm, b->st); });
+}
+void emu_step(EmuBatch *b, const float *action, int nsub) {
+    for (int e = 0; e < b->st.num_envs; e++)
+        emu::run_block(e, b->st.num_envs, [&]() { avsim_step_kernel(b->pk.dm, b->st, action, nsub); });
+}
+void emu_reset(EmuBatch *b, const float *free_pos) {
+    int nb = (b->st.num_envs + 31) / 32;
+    for (int blk = 0; blk < nb; blk++)
+        emu::run_block(blk, nb, [&]() { avsim_reset_kernel(b->pk.dm, b->st, nullptr, free_pos, AV_HOME); });
+    emu_forward(b);
+}
+}

@@ -1,0 +1,85 @@
+"""ctypes front end of the warp-emulation debug harness (tests only; see cuda_emu.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "..", "..", "av_aloha_b200", "csrc")
+_LIB = os.path.join(_HERE, "libavsim_emu.so")
+
+
+def build():
+    srcs = [os.path.join(_HERE, f) for f in ("avsim_emu.cpp", "cuda_emu.h")] + [
+        os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-o", _LIB,
+                               os.path.join(_HERE, "avsim_emu.cpp")])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emu_create.restype = C.c_void_p
+        _lib.emu_create.argtypes = [C.c_char_p, C.c_int]
+        _lib.emu_destroy.argtypes = [C.c_void_p]
+        _lib.emu_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.emu_dim.argtypes = [C.c_void_p, C.c_int]
+        _lib.emu_f.restype = C.POINTER(C.c_float)
+        _lib.emu_f.argtypes = [C.c_void_p, C.c_int]
+        _lib.emu_i.restype = C.POINTER(C.c_int)
+        _lib.emu_i.argtypes = [C.c_void_p, C.c_int]
+        _lib.emu_forward.argtypes = [C.c_void_p]
+        _lib.emu_step.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+        _lib.emu_reset.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    return _lib
+
+
+_F = dict(qpos=0, qvel=1, ctrl=2, warm=3, agent_pos=4, contacts=5, qacc=6, xpos=7, qfrc_bias=8, qacc_smooth=9,
+          mass_diag=10)
+_I = dict(reward=0, status=1, latch=2, ncon=3, episode=4)
+
+
+class EmuBatch:
+    def __init__(self, path, num_envs=1):
+        self.ptr = lib().emu_create(path.encode(), num_envs)
+        assert self.ptr
+        self.B = num_envs
+        d = lambda k: lib().emu_dim(self.ptr, k)
+        self.nq, self.nv, self.nu, self.nbody, self.nj, self.nfree = (d(k) for k in range(6))
+        self._w = dict(qpos=self.nq, qvel=self.nv, ctrl=self.nu, warm=self.nv, agent_pos=self.nj, contacts=40 * 16,
+                       qacc=self.nv, xpos=3 * self.nbody, qfrc_bias=self.nv, qacc_smooth=self.nv, mass_diag=self.nv)
+
+    def __getattr__(self, name):
+        if name in _F:
+            p = lib().emu_f(self.ptr, _F[name])
+            return np.ctypeslib.as_array(p, shape=(self.B, self._w[name]))
+        if name in _I:
+            p = lib().emu_i(self.ptr, _I[name])
+            return np.ctypeslib.as_array(p, shape=(self.B,))
+        raise AttributeError(name)
+
+    def set_options(self, iters=50, noslip=-1, multiccd=-1):
+        lib().emu_set_options(self.ptr, iters, noslip, multiccd)
+
+    def forward(self):
+        lib().emu_forward(self.ptr)
+
+    def step(self, action, nsub=20):
+        a = np.ascontiguousarray(action, dtype=np.float32)
+        lib().emu_step(self.ptr, a.ctypes.data_as(C.POINTER(C.c_float)), nsub)
+
+    def reset(self, free_pos=None):
+        fp = None
+        if free_pos is not None:
+            self._fp = np.ascontiguousarray(free_pos, dtype=np.float32)
+            fp = self._fp.ctypes.data_as(C.POINTER(C.c_float))
+        lib().emu_reset(self.ptr, fp)

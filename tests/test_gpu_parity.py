@@ -1,0 +1,106 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the fp64 CPU oracle on identical qpos/qvel/ctrl.
+
+Tolerances (stated here as the contract):
+  one forward pass, contact-free : |dqacc|inf <= 1e-4 * max(1, |qacc|inf)
+  one forward pass, with contacts: |dqacc|inf <= 1e-2 * max(1, |qacc|inf), identical contact geom pairs
+  one env step (20 substeps)     : |dqpos|inf <= 1e-4
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HOME = np.array([0, -0.082, 1.06, 0, -0.953, 0, 0.02239] * 2 + [0, -0.8, 0.8, 0, 0.5, 0, 0])
+
+
+def _hold_action(nj):
+    a = HOME[:nj].copy()
+    a[6] = 1.0
+    a[13] = 1.0
+    return a
+
+
+@pytest.fixture(scope="module")
+def setup(slot_model_path):
+    import torch
+    from av_aloha_b200 import capi
+    from oracle.oracle import OracleEnv, OracleModel
+
+    model = capi.Model(slot_model_path, 0)
+    om = OracleModel(slot_model_path)
+    return torch, capi, model, om, OracleEnv
+
+
+def test_forward_contact_free(setup):
+    torch, capi, model, om, OracleEnv = setup
+    B = 8
+    rng = np.random.default_rng(0)
+    batch = capi.Batch(model, B, seed=1)
+    fp = np.stack([np.array([[rng.uniform(-0.05, 0.05), rng.uniform(0.1, 0.15), 0.0],
+                             [rng.uniform(-0.08, 0.08), rng.uniform(-0.1, 0.0), 0.0]]) for _ in range(B)])
+    batch.reset(free_pos=fp)
+    qpos = batch.get(capi.QPOS).cpu().numpy().astype(np.float64)
+    qvel = rng.normal(0, 0.3, size=(B, model.nv))
+    qpos[:, :23] += rng.normal(0, 0.05, size=(B, 23))
+    batch.set(capi.QPOS, qpos.astype(np.float32))
+    batch.set(capi.QVEL, qvel.astype(np.float32))
+    batch.forward()
+    qacc = batch.get(capi.QACC).cpu().numpy()
+    bias = batch.get(capi.QFRC_BIAS).cpu().numpy()
+    ncon = batch.get(capi.NCON).cpu().numpy()
+    qpos32 = batch.get(capi.QPOS).cpu().numpy()
+    qvel32 = batch.get(capi.QVEL).cpu().numpy()
+    for e in range(B):
+        o = OracleEnv(om)
+        o.reset(free_pos=fp[e])
+        o.qpos[:] = qpos32[e]
+        o.qvel[:] = qvel32[e]
+        o.forward()
+        if o.ncon or ncon[e]:
+            continue
+        scale = max(1.0, np.abs(o.qacc).max())
+        assert np.abs(bias[e] - o.qfrc_bias).max() <= 1e-4 * max(1.0, np.abs(o.qfrc_bias).max())
+        assert np.abs(qacc[e] - o.qacc).max() <= 1e-4 * scale
+    batch.close()
+
+
+def test_env_steps_resting_contacts(setup):
+    torch, capi, model, om, OracleEnv = setup
+    B = 4
+    batch = capi.Batch(model, B, seed=1)
+    batch.set_options(solver_iters=50)
+    fp = np.array([[[0.01 * e, 0.12, 0.0], [0.02, -0.05 + 0.01 * e, 0.0]] for e in range(B)])
+    batch.reset(free_pos=fp)
+    act = np.tile(_hold_action(model.njoints), (B, 1)).astype(np.float32)
+    act_dev = torch.as_tensor(act, device="cuda")
+    envs = []
+    for e in range(B):
+        o = OracleEnv(om)
+        o.reset(free_pos=fp[e])
+        envs.append(o)
+    for step in range(3):
+        batch.step(act_dev)
+        qpos = batch.get(capi.QPOS).cpu().numpy()
+        ncon = batch.get(capi.NCON).cpu().numpy()
+        rew = batch.get(capi.REWARD).cpu().numpy()
+        status = batch.get(capi.STATUS).cpu().numpy()
+        assert (status == 0).all()
+        for e in range(B):
+            r = envs[e].step(act[e].astype(np.float64))
+            assert np.abs(qpos[e] - envs[e].qpos).max() <= 1e-4, (step, e)
+            assert ncon[e] == envs[e].ncon
+            assert rew[e] == r
+    batch.close()
+
+
+def test_step_host_path(setup):
+    torch, capi, model, om, OracleEnv = setup
+    B = 16
+    batch = capi.Batch(model, B, seed=3)
+    act = np.tile(_hold_action(model.njoints), (B, 1)).astype(np.float32)
+    agent, rew = batch.step_host(act)
+    assert agent.shape == (B, model.njoints) and rew.shape == (B,)
+    assert np.isfinite(agent).all()
+    assert np.abs(agent - act).max() < 0.1
+    assert batch.launch_count >= 3
+    batch.close()
