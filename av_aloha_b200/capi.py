@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libavsim.so")
+LIB_PATH = os.environ.get("AVSIM_LIB") or os.path.join(_HERE, "csrc", "libavsim.so")   # AVSIM_LIB: diagnostics build
 
 # avsim_field
 QPOS, QVEL, CTRL, WARMSTART, AGENT_POS, REWARD, SUCCESS, NCON, CONTACTS, STATUS, LATCH, QACC, XPOS, QFRC_BIAS, \
@@ -22,7 +22,7 @@ MAX_CONTACTS = 40
 SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
-    "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error",
+    "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles",
 ]
 
 
@@ -69,6 +69,7 @@ def load_library():
     L.avsim_gradik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(GradIKParams), vp, vp]
     L.avsim_fk.argtypes = [vp, i32, vp, i32, vp, vp]
     L.avsim_last_error.restype = cp
+    L.avsim_stage_cycles.argtypes = [vp, i32, i32]
     _lib = L
     return L
 

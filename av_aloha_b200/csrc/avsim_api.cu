@@ -276,6 +276,20 @@ extern "C" int avsim_step_host(avsim_batch *b, const float *action_host, int nsu
     return AVSIM_OK;
 }
 
+extern "C" int avsim_stage_cycles(uint64_t *out_host, int n, int reset) {
+#ifdef AVSIM_PROFILE
+    unsigned long long h[PF_N] = {0};
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(h, g_prof, sizeof h));
+    for (int k = 0; k < n && k < PF_N; k++) out_host[k] = h[k];
+    if (reset) { unsigned long long z[PF_N] = {0}; CU(cudaMemcpyToSymbol(g_prof, z, sizeof z)); }
+    return PF_N;
+#else
+    (void)out_host; (void)n; (void)reset;
+    return fail(AVSIM_ERR_ARG, "avsim_stage_cycles: library built without -DAVSIM_PROFILE");
+#endif
+}
+
 extern "C" int64_t avsim_launch_count(const avsim_batch *b) { return b ? b->launches : 0; }
 
 // ------------------------------------------------------------------ IK entry points

@@ -33,6 +33,7 @@ struct DevModel {
     float timestep, impratio, gravity[3];
     // bodies
     const int *body_parent, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_tree, *body_lastdof;
+    const int *body_treemask;   // bit k: the tree-local dof k moves this body
     const float *body_pos, *body_quat, *body_mass, *body_ipos, *body_inertia, *body_invweight0;
     const float *body_xpos0, *body_xquat0;   // world pose at qpos0 (exact for world-welded bodies)
     // trees (bodies and dofs of a tree are contiguous)
@@ -77,6 +78,6 @@ struct BatchState {
     int solver_iters, noslip_iters, multiccd;
 };
 
-// per-contact solver block in global scratch: J[6][16], MinvJT[6][16], AR (21, packed lower), Ainv (15, packed)
-#define AV_CBLK (6 * AV_JW * 2 + 21 + 15)
+// per-contact solver block in global scratch (avsim_solve.cuh): AR 21 | Lc 15 | b 6 | R 4 | mu 3 | 1/mu 3 | J[6][16]
+#define AV_CBLK (52 + 6 * AV_JW)
 #define AV_SCRATCH_FLOATS (AV_NCON * AV_CBLK)

@@ -23,6 +23,8 @@ __device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S,
             st3(S.gpos + 3 * g, ld3(m.geom_xpos0 + 3 * g));
             st3(S.gaabb + 3 * g, ld3(m.geom_xaabb0 + 3 * g));
         }
+    // padding of the per-tree 8x8 blocks must be finite: block_apply multiplies it by exact zeros
+    for (int i = lane; i < AV_MBLK; i += 32) { S.Minv[i] = 0.f; S.L[i] = 0.f; }
     if (lane == 0) { S.status = 0; S.ncon = 0; S.nsc = 0; }
     __syncwarp();
 }
@@ -32,14 +34,20 @@ __device__ inline void env_store(const DevModel &m, const BatchState &B, EnvS &S
     for (int i = lane; i < m.nu; i += 32) B.ctrl[(size_t)env * m.nu + i] = S.ctrl[i];
 }
 
-__device__ inline void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane) {
+__device__ inline void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf) {
     stage_kinematics(m, S, lane);
+    pf.mark(PF_KIN, lane);
     stage_inertia(m, S, lane);
-    stage_collision(m, S, lane, B.multiccd != 0);
+    pf.mark(PF_INERTIA, lane);
+    stage_collision(m, S, lane, B.multiccd != 0, pf);
     stage_smooth(m, S, lane);
+    pf.mark(PF_SMOOTH, lane);
     stage_rows_scalar(m, S, lane);
+    pf.mark(PF_ROWS_S, lane);
     stage_rows_contact(m, S, scratch, lane);
+    pf.mark(PF_ROWS_C, lane);
     stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters);
+    pf.mark(PF_SOLVE, lane);
 }
 
 __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane, bool with_reward) {
@@ -74,11 +82,14 @@ __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS 
 }
 
 // env.step: ctrl write (reference env.py:204-215), nsub x mj_step (env.py:218), trailing position pass, reward
-__global__ void __launch_bounds__(32) avsim_step_kernel(DevModel m, BatchState B, const float *__restrict__ action, int nsub) {
+__global__ void __launch_bounds__(32) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B, const float *__restrict__ action, int nsub) {
     EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
     int lane = threadIdx.x;
+    Prof pf;
     for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
+        pf.start();
         env_load(m, B, S, env, lane);
+        pf.mark(PF_LOAD, lane);
         if (action && lane < m.nj_obs) {
             float a = action[(size_t)env * m.nj_obs + lane];
             if (lane == 6 || lane == 13) a = a * (m.act_ctrl_hi[lane] - m.act_ctrl_lo[lane]) + m.act_ctrl_lo[lane];
@@ -87,25 +98,30 @@ __global__ void __launch_bounds__(32) avsim_step_kernel(DevModel m, BatchState B
         __syncwarp();
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
         for (int s = 0; s < nsub; s++) {
-            env_forward(m, B, S, scratch, lane);
+            env_forward(m, B, S, scratch, lane, pf);
             stage_integrate(m, S, lane);
+            pf.mark(PF_INTEGRATE, lane);
         }
         stage_kinematics(m, S, lane);
-        stage_collision(m, S, lane, B.multiccd != 0);
+        pf.mark(PF_KIN, lane);
+        stage_collision(m, S, lane, B.multiccd != 0, pf);
         env_store(m, B, S, env, lane);
         env_outputs(m, B, S, env, lane, true);
+        pf.mark(PF_OUT, lane);
         __syncwarp();
     }
 }
 
 // physics.forward(): all stages, no integration; dumps stage outputs for the parity tests
-__global__ void __launch_bounds__(32) avsim_forward_kernel(DevModel m, BatchState B) {
+__global__ void __launch_bounds__(32) avsim_forward_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B) {
     EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
     int lane = threadIdx.x;
     for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
+        Prof pf;
+        pf.start();
         env_load(m, B, S, env, lane);
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
-        env_forward(m, B, S, scratch, lane);
+        env_forward(m, B, S, scratch, lane, pf);
         for (int i = lane; i < m.nv; i += 32) {
             B.qacc[(size_t)env * m.nv + i] = S.qacc_smooth[i] + S.acc[i];
             B.qacc_smooth[(size_t)env * m.nv + i] = S.qacc_smooth[i];

@@ -152,6 +152,11 @@ inline bool pack_model(const char *avm_path, PackedModel &out) {
     }
     for (int t = 0; t < ntree; t++)
         if (tdn[t] > AV_TD || ntree > AV_NTREE) { out.error = "kinematic tree too large"; return false; }
+    auto dof_parent_v = a.i("dof_parent");
+    std::vector<int> treemask(d.nbody, 0);
+    for (int b = 1; b < d.nbody; b++)
+        if (body_tree[b] >= 0)
+            for (int i = lastdof[b]; i >= 0; i = dof_parent_v[i]) treemask[b] |= 1 << (i - td0[body_tree[b]]);
     // static world poses (exact for world-welded bodies; compile-time pose otherwise)
     auto bpos = a.d("body_pos"), bquat = a.d("body_quat");
     std::vector<double> xpos(3 * d.nbody, 0.0), xquat(4 * d.nbody, 0.0);
@@ -210,7 +215,7 @@ inline bool pack_model(const char *avm_path, PackedModel &out) {
 #define PI(field, name) P.addi(&d.field, a.i(name))
     PI(body_parent, "body_parent"); PI(body_jntadr, "body_jntadr"); PI(body_jntnum, "body_jntnum");
     PI(body_dofadr, "body_dofadr"); PI(body_dofnum, "body_dofnum"); PI(body_tree, "body_tree");
-    P.addi(&d.body_lastdof, lastdof);
+    P.addi(&d.body_lastdof, lastdof); P.addi(&d.body_treemask, treemask);
     PF(body_pos, "body_pos"); PF(body_quat, "body_quat"); PF(body_mass, "body_mass"); PF(body_ipos, "body_ipos");
     PF(body_inertia, "body_inertia"); PF(body_invweight0, "body_invweight0");
     P.addf(&d.body_xpos0, xposf); P.addf(&d.body_xquat0, xquatf);

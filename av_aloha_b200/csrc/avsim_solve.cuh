@@ -1,0 +1,476 @@
+// avsim_solve.cuh -- K5 (contact rows) and K6 (block projected Gauss-Seidel on the dual + noslip), one warp per env.
+//
+// Replaces mj_makeConstraint's contact rows and the constraint solve that `physics.step` (reference env.py:218) runs
+// inside MuJoCo [third-party; semantics per SURVEY.md Appendix A]: elliptic cones, impratio, soft-constraint
+// reference acceleration, warm start from the previous qacc, then `noslip_iterations` sweeps on the unregularised
+// friction rows.  Same statement as oracle/avsim_oracle.c stage_constraint_rows / stage_solve, fp32.
+//
+// Data layout.  Per contact one 592-byte block in a per-environment global scratch (read-only during the sweeps, so it
+// lives in L1): [AR 21 | Lc 15 | b 6 | Rn Rf Rt Rr | mu0 mu1 mu2 | 1/mu0 1/mu1 1/mu2] = 13 float4, then J[6][16]
+// (8 dof columns of tree 1 | 8 of tree 2).  Cholesky factors keep the RECIPROCAL of their diagonal, so the triangular
+// solves of the sweeps are multiply-only (one MUFU.RSQ per pivot when factoring, none when solving).  The mutable parts -- the force f[6] per contact and the constraint acceleration acc[nv] -- stay in
+// shared memory.  M^-1 J^T is NOT stored: an update applies  acc += Minv_tree (J^T df)  with the 8x8 block inverses
+// that are already in shared memory (4 shuffles + 4 FMAs per lane), halving the block traffic.
+// Everything below indexes its register arrays with compile-time constants only (all loops fully unrolled at the
+// fixed sizes 6 / 5; a condim-3 contact carries three dead rows with J = 0, b = 0 and a unit diagonal), so nothing
+// spills to local memory.  Lane roles: lane = (half = lane >> 4 -> rows 3*half..3*half+2, col = lane & 15).
+#pragma once
+
+#define AV_CB_AR 0
+#define AV_CB_LC 21
+#define AV_CB_B 36
+#define AV_CB_PAR 42
+#define AV_CB_J 52
+// AV_CBLK (avsim_dev.h) = 52 + 6 * AV_JW = 148 floats
+
+#define TRI(i, j) ((i) >= (j) ? (i) * ((i) + 1) / 2 + (j) : (j) * ((j) + 1) / 2 + (i))
+
+// packed tree descriptor of a contact: dofadr1 | n1 << 6 | dofadr2 << 10 | n2 << 16 | tree1 << 20 | tree2 << 23
+__device__ __forceinline__ int tr_pack(const DevModel &m, int t1, int t2) {
+    int v = 0;
+    if (t1 >= 0) v |= m.tree_dofadr[t1] | (m.tree_dofnum[t1] << 6) | (t1 << 20);
+    if (t2 >= 0) v |= (m.tree_dofadr[t2] << 10) | (m.tree_dofnum[t2] << 16) | (t2 << 23);
+    return v;
+}
+__device__ __forceinline__ int tr_dof(int tr, int col) {   // dof of this lane's column, -1 when the column is empty
+    int sh = (col & 8) ? 10 : 0, base = (tr >> sh) & 63, n = (tr >> (sh + 6)) & 15, dl = col & 7;
+    return dl < n ? base + dl : -1;
+}
+__device__ __forceinline__ int tr_tree(int tr, int col) { return (tr >> ((col & 8) ? 23 : 20)) & 7; }
+
+// sum of three per-lane values over the 16 lanes of a half-warp; every lane of the half gets the sums
+__device__ __forceinline__ void half_sum3(float &r0, float &r1, float &r2) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(AV_FULL, r0, o);
+        r1 += __shfl_xor_sync(AV_FULL, r1, o);
+        r2 += __shfl_xor_sync(AV_FULL, r2, o);
+    }
+}
+// J (this lane's three rows j0..j2 at its column) times a joint-space vector x (already gathered per column):
+// all six row results in every lane
+__device__ __forceinline__ void block_rows(float j0, float j1, float j2, float x, int half, float (&res)[6]) {
+    float r0 = j0 * x, r1 = j1 * x, r2 = j2 * x;
+    half_sum3(r0, r1, r2);
+    float o0 = __shfl_xor_sync(AV_FULL, r0, 16), o1 = __shfl_xor_sync(AV_FULL, r1, 16), o2 = __shfl_xor_sync(AV_FULL, r2, 16);
+    res[0] = half ? o0 : r0; res[1] = half ? o1 : r1; res[2] = half ? o2 : r2;
+    res[3] = half ? r0 : o0; res[4] = half ? r1 : o1; res[5] = half ? r2 : o2;
+}
+// acc += Minv_tree (J^T df) for this contact
+__device__ __forceinline__ void block_apply(EnvS &S, float j0, float j1, float j2, const float (&df)[6], int tr, int lane) {
+    int col = lane & 15, half = lane >> 4, dl = col & 7;
+    float t = half ? (j0 * df[3] + j1 * df[4] + j2 * df[5]) : (j0 * df[0] + j1 * df[1] + j2 * df[2]);
+    t += __shfl_xor_sync(AV_FULL, t, 16);            // (J^T df)[col], both halves
+    const float *Mi = S.Minv + tr_tree(tr, col) * (AV_TD * AV_TD) + dl * AV_TD + 4 * half;
+    float da = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) da += Mi[k] * __shfl_sync(AV_FULL, t, (col & 8) + 4 * half + k, 16);
+    da += __shfl_xor_sync(AV_FULL, da, 16);
+    int dof = tr_dof(tr, col);
+    if (half == 0 && dof >= 0) S.acc[dof] += da;
+}
+
+struct CBlk {   // the uniform (per-contact) part of a block, in registers
+    float AR[21], Lc[15], b[6], R[6], mu[5], imu[5];
+};
+__device__ __forceinline__ void cblk_load(const float *blk, CBlk &c) {
+    const float4 *p = reinterpret_cast<const float4 *>(blk);
+    float v[52];
+#pragma unroll
+    for (int i = 0; i < 13; i++) {
+        float4 q = p[i];
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 21; i++) c.AR[i] = v[AV_CB_AR + i];
+#pragma unroll
+    for (int i = 0; i < 15; i++) c.Lc[i] = v[AV_CB_LC + i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) c.b[i] = v[AV_CB_B + i];
+    c.R[0] = v[AV_CB_PAR]; c.R[1] = c.R[2] = v[AV_CB_PAR + 1]; c.R[3] = v[AV_CB_PAR + 2]; c.R[4] = c.R[5] = v[AV_CB_PAR + 3];
+    c.mu[0] = c.mu[1] = v[AV_CB_PAR + 4]; c.mu[2] = v[AV_CB_PAR + 5]; c.mu[3] = c.mu[4] = v[AV_CB_PAR + 6];
+    c.imu[0] = c.imu[1] = v[AV_CB_PAR + 7]; c.imu[2] = v[AV_CB_PAR + 8]; c.imu[3] = c.imu[4] = v[AV_CB_PAR + 9];
+}
+
+// ---- 5x5 helpers on packed lower triangles, compile-time indices only.  L holds 1/L_ii on its diagonal.
+__device__ __forceinline__ void chol5(const float (&A)[15], float lam, float (&L)[15]) {
+#pragma unroll
+    for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            float s = A[TRI(i, j)] + (i == j ? lam : 0.f);
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= L[TRI(i, k)] * L[TRI(j, k)];
+            L[TRI(i, j)] = (i == j) ? rsqrtf(fmaxf(s, AV_MINVAL)) : s * L[TRI(j, j)];
+        }
+}
+// solve L L^T x = -b
+__device__ __forceinline__ void trisolve5(const float (&L)[15], const float (&b)[5], float (&x)[5]) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        float s = -b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= L[TRI(i, k)] * x[k];
+        x[i] = s * L[TRI(i, i)];
+    }
+#pragma unroll
+    for (int i = 4; i >= 0; i--) {
+        float s = x[i];
+#pragma unroll
+        for (int k = i + 1; k < 5; k++) s -= L[TRI(k, i)] * x[k];
+        x[i] = s * L[TRI(i, i)];
+    }
+}
+// minimise 0.5 y'Ay + y'b  s.t.  sum (y_i/mu_i)^2 <= r^2  (A packed lower 5x5).  L0 = Cholesky factor of A when
+// have_L0, otherwise it is computed here.  `lam` carries the multiplier of the previous sweep for this contact:
+// the local problems barely change from sweep to sweep, so the Newton iteration on |z(lam)| = r restarts next to its root.
+__device__ __forceinline__ void qcqp5(const float (&A)[15], const float (&b)[5], const float (&mu)[5], const float (&imu)[5],
+                                      float r, const float (&L0)[15], bool have_L0, float &lam, float (&y)[5]) {
+    float L[15];
+    if (have_L0) {
+#pragma unroll
+        for (int i = 0; i < 15; i++) L[i] = L0[i];
+    } else
+        chol5(A, 0.f, L);
+    trisolve5(L, b, y);
+    float zz = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; i++) zz += (y[i] * imu[i]) * (y[i] * imu[i]);
+    if (zz <= r * r) { lam = 0.f; return; }
+    // scaled problem z = y / mu; Newton on the multiplier of |z| = r
+    float As[15], bs[5], z[5], w[5], mz[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        bs[i] = b[i] * mu[i];
+#pragma unroll
+        for (int j = 0; j <= i; j++) As[TRI(i, j)] = A[TRI(i, j)] * mu[i] * mu[j];
+    }
+    float ir = 1.0f / r;
+    for (int it = 0; it < 12; it++) {
+        chol5(As, lam, L);
+        trisolve5(L, bs, z);
+        zz = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; i++) { zz += z[i] * z[i]; mz[i] = -z[i]; }
+        if (fabsf(zz - r * r) < 1e-6f * fmaxf(1e-12f, r * r)) break;
+        trisolve5(L, mz, w);
+        float zw = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; i++) zw += z[i] * w[i];
+        float nz = sqrtf(zz);
+        lam = fmaxf(0.f, lam + (nz - r) * ir * zz / fmaxf(zw, AV_MINVAL));
+    }
+    if (zz > r * r) {
+        float s = r * rsqrtf(zz);
+#pragma unroll
+        for (int i = 0; i < 5; i++) z[i] *= s;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) y[i] = z[i] * mu[i];
+}
+
+// ------------------------------------------------------------------ K5: contact rows, one contact at a time
+__device__ inline void stage_rows_contact(const DevModel &m, EnvS &S, float *scratch, int lane) {
+    int col = lane & 15, half = lane >> 4;
+    for (int c = 0; c < S.ncon; c++) {
+        int info = S.c_info[c], g1 = info & 0xff, g2 = (info >> 8) & 0xff, dim = (info >> 16) & 0xf;
+        if ((info >> 20) & 1) continue;   // detected but outside margin - gap (pin geoms): no rows
+        int b1 = m.geom_body[g1], b2 = m.geom_body[g2];
+        int t1 = m.body_tree[b1], t2 = m.body_tree[b2];
+        if (t1 < 0) { t1 = t2; t2 = -1; }   // keep the first slot occupied; signs are handled per body below
+        if (t2 == t1) t2 = -1;
+        int tr = tr_pack(m, t1, t2);
+        int t = col < 8 ? t1 : t2, dl = col & 7, dof = tr_dof(tr, col);
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+        V3 p = ld3(S.c_pos + 3 * c);
+        V3 fn = ld3(S.c_frame + 9 * c), ft1 = ld3(S.c_frame + 9 * c + 3), ft2 = ld3(S.c_frame + 9 * c + 6);
+        if (dof >= 0) {
+            float sgn = 0.f;
+            if (m.body_tree[b2] == t && ((m.body_treemask[b2] >> dl) & 1)) sgn += 1.f;
+            if (m.body_tree[b1] == t && ((m.body_treemask[b1] >> dl) & 1)) sgn -= 1.f;
+            if (sgn != 0.f) {
+                S6 cd = ld6(S.cdof + 6 * dof);
+                V3 v = half == 0 ? cd.l + cross(cd.a, p - ld3(S.torig + 3 * t)) : cd.a;
+                v = v * sgn;
+                j0 = dot(fn, v); j1 = dot(ft1, v); j2 = dot(ft2, v);
+            }
+        }
+        if (half == 1 && dim < 6) { j0 = j1 = j2 = 0.f; }   // condim 3: no torsional / rolling rows
+        float *Js = S.stage, *MJs = S.stage + 6 * AV_JW;
+        Js[(3 * half + 0) * AV_JW + col] = j0; Js[(3 * half + 1) * AV_JW + col] = j1; Js[(3 * half + 2) * AV_JW + col] = j2;
+        __syncwarp();
+        // M^-1 J^T rows (only needed to form A = J M^-1 J^T here)
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        if (dof >= 0) {
+            const float *Mi = S.Minv + t * AV_TD * AV_TD + dl;  // column dl (symmetric)
+            int cb = col & 8;
+#pragma unroll
+            for (int k = 0; k < AV_TD; k++) {
+                float mv = Mi[k * AV_TD];
+                m0 += Js[(3 * half + 0) * AV_JW + cb + k] * mv;
+                m1 += Js[(3 * half + 1) * AV_JW + cb + k] * mv;
+                m2 += Js[(3 * half + 2) * AV_JW + cb + k] * mv;
+            }
+        }
+        MJs[(3 * half + 0) * AV_JW + col] = m0; MJs[(3 * half + 1) * AV_JW + col] = m1; MJs[(3 * half + 2) * AV_JW + col] = m2;
+        float *blk = scratch + c * AV_CBLK;
+        blk[AV_CB_J + (3 * half + 0) * AV_JW + col] = j0; blk[AV_CB_J + (3 * half + 1) * AV_JW + col] = j1;
+        blk[AV_CB_J + (3 * half + 2) * AV_JW + col] = j2;
+        // velocities / smooth accelerations / warm-start accelerations along the rows
+        float xv = dof >= 0 ? S.qvel[dof] : 0.f, xa = dof >= 0 ? S.qacc_smooth[dof] : 0.f, xw = dof >= 0 ? S.warm[dof] : 0.f;
+        float vv[6], aa[6], ww[6];
+        block_rows(j0, j1, j2, xv, half, vv);
+        block_rows(j0, j1, j2, xa, half, aa);
+        block_rows(j0, j1, j2, xw, half, ww);
+        __syncwarp();
+        // impedance, regularisation, reference acceleration (uniform)
+        float K, B, imp, solref[2], solimp[5];
+#pragma unroll
+        for (int k = 0; k < 2; k++) solref[k] = 0.5f * (m.geom_solref[2 * g1 + k] + m.geom_solref[2 * g2 + k]);
+#pragma unroll
+        for (int k = 0; k < 5; k++) solimp[k] = 0.5f * (m.geom_solimp[5 * g1 + k] + m.geom_solimp[5 * g2 + k]);
+        float dist = S.c_dist[c];
+        kbi(m, solref, solimp, dist, K, B, imp);
+        float Rn = fmaxf(AV_MINVAL, (1.f - imp) / imp * (m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2]));
+        float mu0 = S.c_mu[3 * c], mu1 = S.c_mu[3 * c + 1], mu2 = S.c_mu[3 * c + 2];
+        float Rf = Rn / m.impratio;
+        float R[6] = {Rn, Rf, Rf, Rf * mu0 * mu0 / (mu1 * mu1), Rf * mu0 * mu0 / (mu2 * mu2), Rf * mu0 * mu0 / (mu2 * mu2)};
+        if (lane < 6) {
+            // row = lane; select the row's values without dynamic register indexing
+            float v = 0.f, a = 0.f, w = 0.f, Rr = 1.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (k == lane) { v = vv[k]; a = aa[k]; w = ww[k]; Rr = R[k]; }
+            float aref = -B * v - (lane == 0 ? K * imp * dist : 0.f);
+            bool live = lane < dim;
+            blk[AV_CB_B + lane] = live ? a - aref : 0.f;
+            S.c_f[6 * c + lane] = live ? -(w - aref) / Rr : 0.f;
+        }
+        if (lane == 0) {
+            blk[AV_CB_PAR] = R[0]; blk[AV_CB_PAR + 1] = R[1]; blk[AV_CB_PAR + 2] = R[3]; blk[AV_CB_PAR + 3] = R[4];
+            blk[AV_CB_PAR + 4] = mu0; blk[AV_CB_PAR + 5] = mu1; blk[AV_CB_PAR + 6] = mu2;
+            blk[AV_CB_PAR + 7] = 1.0f / mu0; blk[AV_CB_PAR + 8] = 1.0f / mu1; blk[AV_CB_PAR + 9] = 1.0f / mu2;
+            S.c_tree[c] = tr;
+            S.c_lam[c] = 0.f;
+        }
+        // AR = J MinvJT^T + R, packed lower triangle (21 entries), lane = entry
+        if (lane < 21) {
+            int i = 0;
+            while ((i + 1) * (i + 2) / 2 <= lane) i++;
+            int j = lane - i * (i + 1) / 2;
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < AV_JW; k++) s += Js[i * AV_JW + k] * MJs[j * AV_JW + k];
+            if (i == j) {
+                float Rr = 1.f;   // dead rows get a unit diagonal
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                    if (k == i && k < dim) Rr = R[k];
+                s += Rr;
+            }
+            blk[AV_CB_AR + lane] = s;
+        }
+        __syncwarp();
+    }
+    // lane = contact: Cholesky factor of the regularised friction block (rows 1..5), packed lower (15);
+    // projection of the warm-start force onto the cone
+    for (int c = lane; c < S.ncon; c += 32) {
+        int info = S.c_info[c];
+        if ((info >> 20) & 1) continue;
+        float *blk = scratch + c * AV_CBLK;
+        float A[15], Lc[15];
+#pragma unroll
+        for (int i = 0; i < 5; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) A[TRI(i, j)] = blk[AV_CB_AR + TRI(i + 1, j + 1)];
+        chol5(A, 0.f, Lc);
+#pragma unroll
+        for (int k = 0; k < 15; k++) blk[AV_CB_LC + k] = Lc[k];
+        float *f = S.c_f + 6 * c;
+        if (f[0] <= 0.f) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) f[k] = 0.f;
+        } else {
+            float mu0 = S.c_mu[3 * c], mu1 = S.c_mu[3 * c + 1], mu2 = S.c_mu[3 * c + 2];
+            float mu[5] = {mu0, mu0, mu1, mu2, mu2};
+            float s = 0.f;
+#pragma unroll
+            for (int k = 1; k < 6; k++) s += (f[k] / mu[k - 1]) * (f[k] / mu[k - 1]);
+            if (s > f[0] * f[0]) {
+                float sc = f[0] * rsqrtf(s);
+#pragma unroll
+                for (int k = 1; k < 6; k++) f[k] *= sc;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ K6: block projected Gauss-Seidel + noslip
+// one block update in the regularised sweep: (a) ray update, (b) friction rows on the ellipsoid of radius f_n
+__device__ __forceinline__ void contact_update(const CBlk &cb, float (&res)[6], const float (&old)[6], float &lam, float (&f)[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) { res[k] += cb.b[k] + cb.R[k] * old[k]; f[k] = old[k]; }
+    if (old[0] < AV_MINVAL) {
+        f[0] = fmaxf(0.f, old[0] - __fdividef(res[0], cb.AR[0]));
+#pragma unroll
+        for (int k = 1; k < 6; k++) f[k] = 0.f;
+    } else {
+        float vAv = 0.f, vr = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            vr += old[k] * res[k];
+#pragma unroll
+            for (int l = 0; l < 6; l++) vAv += old[k] * cb.AR[TRI(k, l)] * old[l];
+        }
+        if (vAv > AV_MINVAL) {
+            float x = -__fdividef(vr, vAv);
+            if (old[0] + x * old[0] < 0.f) x = -1.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) f[k] = old[k] + x * old[k];
+        }
+    }
+    if (f[0] < AV_MINVAL) {
+#pragma unroll
+        for (int k = 1; k < 6; k++) f[k] = 0.f;
+    } else {
+        float Ac[15], bc[5], y[5];
+#pragma unroll
+        for (int k = 1; k < 6; k++) {
+            float s = res[k] + cb.AR[TRI(k, 0)] * (f[0] - old[0]);
+#pragma unroll
+            for (int l = 1; l < 6; l++) s -= cb.AR[TRI(k, l)] * old[l];
+            bc[k - 1] = s;
+#pragma unroll
+            for (int l = 1; l <= k; l++) Ac[TRI(k - 1, l - 1)] = cb.AR[TRI(k, l)];
+        }
+        qcqp5(Ac, bc, cb.mu, cb.imu, f[0], cb.Lc, true, lam, y);
+#pragma unroll
+        for (int k = 1; k < 6; k++) f[k] = y[k - 1];
+    }
+}
+// noslip: friction rows only, unregularised A, normal force fixed
+__device__ __forceinline__ void contact_noslip(const CBlk &cb, int dim, const float (&res)[6], const float (&old)[6], float &lam, float (&f)[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) f[k] = old[k];
+    if (old[0] < AV_MINVAL) {
+#pragma unroll
+        for (int k = 1; k < 6; k++) f[k] = 0.f;
+        return;
+    }
+    float Ac[15], bc[5], y[5];
+#pragma unroll
+    for (int k = 1; k < 6; k++) {
+        float s = res[k] + cb.b[k];
+#pragma unroll
+        for (int l = 1; l < 6; l++) {
+            float a = cb.AR[TRI(k, l)] - ((k == l && k < dim) ? cb.R[k] : 0.f);
+            if (l <= k) Ac[TRI(k - 1, l - 1)] = a;
+            s -= a * old[l];
+        }
+        bc[k - 1] = s;
+    }
+    qcqp5(Ac, bc, cb.mu, cb.imu, old[0], cb.Lc, false, lam, y);
+#pragma unroll
+    for (int k = 1; k < 6; k++) f[k] = y[k - 1];
+}
+
+__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters) {
+    int col = lane & 15, half = lane >> 4;
+    // acc <- M^-1 J^T f_warm  (constraint part of the acceleration); dual cost of the warm start
+    for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
+    __syncwarp();
+    for (int r = 0; r < S.nsc; r++) {
+        float f = S.sc_f[r];
+        int t = S.sc_tree[r];
+        if (lane < m.tree_dofnum[t]) S.acc[m.tree_dofadr[t] + lane] += S.sc_MJ[r * AV_TD + lane] * f;
+        __syncwarp();
+    }
+    for (int c = 0; c < S.ncon; c++) {
+        if ((S.c_info[c] >> 20) & 1) continue;
+        const float *J = scratch + c * AV_CBLK + AV_CB_J;
+        float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
+        float df[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) df[k] = S.c_f[6 * c + k];
+        block_apply(S, j0, j1, j2, df, S.c_tree[c], lane);
+        __syncwarp();
+    }
+    float cost = 0.f;
+    for (int r = 0; r < S.nsc; r++) {
+        float f = S.sc_f[r];
+        float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
+        cost += f * (0.5f * (ja + S.sc_R[r] * f) + S.sc_b[r]);
+    }
+    for (int c = 0; c < S.ncon; c++) {
+        if ((S.c_info[c] >> 20) & 1) continue;
+        const float *blk = scratch + c * AV_CBLK;
+        int tr = S.c_tree[c], dof = tr_dof(tr, col);
+        const float *J = blk + AV_CB_J;
+        float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
+        float res[6];
+        block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
+        CBlk cb;
+        cblk_load(blk, cb);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            float f = S.c_f[6 * c + k];   // dead rows: f = 0
+            cost += f * (0.5f * (res[k] + cb.R[k] * f) + cb.b[k]);
+        }
+    }
+    __syncwarp();
+    if (cost >= 0.f) {  // the warm start does not beat f = 0
+        for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
+        for (int i = lane; i < AV_NSC; i += 32) S.sc_f[i] = 0.f;
+        for (int i = lane; i < AV_NCON * 6; i += 32) S.c_f[i] = 0.f;
+        __syncwarp();
+    }
+    for (int it = 0; it < iters + noslip_iters; it++) {
+        bool noslip = it >= iters;
+        // scalar rows: every lane computes the (uniform) update, lanes < nt apply it
+        for (int r = 0; r < S.nsc; r++) {
+            bool floss = S.sc_lo[r] > -1e37f && S.sc_lo[r] < 0.f;
+            if (noslip && !floss) continue;
+            float f = S.sc_f[r], R = noslip ? 0.f : S.sc_R[r];
+            float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
+            float res = S.sc_b[r] + R * f + ja;
+            float x = fminf(fmaxf(f - res / (S.sc_A[r] + R), S.sc_lo[r]), S.sc_hi[r]);
+            float df = x - f;
+            __syncwarp();
+            int t = S.sc_tree[r];
+            if (lane < m.tree_dofnum[t]) S.acc[m.tree_dofadr[t] + lane] += S.sc_MJ[r * AV_TD + lane] * df;
+            if (lane == 0) S.sc_f[r] = x;
+            __syncwarp();
+        }
+        for (int c = 0; c < S.ncon; c++) {
+            int info = S.c_info[c], dim = (info >> 16) & 0xf;
+            if ((info >> 20) & 1) continue;
+            const float *blk = scratch + c * AV_CBLK;
+            int tr = S.c_tree[c], dof = tr_dof(tr, col);
+            const float *J = blk + AV_CB_J;
+            float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
+            CBlk cb;
+            cblk_load(blk, cb);
+            float res[6], old[6], f[6], df[6];
+            block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
+#pragma unroll
+            for (int k = 0; k < 6; k++) old[k] = S.c_f[6 * c + k];
+            float lam = S.c_lam[c];
+            if (!noslip) contact_update(cb, res, old, lam, f);
+            else contact_noslip(cb, dim, res, old, lam, f);
+#pragma unroll
+            for (int k = 0; k < 6; k++) df[k] = f[k] - old[k];
+            __syncwarp();
+            block_apply(S, j0, j1, j2, df, tr, lane);
+            if (lane < 6) {
+                float fv = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                    if (k == lane) fv = f[k];
+                S.c_f[6 * c + lane] = fv;
+            }
+            if (lane == 6) S.c_lam[c] = lam;
+            __syncwarp();
+        }
+    }
+}

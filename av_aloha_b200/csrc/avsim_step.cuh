@@ -13,6 +13,27 @@
 #pragma once
 #include "avsim_collide.cuh"
 
+// ---- optional per-stage cycle counters (-DAVSIM_PROFILE; read back with avsim_stage_cycles)
+enum { PF_LOAD = 0, PF_KIN, PF_INERTIA, PF_BROAD, PF_PRIM, PF_CONVEX, PF_SMOOTH, PF_ROWS_S, PF_ROWS_C, PF_SOLVE, PF_INTEGRATE,
+       PF_OUT, PF_N };
+#ifdef AVSIM_PROFILE
+__device__ unsigned long long g_prof[PF_N];
+struct Prof {
+    long long t;
+    __device__ __forceinline__ void start() { t = clock64(); }
+    __device__ __forceinline__ void mark(int k, int lane) {
+        long long n = clock64();
+        if (lane == 0) atomicAdd(&g_prof[k], (unsigned long long)(n - t));
+        t = n;
+    }
+};
+#else
+struct Prof {
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void mark(int, int) {}
+};
+#endif
+
 struct EnvS {
     float qpos[AV_NQ], qvel[AV_NVP], ctrl[24], warm[AV_NVP];
     float xpos[AV_NB * 3], xquat[AV_NB * 4], xmat[AV_NB * 9], xipos[AV_NB * 3];
@@ -25,15 +46,14 @@ struct EnvS {
     float qfrc_smooth[AV_NVP], qacc_smooth[AV_NVP], acc[AV_NVP], qfrc_bias[AV_NVP];
     float gpos[AV_NG * 3], gaabb[AV_NG * 3];  // world centre + world-axis half extents of every geom
     // contacts
-    float c_pos[AV_NCON * 3], c_frame[AV_NCON * 9], c_dist[AV_NCON], c_mu[AV_NCON * 3], c_b[AV_NCON * 6],
-        c_f[AV_NCON * 6], c_Rn[AV_NCON], c_aref[AV_NCON * 6];
+    float c_pos[AV_NCON * 3], c_frame[AV_NCON * 9], c_dist[AV_NCON], c_mu[AV_NCON * 3], c_f[AV_NCON * 6], c_lam[AV_NCON];
     int c_info[AV_NCON];  // geom1 | geom2 << 8 | dim << 16 | excluded << 20
-    int c_tree[AV_NCON];  // tree1 | tree2 << 8 (0xff: none)
+    int c_tree[AV_NCON];  // packed dof ranges / tree ids of the two kinematic trees (tr_pack)
     // scalar rows
     int sc_dof1[AV_NSC], sc_dof2[AV_NSC], sc_tree[AV_NSC];
     float sc_c1[AV_NSC], sc_c2[AV_NSC], sc_b[AV_NSC], sc_R[AV_NSC], sc_f[AV_NSC], sc_lo[AV_NSC], sc_hi[AV_NSC],
         sc_A[AV_NSC], sc_aref[AV_NSC], sc_MJ[AV_NSC * AV_TD];
-    float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
+    __align__(16) float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
     int cand_p[AV_NCAND], cand_c[AV_NCAND];
     int ncon, nsc, ncand_p, ncand_c, status;
 };
@@ -239,7 +259,7 @@ __device__ inline void add_contact(const DevModel &m, EnvS &S, int slot, int g1,
     S.c_info[slot] = g1 | (g2 << 8) | (dim << 16) | (excluded << 20);
 }
 
-__device__ inline void stage_collision(const DevModel &m, EnvS &S, int lane, bool multiccd) {
+__device__ inline void stage_collision(const DevModel &m, EnvS &S, int lane, bool multiccd, Prof &pf) {
     if (lane == 0) { S.ncon = 0; S.ncand_p = 0; S.ncand_c = 0; }
     __syncwarp();
     // broadphase: bounding spheres + world AABBs, pair list strided over lanes, warp-aggregated append
@@ -265,6 +285,7 @@ __device__ inline void stage_collision(const DevModel &m, EnvS &S, int lane, boo
         if (lane == 0) { S.ncand_p = min(AV_NCAND, np + __popc(mp)); S.ncand_c = min(AV_NCAND, nc + __popc(mc)); }
         __syncwarp();
     }
+    pf.mark(PF_BROAD, lane);
     // primitive pairs: one candidate per lane
     for (int base = 0; base < S.ncand_p; base += 32) {
         int k = base + lane;
@@ -295,6 +316,7 @@ __device__ inline void stage_collision(const DevModel &m, EnvS &S, int lane, boo
         if (lane == 0) S.ncon = min(AV_NCON, S.ncon + total);
         __syncwarp();
     }
+    pf.mark(PF_PRIM, lane);
     // convex pairs: oriented-box rejection per lane, then warp-cooperative MPR one pair at a time
     for (int base = 0; base < S.ncand_c; base += 32) {
         int k = base + lane, keep = 0;
@@ -322,6 +344,7 @@ __device__ inline void stage_collision(const DevModel &m, EnvS &S, int lane, boo
             __syncwarp();
         }
     }
+    pf.mark(PF_CONVEX, lane);
 }
 
 // ------------------------------------------------------------------ K3b: velocity, bias, actuation, smooth acceleration
@@ -485,341 +508,7 @@ __device__ inline void stage_rows_scalar(const DevModel &m, EnvS &S, int lane) {
     __syncwarp();
 }
 
-// packed lower-triangular index
-__device__ __forceinline__ int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
-
-// J . x for the 3 rows this lane holds, reduced over the 16 columns of its half; lane 0 / lane 16 hold the sums
-__device__ __forceinline__ void block_dot(const float j0, const float j1, const float j2, float x, float &r0, float &r1,
-                                          float &r2) {
-    r0 = j0 * x; r1 = j1 * x; r2 = j2 * x;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        r0 += __shfl_xor_sync(AV_FULL, r0, o);
-        r1 += __shfl_xor_sync(AV_FULL, r1, o);
-        r2 += __shfl_xor_sync(AV_FULL, r2, o);
-    }
-}
-
-// contacts, one at a time, lane = (half = lane >> 4 -> rows 3*half..3*half+2, col = lane & 15)
-__device__ inline void stage_rows_contact(const DevModel &m, EnvS &S, float *scratch, int lane) {
-    int col = lane & 15, half = lane >> 4;
-    for (int c = 0; c < S.ncon; c++) {
-        int info = S.c_info[c], g1 = info & 0xff, g2 = (info >> 8) & 0xff, dim = (info >> 16) & 0xf;
-        if ((info >> 20) & 1) { if (lane == 0) S.c_tree[c] = 0xffff; continue; }
-        int b1 = m.geom_body[g1], b2 = m.geom_body[g2];
-        int t1 = m.body_tree[b1], t2 = m.body_tree[b2];
-        if (t1 < 0) { t1 = t2; t2 = -1; }   // keep the first slot occupied; signs are handled per body below
-        if (t2 == t1) t2 = -1;
-        int t = col < 8 ? t1 : t2, dl = col & 7, dof = -1;
-        if (t >= 0 && dl < m.tree_dofnum[t]) dof = m.tree_dofadr[t] + dl;
-        float j0 = 0.f, j1 = 0.f, j2 = 0.f;
-        V3 p = ld3(S.c_pos + 3 * c);
-        if (dof >= 0) {
-            float sgn = 0.f;
-            if (m.body_tree[b2] == t && body_mask_has(m, b2, dof)) sgn += 1.f;
-            if (m.body_tree[b1] == t && body_mask_has(m, b1, dof)) sgn -= 1.f;
-            if (sgn != 0.f) {
-                S6 cd = ld6(S.cdof + 6 * dof);
-                V3 v = half == 0 ? cd.l + cross(cd.a, p - ld3(S.torig + 3 * t)) : cd.a;
-                v = v * sgn;
-                j0 = dot(ld3(S.c_frame + 9 * c), v);
-                j1 = dot(ld3(S.c_frame + 9 * c + 3), v);
-                j2 = dot(ld3(S.c_frame + 9 * c + 6), v);
-            }
-        }
-        if (half == 1 && dim < 6) { j0 = j1 = j2 = 0.f; }   // condim 3: no torsional / rolling rows
-        float *Js = S.stage, *MJs = S.stage + 6 * AV_JW;
-        Js[(3 * half + 0) * AV_JW + col] = j0; Js[(3 * half + 1) * AV_JW + col] = j1; Js[(3 * half + 2) * AV_JW + col] = j2;
-        __syncwarp();
-        // MinvJT rows: (J row) x (block inverse of the column's tree)
-        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        if (dof >= 0) {
-            const float *Mi = S.Minv + t * AV_TD * AV_TD + dl;  // column dl (symmetric)
-            int cb = col & 8, nt = m.tree_dofnum[t];
-            for (int k = 0; k < nt; k++) {
-                float mv = Mi[k * AV_TD];
-                m0 += Js[(3 * half + 0) * AV_JW + cb + k] * mv;
-                m1 += Js[(3 * half + 1) * AV_JW + cb + k] * mv;
-                m2 += Js[(3 * half + 2) * AV_JW + cb + k] * mv;
-            }
-        }
-        MJs[(3 * half + 0) * AV_JW + col] = m0; MJs[(3 * half + 1) * AV_JW + col] = m1; MJs[(3 * half + 2) * AV_JW + col] = m2;
-        float *blk = scratch + c * AV_CBLK;
-        blk[(3 * half + 0) * AV_JW + col] = j0; blk[(3 * half + 1) * AV_JW + col] = j1; blk[(3 * half + 2) * AV_JW + col] = j2;
-        blk[6 * AV_JW + (3 * half + 0) * AV_JW + col] = m0; blk[6 * AV_JW + (3 * half + 1) * AV_JW + col] = m1;
-        blk[6 * AV_JW + (3 * half + 2) * AV_JW + col] = m2;
-        // velocities / smooth accelerations / warm-start accelerations along the rows
-        float xv = dof >= 0 ? S.qvel[dof] : 0.f, xa = dof >= 0 ? S.qacc_smooth[dof] : 0.f, xw = dof >= 0 ? S.warm[dof] : 0.f;
-        float v0, v1, v2, a0, a1, a2, w0, w1, w2;
-        block_dot(j0, j1, j2, xv, v0, v1, v2);
-        block_dot(j0, j1, j2, xa, a0, a1, a2);
-        block_dot(j0, j1, j2, xw, w0, w1, w2);
-        __syncwarp();
-        // impedance, regularisation, reference acceleration
-        float K, B, imp, solref[2], solimp[5];
-        for (int k = 0; k < 2; k++) solref[k] = 0.5f * (m.geom_solref[2 * g1 + k] + m.geom_solref[2 * g2 + k]);
-        for (int k = 0; k < 5; k++) solimp[k] = 0.5f * (m.geom_solimp[5 * g1 + k] + m.geom_solimp[5 * g2 + k]);
-        float dist = S.c_dist[c];
-        kbi(m, solref, solimp, dist, K, B, imp);
-        float Rn = fmaxf(AV_MINVAL, (1.f - imp) / imp * (m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2]));
-        float mu0 = S.c_mu[3 * c], mu1 = S.c_mu[3 * c + 1], mu2 = S.c_mu[3 * c + 2];
-        float Rf = Rn / m.impratio;
-        float R[6] = {Rn, Rf, Rf, Rf * mu0 * mu0 / (mu1 * mu1), Rf * mu0 * mu0 / (mu2 * mu2), Rf * mu0 * mu0 / (mu2 * mu2)};
-        if (col == 0) {  // lanes 0 and 16 hold the reduced sums of their three rows
-            float vv[3] = {v0, v1, v2}, aa[3] = {a0, a1, a2}, ww[3] = {w0, w1, w2};
-            for (int k = 0; k < 3; k++) {
-                int row = 3 * half + k;
-                float aref = -B * vv[k] - (row == 0 ? K * imp * dist : 0.f);
-                bool live = row < dim;
-                S.c_aref[6 * c + row] = live ? aref : 0.f;
-                S.c_b[6 * c + row] = live ? aa[k] - aref : 0.f;
-                S.c_f[6 * c + row] = live ? -(ww[k] - aref) / R[row] : 0.f;
-            }
-        }
-        if (lane == 0) { S.c_Rn[c] = Rn; S.c_tree[c] = (t1 & 0xff) | ((t2 & 0xff) << 8); }
-        // AR = J MinvJT^T + R, packed lower triangle (21 entries), lane = entry
-        if (lane < 21) {
-            int i = 0;
-            while ((i + 1) * (i + 2) / 2 <= lane) i++;
-            int j = lane - i * (i + 1) / 2;
-            float s = 0.f;
-            for (int k = 0; k < AV_JW; k++) s += Js[i * AV_JW + k] * MJs[j * AV_JW + k];
-            if (i == j) s += (i < dim) ? R[i] : 1.f;   // dead rows get a unit diagonal
-            blk[12 * AV_JW + lane] = s;
-        }
-        __syncwarp();
-    }
-    // lane = contact: Cholesky factor of the regularised friction block (rows 1..dim-1), packed lower (15)
-    for (int c = lane; c < S.ncon; c += 32) {
-        int info = S.c_info[c], dim = (info >> 16) & 0xf;
-        if ((info >> 20) & 1) continue;
-        float *blk = scratch + c * AV_CBLK;
-        const float *AR = blk + 12 * AV_JW;
-        float Lc[15];
-        int n = dim - 1;
-        for (int i = 0; i < n; i++)
-            for (int j = 0; j <= i; j++) {
-                float s = AR[tri(i + 1, j + 1)];
-                for (int k = 0; k < j; k++) s -= Lc[tri(i, k)] * Lc[tri(j, k)];
-                Lc[tri(i, j)] = (i == j) ? sqrtf(fmaxf(s, AV_MINVAL)) : s / Lc[tri(j, j)];
-            }
-        for (int k = 0; k < n * (n + 1) / 2; k++) blk[12 * AV_JW + 21 + k] = Lc[k];
-        // project the warm-start force onto the cone
-        float *f = S.c_f + 6 * c;
-        if (f[0] <= 0.f) { for (int k = 0; k < 6; k++) f[k] = 0.f; }
-        else {
-            float mu[5] = {S.c_mu[3 * c], S.c_mu[3 * c], S.c_mu[3 * c + 1], S.c_mu[3 * c + 2], S.c_mu[3 * c + 2]};
-            float s = 0.f;
-            for (int k = 1; k < dim; k++) s += (f[k] / mu[k - 1]) * (f[k] / mu[k - 1]);
-            if (s > f[0] * f[0]) { float sc = f[0] * rsqrtf(s); for (int k = 1; k < dim; k++) f[k] *= sc; }
-        }
-    }
-    __syncwarp();
-}
-
-// ------------------------------------------------------------------ K6: block projected Gauss-Seidel on the dual + noslip
-// solve Lc Lc^T x = -b (n <= 5, Lc packed lower)
-__device__ __forceinline__ void tri_solve(const float *Lc, int n, const float *b, float *x) {
-    for (int i = 0; i < n; i++) {
-        float s = -b[i];
-        for (int k = 0; k < i; k++) s -= Lc[tri(i, k)] * x[k];
-        x[i] = s / Lc[tri(i, i)];
-    }
-    for (int i = n - 1; i >= 0; i--) {
-        float s = x[i];
-        for (int k = i + 1; k < n; k++) s -= Lc[tri(k, i)] * x[k];
-        x[i] = s / Lc[tri(i, i)];
-    }
-}
-__device__ inline void chol_small(const float A[5][5], int n, float lam, float *Lc) {
-    for (int i = 0; i < n; i++)
-        for (int j = 0; j <= i; j++) {
-            float s = A[i][j] + (i == j ? lam : 0.f);
-            for (int k = 0; k < j; k++) s -= Lc[tri(i, k)] * Lc[tri(j, k)];
-            Lc[tri(i, j)] = (i == j) ? sqrtf(fmaxf(s, AV_MINVAL)) : s / Lc[tri(j, j)];
-        }
-}
-// minimise 0.5 y'Ay + y'b  s.t.  sum (y_i/mu_i)^2 <= r^2.  Lc0 (nullable) = Cholesky factor of A itself.
-__device__ inline void qcqp(int n, const float Ain[5][5], const float *bin, const float *mu, float r, const float *Lc0,
-                            float *y) {
-    float Lc[15], z[5];
-    if (Lc0) tri_solve(Lc0, n, bin, y);
-    else { chol_small(Ain, n, 0.f, Lc); tri_solve(Lc, n, bin, y); }
-    float zz = 0.f;
-    for (int i = 0; i < n; i++) zz += (y[i] / mu[i]) * (y[i] / mu[i]);
-    if (zz <= r * r) return;
-    // scaled problem z = y / mu;  Newton on the multiplier of |z| = r
-    float A[5][5], b[5], w[5], mz[5];
-    for (int i = 0; i < n; i++) {
-        b[i] = bin[i] * mu[i];
-        for (int j = 0; j < n; j++) A[i][j] = Ain[i][j] * mu[i] * mu[j];
-    }
-    float lam = 0.f;
-    for (int it = 0; it < 12; it++) {
-        chol_small(A, n, lam, Lc);
-        tri_solve(Lc, n, b, z);
-        zz = 0.f;
-        for (int i = 0; i < n; i++) { zz += z[i] * z[i]; mz[i] = -z[i]; }
-        if (zz - r * r < 1e-6f * fmaxf(1e-12f, r * r)) break;
-        tri_solve(Lc, n, mz, w);
-        float zw = 0.f;
-        for (int i = 0; i < n; i++) zw += z[i] * w[i];
-        float nz = sqrtf(zz);
-        lam = fmaxf(0.f, lam + (nz - r) / r * zz / fmaxf(zw, AV_MINVAL));
-    }
-    if (zz > r * r) { float s = r * rsqrtf(zz); for (int i = 0; i < n; i++) z[i] *= s; }
-    for (int i = 0; i < n; i++) y[i] = z[i] * mu[i];
-}
-
-// acc += MinvJT_c^T df for contact block c (lane layout as in stage_rows_contact)
-__device__ __forceinline__ void apply_block(EnvS &S, const DevModel &m, const float *blk, int tr, int lane, const float *df) {
-    int col = lane & 15, half = lane >> 4;
-    const float *MJ = blk + 6 * AV_JW;
-    float s = MJ[(3 * half) * AV_JW + col] * df[3 * half] + MJ[(3 * half + 1) * AV_JW + col] * df[3 * half + 1] +
-              MJ[(3 * half + 2) * AV_JW + col] * df[3 * half + 2];
-    s += __shfl_xor_sync(AV_FULL, s, 16);
-    int t = col < 8 ? (tr & 0xff) : ((tr >> 8) & 0xff), dl = col & 7;
-    if (half == 0 && t != 0xff && dl < m.tree_dofnum[t]) S.acc[m.tree_dofadr[t] + dl] += s;
-}
-// residual J_c . acc for all 6 rows, broadcast to every lane
-__device__ __forceinline__ void block_residual(const EnvS &S, const DevModel &m, const float *blk, int tr, int lane, float *res) {
-    int col = lane & 15, half = lane >> 4;
-    int t = col < 8 ? (tr & 0xff) : ((tr >> 8) & 0xff), dl = col & 7;
-    float x = (t != 0xff && dl < m.tree_dofnum[t]) ? S.acc[m.tree_dofadr[t] + dl] : 0.f;
-    float r0, r1, r2;
-    block_dot(blk[(3 * half) * AV_JW + col], blk[(3 * half + 1) * AV_JW + col], blk[(3 * half + 2) * AV_JW + col], x, r0, r1, r2);
-    res[0] = __shfl_sync(AV_FULL, r0, 0); res[1] = __shfl_sync(AV_FULL, r1, 0); res[2] = __shfl_sync(AV_FULL, r2, 0);
-    res[3] = __shfl_sync(AV_FULL, r0, 16); res[4] = __shfl_sync(AV_FULL, r1, 16); res[5] = __shfl_sync(AV_FULL, r2, 16);
-}
-
-__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters) {
-    // acc <- M^-1 J^T f_warm  (constraint part of the acceleration); dual cost of the warm start
-    for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
-    __syncwarp();
-    for (int r = 0; r < S.nsc; r++) {
-        float f = S.sc_f[r];
-        int t = S.sc_tree[r];
-        if (lane < m.tree_dofnum[t]) S.acc[m.tree_dofadr[t] + lane] += S.sc_MJ[r * AV_TD + lane] * f;
-        __syncwarp();
-    }
-    for (int c = 0; c < S.ncon; c++) {
-        if ((S.c_info[c] >> 20) & 1) continue;
-        apply_block(S, m, scratch + c * AV_CBLK, S.c_tree[c], lane, S.c_f + 6 * c);
-        __syncwarp();
-    }
-    float cost = 0.f;
-    for (int r = 0; r < S.nsc; r++) {
-        float f = S.sc_f[r];
-        float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
-        cost += f * (0.5f * (ja + S.sc_R[r] * f) + S.sc_b[r]);
-    }
-    for (int c = 0; c < S.ncon; c++) {
-        int info = S.c_info[c], dim = (info >> 16) & 0xf;
-        if ((info >> 20) & 1) continue;
-        float res[6];
-        block_residual(S, m, scratch + c * AV_CBLK, S.c_tree[c], lane, res);
-        float Rn = S.c_Rn[c], mu0 = S.c_mu[3 * c], mu1 = S.c_mu[3 * c + 1], mu2 = S.c_mu[3 * c + 2], Rf = Rn / m.impratio;
-        float R[6] = {Rn, Rf, Rf, Rf * mu0 * mu0 / (mu1 * mu1), Rf * mu0 * mu0 / (mu2 * mu2), Rf * mu0 * mu0 / (mu2 * mu2)};
-        for (int k = 0; k < dim; k++) {
-            float f = S.c_f[6 * c + k];
-            cost += f * (0.5f * (res[k] + R[k] * f) + S.c_b[6 * c + k]);
-        }
-    }
-    __syncwarp();
-    if (cost >= 0.f) {  // the warm start does not beat f = 0
-        for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
-        for (int i = lane; i < AV_NSC; i += 32) S.sc_f[i] = 0.f;
-        for (int i = lane; i < AV_NCON * 6; i += 32) S.c_f[i] = 0.f;
-        __syncwarp();
-    }
-    for (int it = 0; it < iters + noslip_iters; it++) {
-        bool noslip = it >= iters;
-        // scalar rows: every lane computes the (uniform) update, lanes < nt apply it
-        for (int r = 0; r < S.nsc; r++) {
-            bool floss = S.sc_lo[r] > -1e37f && S.sc_lo[r] < 0.f;
-            if (noslip && !floss) continue;
-            float f = S.sc_f[r], R = noslip ? 0.f : S.sc_R[r];
-            float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
-            float res = S.sc_b[r] + R * f + ja;
-            float x = fminf(fmaxf(f - res / (S.sc_A[r] + R), S.sc_lo[r]), S.sc_hi[r]);
-            float df = x - f;
-            __syncwarp();
-            int t = S.sc_tree[r];
-            if (lane < m.tree_dofnum[t]) S.acc[m.tree_dofadr[t] + lane] += S.sc_MJ[r * AV_TD + lane] * df;
-            if (lane == 0) S.sc_f[r] = x;
-            __syncwarp();
-        }
-        for (int c = 0; c < S.ncon; c++) {
-            int info = S.c_info[c], dim = (info >> 16) & 0xf;
-            if ((info >> 20) & 1) continue;
-            const float *blk = scratch + c * AV_CBLK;
-            int tr = S.c_tree[c];
-            float res[6], f[6], old[6], AR[21];
-            block_residual(S, m, blk, tr, lane, res);
-            float Rn = S.c_Rn[c], mu0 = S.c_mu[3 * c], mu1 = S.c_mu[3 * c + 1], mu2 = S.c_mu[3 * c + 2], Rf = Rn / m.impratio;
-            float R[6] = {Rn, Rf, Rf, Rf * mu0 * mu0 / (mu1 * mu1), Rf * mu0 * mu0 / (mu2 * mu2), Rf * mu0 * mu0 / (mu2 * mu2)};
-            float mu[5] = {mu0, mu0, mu1, mu2, mu2};
-            for (int k = 0; k < 21; k++) AR[k] = blk[12 * AV_JW + k];
-            for (int k = 0; k < 6; k++) { old[k] = f[k] = S.c_f[6 * c + k]; }
-            if (!noslip) {
-                for (int k = 0; k < dim; k++) res[k] += S.c_b[6 * c + k] + R[k] * old[k];
-                // (a) ray update (normal-only when the block is empty)
-                if (old[0] < AV_MINVAL) {
-                    f[0] = fmaxf(0.f, old[0] - res[0] / AR[0]);
-                    for (int k = 1; k < dim; k++) f[k] = 0.f;
-                } else {
-                    float vAv = 0.f, vr = 0.f;
-                    for (int k = 0; k < dim; k++) {
-                        vr += old[k] * res[k];
-                        for (int l = 0; l < dim; l++) vAv += old[k] * AR[tri(k, l)] * old[l];
-                    }
-                    if (vAv > AV_MINVAL) {
-                        float x = -vr / vAv;
-                        if (old[0] + x * old[0] < 0.f) x = -1.f;
-                        for (int k = 0; k < dim; k++) f[k] = old[k] + x * old[k];
-                    }
-                }
-                // (b) friction rows on the ellipsoid of radius f_n
-                if (f[0] < AV_MINVAL) {
-                    for (int k = 1; k < dim; k++) f[k] = 0.f;
-                } else {
-                    float Ac[5][5], bc[5], y[5];
-                    for (int k = 1; k < dim; k++) {
-                        float s = res[k] + AR[tri(k, 0)] * (f[0] - old[0]);
-                        for (int l = 1; l < dim; l++) { Ac[k - 1][l - 1] = AR[tri(k, l)]; s -= AR[tri(k, l)] * old[l]; }
-                        bc[k - 1] = s;
-                    }
-                    qcqp(dim - 1, Ac, bc, mu, f[0], blk + 12 * AV_JW + 21, y);
-                    for (int k = 1; k < dim; k++) f[k] = y[k - 1];
-                }
-            } else {
-                // noslip: friction rows only, unregularised A, normal force fixed
-                if (old[0] < AV_MINVAL) {
-                    for (int k = 1; k < dim; k++) f[k] = 0.f;
-                } else {
-                    float Ac[5][5], bc[5], y[5];
-                    for (int k = 1; k < dim; k++) {
-                        float s = res[k] + S.c_b[6 * c + k];
-                        for (int l = 1; l < dim; l++) {
-                            float a = AR[tri(k, l)] - (k == l ? R[k] : 0.f);
-                            Ac[k - 1][l - 1] = a;
-                            s -= a * old[l];
-                        }
-                        bc[k - 1] = s;
-                    }
-                    qcqp(dim - 1, Ac, bc, mu, old[0], nullptr, y);
-                    for (int k = 1; k < dim; k++) f[k] = y[k - 1];
-                }
-            }
-            float df[6];
-            for (int k = 0; k < 6; k++) df[k] = (k < dim) ? f[k] - old[k] : 0.f;
-            __syncwarp();
-            apply_block(S, m, blk, tr, lane, df);
-            if (lane < 6) S.c_f[6 * c + lane] = (lane < dim) ? f[lane] : 0.f;
-            __syncwarp();
-        }
-    }
-}
+#include "avsim_solve.cuh"
 
 // ------------------------------------------------------------------ K7: Euler with implicit joint damping
 __device__ inline void stage_integrate(const DevModel &m, EnvS &S, int lane) {

@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched env.step() hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): SlotInsertion-3Arms-v0, 4096 environments per GPU in
+lockstep, no render, synthetic scripted joint-target actions (home -> reach above the stick -> close -> lift, plus
+per-env N(0, 0.01 rad) noise, seed 1234); one "step" = one env.step over the whole batch = 20 physics substeps of
+2 ms + reward + agent_pos (reference gym_guided_vision/env.py:203-226).  Episodes are 300 steps
+(sim_slot_insertion_3arms.yaml:17); the batch is reset (device-side Philox draw) when an episode ends.
+
+Arms:
+  default            : the CUDA path through the C-ABI (libavsim.so).  `value` = device-resident actions;
+                       `e2e` = avsim_step_host with HOST numpy buffers (H2D of actions, D2H of agent_pos + reward
+                       inside the timed region, every step).
+  --impl reference   : the CPU path on this box's host cores (the fp64 oracle, "CPU restatement -- MuJoCo is not
+                       installable offline"), all host threads, on a bounded sample of the same workload.
+
+Multi-GPU (torchrun, one rank per GPU): envs are independent, every rank steps its own 4096 (weak scaling, no
+data-path collective); one NCCL all_gather of per-env success at the end.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TASK, ARMS = "slot_insertion", 3
+EPISODE_LEN = 300
+ALGO_BYTES_PER_ENV_STEP = 1032   # fp32 state read + written per env.step
+HOME = np.array([0, -0.082, 1.06, 0, -0.953, 0, 0.02239] * 2 + [0, -0.8, 0.8, 0, 0.5, 0, 0], np.float64)
+METRIC = "env-steps/sec SlotInsertion-3Arms batch=4096"
+
+
+def script_actions(T, B, seed, xp=np):
+    """Joint-target script [T, B, 21] float32: reach (0-100), close gripper (100-130), lift (130-200), hold."""
+    rng = np.random.default_rng(seed)
+    home = HOME.copy()
+    home[6] = home[13] = 1.0                          # gripper open (normalised)
+    # a reach pose that brings both grippers down toward the table centre where stick / slot are placed
+    reach = home.copy()
+    reach[0:6] = [0.10, 0.55, 0.65, 0.0, 0.35, 0.0]
+    reach[7:13] = [-0.10, 0.55, 0.65, 0.0, 0.35, 0.0]
+    lift = reach.copy()
+    lift[1] -= 0.35; lift[8] -= 0.35
+    noise = rng.normal(0.0, 0.01, size=(B, 21))
+    noise[:, [6, 13]] = 0.0
+    offs = rng.normal(0.0, 0.08, size=(B, 21)) * np.array([1, 1, 1, 0, 1, 0, 0] * 2 + [0.3] * 7)
+    acts = np.empty((T, B, 21), np.float32)
+    for t in range(T):
+        if t < 100:
+            s = t / 100.0
+            a = home + s * (reach - home)
+            g = 1.0
+        elif t < 130:
+            a = reach.copy()
+            g = 1.0 - (t - 100) / 30.0
+        elif t < 200:
+            s = (t - 130) / 70.0
+            a = reach + s * (lift - reach)
+            g = 0.0
+        else:
+            a = lift.copy()
+            g = 0.0
+        w = min(1.0, t / 100.0)
+        row = a[None, :] + noise + w * offs
+        row[:, 6] = g
+        row[:, 13] = g
+        acts[t] = row
+    return acts
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (oracle)
+def cpu_steps_per_sec(n_envs, n_steps, threads, solver_iters, seed=1234):
+    """The CPU path (fp64 oracle) on `threads` host threads: n_envs environments x n_steps env.steps of the bench
+    workload (same script, same solver sweep count).  ctypes releases the GIL, so threads run in parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleEnv, OracleModel
+
+    path = model_io.model_path(TASK, ARMS)
+    om = OracleModel(path)
+    acts = script_actions(EPISODE_LEN, n_envs, seed).astype(np.float64)
+    rng = np.random.default_rng(seed)
+    envs = []
+    for e in range(n_envs):
+        o = OracleEnv(om)
+        o.set_options(max_iter=solver_iters, tol=0.0)
+        fp = np.array([[rng.uniform(-0.05, 0.05), rng.uniform(0.1, 0.15), 0.0],
+                       [rng.uniform(-0.08, 0.08), rng.uniform(-0.1, 0.0), 0.0]])
+        o.reset(free_pos=fp)
+        envs.append(o)
+    # sample the script across the episode so free motion and contact phases are both represented
+    ts = np.linspace(0, EPISODE_LEN - 1, n_steps).astype(int)
+
+    def run(e):
+        for t in ts:
+            envs[e].step(acts[t, e])
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(run, range(n_envs)))
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = max(cores, 8)
+    per_step_envs = n_envs
+    vals = []
+    total = args.warmup + args.steps
+    # each "step" of this arm = one env.step of a bounded sample of `n_envs` environments on all host threads
+    v, dt = cpu_steps_per_sec(n_envs, total, cores, args.solver_iters)
+    vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step_envs / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SlotInsertion-3Arms-v0 no render, scripted reach/grasp actions, sample of {n_envs} envs "
+                               f"x {total} env.steps spread over the 300-step episode (of the B=4096 workload)",
+                   "solver_iters": args.solver_iters, "nsubsteps": 20},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_envs} envs x {total} env.steps, fp64 CPU restatement (MuJoCo not installable offline)"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from av_aloha_b200 import capi, model_io
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model = capi.Model(model_io.model_path(TASK, ARMS), local)
+    batch = capi.Batch(model, B, seed=1234 + rank)
+    batch.set_options(solver_iters=args.solver_iters)
+    acts_np = script_actions(EPISODE_LEN, B, 1234 + rank)
+    acts = torch.as_tensor(acts_np, device=dev)                       # [T, B, 21] resident in HBM
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state = {"t": 0}
+
+    def advance():
+        if state["t"] == EPISODE_LEN:
+            batch.reset()
+            state["t"] = 0
+        t = state["t"]
+        state["t"] += 1
+        return t
+
+    def dev_step():
+        batch.step(acts[advance()])
+
+    agent_out = np.empty((B, model.njoints), np.float32)
+    rew_out = np.empty((B,), np.int32)
+
+    def host_step():
+        batch.step_host(acts_np[advance()], agent_pos_out=agent_out, reward_out=rew_out)
+
+    # ---- device-resident arm: per-step CUDA events on the launching (current) stream, L2 flushed between steps
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = batch.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    w0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        t = advance()
+        a = acts[t]
+        ev[k][0].record()
+        batch.step(a)
+        ev[k][1].record()
+    barrier()
+    wall = time.perf_counter() - w0
+    launches = batch.launch_count - l0
+    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(kern_ms))
+    status = batch.get(capi.STATUS)
+    n_bad = int((status & 1).sum().item())
+    n_ovf = int((status & 2 != 0).sum().item())
+    ncon_mean = float(batch.get(capi.NCON).float().mean().item())
+    rew_max = int(batch.get(capi.REWARD).max().item())
+
+    # ---- end-to-end arm: host numpy buffers through avsim_step_host, copies inside the timed region
+    for _ in range(min(args.warmup, 3)):
+        host_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        host_step()
+    e1.record()
+    barrier()
+    e2e_ms = float(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # success reduction: the only collective of the path (K10), one all_gather per rollout
+    succ = batch.get(capi.SUCCESS).to(torch.uint8)
+    if world > 1:
+        t_all = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t_all[0].item()), float(t_all[1].item())
+        gathered = [torch.empty_like(succ) for _ in range(world)]
+        dist.all_gather(gathered, succ)
+        succ = torch.cat(gathered)
+    n_succ = int(succ.sum().item())
+
+    if rank == 0:
+        value = world * B * args.steps / (total_ms * 1e-3)
+        e2e = world * B * args.steps / (e2e_ms * 1e-3)
+        peak, how = peaks()
+        kern_avg_ms = total_ms / args.steps
+        achieved = ALGO_BYTES_PER_ENV_STEP * B / (kern_avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": kern_avg_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"SlotInsertion-3Arms-v0 batch={B}/GPU lockstep, no render, scripted reach/grasp joint targets "
+                                   f"+ N(0,0.01) noise, 300-step episodes", "batch_per_gpu": B, "nsubsteps": 20,
+                       "solver_iters": args.solver_iters, "noslip_iters": 3, "parallelism": f"env-sharded x{world}",
+                       "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
+                       "timing": "sum of per-step CUDA event pairs on the launching stream, max over ranks"},
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(B * model.njoints * 4),
+                    "d2h_bytes_per_step": int(B * model.njoints * 4 + B * 4), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": how, "kernel": "avsim_step_kernel",
+                         "note": "latency/FP32-ALU bound by construction (SURVEY.md 8d): 1032 algorithmic bytes per env-step"},
+            "clocks": clocks,
+            "health": {"blown_up_envs": n_bad, "contact_overflow_envs": n_ovf, "ncon_mean": ncon_mean,
+                       "reward_max": rew_max, "successes": n_succ, "wall_s": wall},
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            n_envs, n_steps = max(cores, 8), 12
+            v, dt = cpu_steps_per_sec(n_envs, n_steps, cores, args.solver_iters)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n_envs} envs x {n_steps} env.steps spread over the episode, {dt:.1f} s, "
+                                              f"fp64 CPU restatement (MuJoCo not installable offline)"}
+        print(json.dumps(line))
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--solver-iters", type=int, default=20, dest="solver_iters")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

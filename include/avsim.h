@@ -85,6 +85,11 @@ int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, flo
 /* number of kernel launches issued by this batch so far (bench.py's gpu_launches) */
 int64_t avsim_launch_count(const avsim_batch *b);
 
+/* diagnostics: per-stage SM cycle counters summed over warps (only in a -DAVSIM_PROFILE build; otherwise returns
+ * AVSIM_ERR_ARG).  Stages: load, kinematics, inertia, broadphase, primitive narrowphase, convex narrowphase, smooth,
+ * scalar rows, contact rows, solve, integrate, outputs.  Returns the number of stages. */
+int avsim_stage_cycles(uint64_t *out_host, int n, int reset);
+
 /* ---- IK controllers (reference data_collection_scripts/diff_ik.py:51-90, grad_ik.py:8-99).
  * arm: 0 left, 1 right, 2 middle.  q/pos/quat_wxyz/q_out are device f32 arrays of n rows. */
 typedef struct {

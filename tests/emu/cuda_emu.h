@@ -21,6 +21,9 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__
+#define __grid_constant__
+static inline float __fdividef(float a, float b) { return a / b; }
+#define __align__(n) alignas(n)
 
 struct float4 {
     float x, y, z, w;
@@ -67,6 +70,10 @@ static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::exchange(0); }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::exchange((uint32_t)v)[src & 31]; }
 static inline float __shfl_sync(unsigned, float v, int src) { return u2f(emu::exchange(f2u(v))[src & 31]); }
+static inline float __shfl_sync(unsigned, float v, int src, int width) {
+    int l = emu::W.cur, base = l & ~(width - 1);
+    return u2f(emu::exchange(f2u(v))[base + (src & (width - 1))]);
+}
 static inline int __shfl_xor_sync(unsigned, int v, int o) { int l = emu::W.cur; return (int)emu::exchange((uint32_t)v)[(l ^ o) & 31]; }
 static inline float __shfl_xor_sync(unsigned, float v, int o) { int l = emu::W.cur; return u2f(emu::exchange(f2u(v))[(l ^ o) & 31]); }
 static inline int __shfl_up_sync(unsigned, int v, int off) {
