@@ -93,6 +93,8 @@ class Model:
             raise RuntimeError("av_aloha_b200 needs a CUDA device; there is no CPU path")
         self.lib = load_library()
         self.device = int(device)
+        self.avm_path = os.fspath(avm_path)
+        self._tables = None
         self.ptr = self.lib.avsim_model_load(os.fsencode(avm_path), self.device)
         if not self.ptr:
             raise AvsimError(self.lib.avsim_last_error().decode())
@@ -100,6 +102,17 @@ class Model:
         self.nq, self.nv, self.nu, self.nbody, self.ngeom = d("nq"), d("nv"), d("nu"), d("nbody"), d("ngeom")
         self.njoints, self.nfree, self.max_reward, self.task_id, self.num_arms = (
             d("njoints"), d("nfree"), d("max_reward"), d("task_id"), d("num_arms"))
+
+    def table(self, name):
+        """Host copy of a compiled-model array (names as in mjcf_compile.py), e.g. 'ik_range', 'reset_lo'."""
+        if self._tables is None:
+            from . import model_io
+            self._tables = model_io.load_avm(self.avm_path)
+        return self._tables[name]
+
+    def ik_range(self, arm):
+        n = int(self.table("ik_ndof")[arm])
+        return self.table("ik_range")[arm, :n]
 
     def __del__(self):
         try:

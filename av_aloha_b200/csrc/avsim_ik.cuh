@@ -100,9 +100,11 @@ __device__ inline void ik_quat2mat_xyzw(const double *qxyzw, double *R) {
     for (int i = 0; i < 4; i++) q[i] = (float)((double)q[i] * s);
     float q2[4][4];
     for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) q2[i][j] = q[i] * q[j];
-    R[0] = 1.0 - q2[2][2] - q2[3][3]; R[1] = (double)q2[1][2] - q2[3][0]; R[2] = (double)q2[1][3] + q2[2][0];
-    R[3] = (double)q2[1][2] + q2[3][0]; R[4] = 1.0 - q2[1][1] - q2[3][3]; R[5] = (double)q2[2][3] - q2[1][0];
-    R[6] = (double)q2[1][3] - q2[2][0]; R[7] = (double)q2[2][3] + q2[1][0]; R[8] = 1.0 - q2[1][1] - q2[2][2];
+    // the reference's off-diagonal sums are float32 +/- float32 (numpy promotion keeps float32); the diagonal starts
+    // from the float64 literal 1.0 and is therefore float64
+    R[0] = 1.0 - q2[2][2] - q2[3][3]; R[1] = (double)(q2[1][2] - q2[3][0]); R[2] = (double)(q2[1][3] + q2[2][0]);
+    R[3] = (double)(q2[1][2] + q2[3][0]); R[4] = 1.0 - q2[1][1] - q2[3][3]; R[5] = (double)(q2[2][3] - q2[1][0]);
+    R[6] = (double)(q2[1][3] - q2[2][0]); R[7] = (double)(q2[2][3] + q2[1][0]); R[8] = 1.0 - q2[1][1] - q2[2][2];
 }
 // angular_error (transform_utils.py:183-194)
 __device__ inline void ik_ang_err(const double *des, const double *cur, double *e) {

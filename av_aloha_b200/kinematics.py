@@ -1,0 +1,133 @@
+"""Batched IK controllers behind the reference's DiffIK / GradIK interface.
+
+Mirrors data_collection_scripts/diff_ik.py:8-22,89-90 (``DiffIK(...).run(q, target_pos, target_quat_wxyz) -> q``) and
+grad_ik.py:103-166 (``GradIK(...).run(...)``), plus ``create_fk_fn`` (kinematics.py:7-26).  The reference builds numba
+closures from a dm_control ``physics``; here the q = 0 screw axes / anchors / site pose live in the compiled model on
+the GPU and ``run`` launches the hand-written kernels (csrc/avsim_ik.cuh) through the C-ABI for one problem or a
+whole batch.  Quaternions are wxyz at this API like the reference.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+ARM_INDEX = {"left": 0, "right": 1, "middle": 2}
+
+# reference sim_env.py:89-138 (teleop sim env) and real_env.py:84-97
+GRADIK_SIM = dict(step_size=0.0001, min_cost_delta=1.0e-12, max_iterations=50, position_weight=500.0,
+                  rotation_weight=100.0, joint_center_weight=(10.0, 10.0, 1.0, 50.0, 1.0, 1.0),
+                  joint_displacement_weight=(50.0,) * 6, position_threshold=0.001, rotation_threshold=0.001,
+                  max_pos_diff=0.1, max_rot_diff=0.3, joint_p=0.9)
+DIFFIK_SIM = dict(k_pos=0.9, k_ori=0.9, damping=1.0e-4, k_null=(10.0, 10.0, 10.0, 10.0, 5.0, 5.0, 5.0),
+                  q0=(0, -0.8, 0.8, 0, 0.5, 0, 0), max_angvel=3.14, integration_dt=0.04, iterations=10)
+DIFFIK_REAL = dict(DIFFIK_SIM, k_pos=0.3, k_ori=0.3, integration_dt=0.02)
+
+
+def _arm(arm):
+    return ARM_INDEX[arm] if isinstance(arm, str) else int(arm)
+
+
+class _Controller:
+    def __init__(self, model: capi.Model, arm):
+        self.model, self.arm = model, _arm(arm)
+        self.lib = model.lib
+        self.ndof = (6, 6, 7)[self.arm]
+
+    def _io(self, q, pos, quat):
+        import torch
+
+        dev = torch.device("cuda", self.model.device)
+        single = np.ndim(q) == 1 if not hasattr(q, "dim") else q.dim() == 1
+        as_np = not hasattr(q, "is_cuda")
+        t = lambda x, w: torch.as_tensor(np.asarray(x, np.float32) if not hasattr(x, "is_cuda") else x,
+                                         dtype=torch.float32, device=dev).reshape(-1, w).contiguous()
+        qd, pd, qtd = t(q, self.ndof), t(pos, 3), t(quat, 4)
+        if not (len(qd) == len(pd) == len(qtd)):
+            raise ValueError("q, target_pos and target_quat must have the same leading dimension")
+        out = torch.empty_like(qd)
+        return qd, pd, qtd, out, single, as_np
+
+    @staticmethod
+    def _ret(out, single, as_np):
+        if as_np:
+            out = out.cpu().numpy().astype(np.float64)
+        return out[0] if single else out
+
+
+class DiffIK(_Controller):
+    """Damped-least-squares differential IK with a null-space posture term (reference diff_ik.py:51-85)."""
+
+    def __init__(self, model, arm="middle", k_pos=0.9, k_ori=0.9, damping=1.0e-4, k_null=DIFFIK_SIM["k_null"],
+                 q0=DIFFIK_SIM["q0"], max_angvel=3.14, integration_dt=0.04, iterations=10):
+        super().__init__(model, arm)
+        p = capi.DiffIKParams()
+        p.k_pos, p.k_ori, p.damping, p.max_angvel, p.integration_dt = k_pos, k_ori, damping, max_angvel, integration_dt
+        p.iterations = int(iterations)
+        for k in range(7):
+            p.k_null[k] = float(k_null[k]) if k < len(k_null) else 0.0
+            p.q0[k] = float(q0[k]) if k < len(q0) else 0.0
+        self.params = p
+
+    def run(self, q, target_pos, target_quat):
+        qd, pd, qtd, out, single, as_np = self._io(q, target_pos, target_quat)
+        capi.check(self.lib.avsim_diffik(self.model.ptr, self.arm, C.c_void_p(qd.data_ptr()), C.c_void_p(pd.data_ptr()),
+                                         C.c_void_p(qtd.data_ptr()), len(qd), C.byref(self.params),
+                                         C.c_void_p(out.data_ptr()), None))
+        return self._ret(out, single, as_np)
+
+
+class GradIK(_Controller):
+    """Finite-difference gradient-descent IK with a secant line step (reference grad_ik.py:8-99)."""
+
+    def __init__(self, model, arm="left", step_size=0.0001, min_cost_delta=1.0e-12, max_iterations=50,
+                 position_weight=500.0, rotation_weight=100.0, joint_center_weight=GRADIK_SIM["joint_center_weight"],
+                 joint_displacement_weight=GRADIK_SIM["joint_displacement_weight"], position_threshold=0.001,
+                 rotation_threshold=0.001, max_pos_diff=0.1, max_rot_diff=0.1, joint_p=0.1):
+        super().__init__(model, arm)
+        from . import model_io  # joint ranges of the arm (reference grad_ik.py:134-137 divides by the half range)
+
+        p = capi.GradIKParams()
+        p.step_size, p.min_cost_delta, p.max_iterations = step_size, min_cost_delta, int(max_iterations)
+        p.position_weight, p.rotation_weight = position_weight, rotation_weight
+        p.position_threshold, p.rotation_threshold = position_threshold, rotation_threshold
+        p.max_pos_diff, p.max_rot_diff, p.joint_p = max_pos_diff, max_rot_diff, joint_p
+        rng = model.ik_range(self.arm)
+        half = 0.5 * (rng[:, 1] - rng[:, 0])
+        for k in range(7):
+            live = k < self.ndof and k < len(joint_center_weight)
+            p.joint_center_weight[k] = float(joint_center_weight[k]) / float(half[k]) if live else 0.0
+            p.joint_displacement_weight[k] = float(joint_displacement_weight[k]) if k < len(joint_displacement_weight) else 0.0
+        self.params = p
+
+    def run(self, q, target_pos, target_quat):
+        qd, pd, qtd, out, single, as_np = self._io(q, target_pos, target_quat)
+        capi.check(self.lib.avsim_gradik(self.model.ptr, self.arm, C.c_void_p(qd.data_ptr()), C.c_void_p(pd.data_ptr()),
+                                         C.c_void_p(qtd.data_ptr()), len(qd), C.byref(self.params),
+                                         C.c_void_p(out.data_ptr()), None))
+        return self._ret(out, single, as_np)
+
+
+def create_fk_fn(model, arm):
+    """``fk(theta) -> 4x4`` (or [n,4,4]) end-effector site pose by product of exponentials (reference kinematics.py:7-26)."""
+    a = _arm(arm)
+    ndof = (6, 6, 7)[a]
+
+    def forward_kinematics(theta):
+        import torch
+
+        dev = torch.device("cuda", model.device)
+        as_np = not hasattr(theta, "is_cuda")
+        th = torch.as_tensor(np.asarray(theta, np.float32) if as_np else theta, dtype=torch.float32, device=dev)
+        single = th.dim() == 1
+        th = th.reshape(-1, ndof).contiguous()
+        out = torch.empty((len(th), 16), dtype=torch.float32, device=dev)
+        capi.check(model.lib.avsim_fk(model.ptr, a, C.c_void_p(th.data_ptr()), len(th), C.c_void_p(out.data_ptr()), None))
+        out = out.reshape(-1, 4, 4)
+        if as_np:
+            out = out.cpu().numpy().astype(np.float64)
+        return out[0] if single else out
+
+    return forward_kinematics

@@ -42,6 +42,7 @@ void run_block(int block, int grid, const std::function<void()> &body) {
 }  // namespace emu
 
 #include "../../av_aloha_b200/csrc/avsim_kernels.cuh"
+#include "../../av_aloha_b200/csrc/avsim_ik.cuh"
 #include "../../av_aloha_b200/csrc/avsim_model_pack.h"
 
 float4 av_smem_raw[(sizeof(EnvS) + 15) / 16 + 1];
@@ -106,5 +107,18 @@ void emu_reset(EmuBatch *b, const float *free_pos) {
     for (int blk = 0; blk < nb; blk++)
         emu::run_block(blk, nb, [&]() { avsim_reset_kernel(b->pk.dm, b->st, nullptr, free_pos, AV_HOME); });
     emu_forward(b);
+}
+// IK kernels (thread per problem): arm 0 left, 1 right, 2 middle
+void emu_fk(EmuBatch *b, int arm, const float *q, int n, float *T_out) {
+    int nb = (n + 31) / 32;
+    for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_fk_kernel(b->pk.dm, arm, q, n, T_out); });
+}
+void emu_diffik(EmuBatch *b, int arm, const float *q, const float *pos, const float *quat, int n, const DiffIKParams *p, float *out) {
+    int nb = (n + 31) / 32;
+    for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_diffik_kernel(b->pk.dm, arm, q, pos, quat, n, *p, out); });
+}
+void emu_gradik(EmuBatch *b, int arm, const float *q, const float *pos, const float *quat, int n, const GradIKParams *p, float *out) {
+    int nb = (n + 31) / 32;
+    for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_gradik_kernel(b->pk.dm, arm, q, pos, quat, n, *p, out); });
 }
 }

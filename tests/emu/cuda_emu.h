@@ -91,5 +91,6 @@ static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pre
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+using std::isfinite;
 using std::max;
 using std::min;

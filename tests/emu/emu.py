@@ -83,3 +83,42 @@ class EmuBatch:
             self._fp = np.ascontiguousarray(free_pos, dtype=np.float32)
             fp = self._fp.ctypes.data_as(C.POINTER(C.c_float))
         lib().emu_reset(self.ptr, fp)
+
+
+# ---- IK kernels through the emulator (same parameter structs as the C-ABI)
+def _ik_setup():
+    from av_aloha_b200.capi import DiffIKParams, GradIKParams
+    L = lib()
+    fp = C.POINTER(C.c_float)
+    L.emu_fk.argtypes = [C.c_void_p, C.c_int, fp, C.c_int, fp]
+    L.emu_diffik.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_int, C.POINTER(DiffIKParams), fp]
+    L.emu_gradik.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_int, C.POINTER(GradIKParams), fp]
+    return L
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def emu_fk(eb, arm, q):
+    L = _ik_setup()
+    q = np.ascontiguousarray(q, np.float32)
+    out = np.zeros((len(q), 16), np.float32)
+    L.emu_fk(eb.ptr, arm, _fp(q), len(q), _fp(out))
+    return out.reshape(-1, 4, 4)
+
+
+def emu_diffik(eb, arm, q, pos, quat, params):
+    L = _ik_setup()
+    q, pos, quat = (np.ascontiguousarray(x, np.float32) for x in (q, pos, quat))
+    out = np.zeros_like(q)
+    L.emu_diffik(eb.ptr, arm, _fp(q), _fp(pos), _fp(quat), len(q), C.byref(params), _fp(out))
+    return out
+
+
+def emu_gradik(eb, arm, q, pos, quat, params):
+    L = _ik_setup()
+    q, pos, quat = (np.ascontiguousarray(x, np.float32) for x in (q, pos, quat))
+    out = np.zeros_like(q)
+    L.emu_gradik(eb.ptr, arm, _fp(q), _fp(pos), _fp(quat), len(q), C.byref(params), _fp(out))
+    return out

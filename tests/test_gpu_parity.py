@@ -36,6 +36,7 @@ def test_forward_contact_free(setup):
     B = 8
     rng = np.random.default_rng(0)
     batch = capi.Batch(model, B, seed=1)
+    batch.set_options(solver_iters=100)   # parity is on the converged solution (equality + friction-loss rows are live)
     fp = np.stack([np.array([[rng.uniform(-0.05, 0.05), rng.uniform(0.1, 0.15), 0.0],
                              [rng.uniform(-0.08, 0.08), rng.uniform(-0.1, 0.0), 0.0]]) for _ in range(B)])
     batch.reset(free_pos=fp)
