@@ -170,7 +170,9 @@ class Batch:
             self._mask = t.as_tensor(mask, dtype=t.uint8, device=self.dev).contiguous()
             mp = C.c_void_p(self._mask.data_ptr())
         if free_pos is not None:
-            self._fp = t.as_tensor(np.asarray(free_pos, dtype=np.float32), device=self.dev).contiguous()
+            if not t.is_tensor(free_pos):
+                free_pos = np.asarray(free_pos, dtype=np.float32)
+            self._fp = t.as_tensor(free_pos, dtype=t.float32, device=self.dev).contiguous()
             assert self._fp.shape == (self.num_envs, self.model.nfree, 3), self._fp.shape
             fp = C.c_void_p(self._fp.data_ptr())
         check(self.lib.avsim_reset(self.ptr, mp, fp))

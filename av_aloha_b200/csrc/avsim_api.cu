@@ -14,6 +14,13 @@
 #include "avsim_kernels.cuh"
 #include "avsim_model_pack.h"
 
+#ifndef AV_DEFAULT_WARPS
+#define AV_DEFAULT_WARPS 1
+#endif
+#ifndef AV_DEFAULT_SYNC
+#define AV_DEFAULT_SYNC 0
+#endif
+
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
     snprintf(g_err, sizeof g_err, fmt, a, b);
@@ -94,7 +101,7 @@ struct avsim_batch {
     const avsim_model *model;
     BatchState st;
     cudaStream_t stream;
-    int grid;
+    int grid, warps;
     int64_t launches = 0;
     std::vector<void *> allocs;
     float *h_action = nullptr, *h_agent = nullptr;   // pinned staging for the host-buffer path
@@ -136,14 +143,20 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
         avsim_destroy(b);
         return nullptr;
     }
-    int smem = (int)sizeof(EnvS);
+    // block shape: W warps = W environments per block (diagnostic overrides: AVSIM_WARPS, AVSIM_SYNC)
+    const char *ew = getenv("AVSIM_WARPS"), *es = getenv("AVSIM_SYNC");
+    b->warps = ew ? atoi(ew) : AV_DEFAULT_WARPS;
+    s.sync = es ? atoi(es) : AV_DEFAULT_SYNC;
+    if (b->warps < 1 || b->warps > AV_MAX_WARPS) { fail(AVSIM_ERR_ARG, "avsim_create: AVSIM_WARPS out of range"); avsim_destroy(b); return nullptr; }
+    int smem = (int)sizeof(EnvS) * b->warps;
     CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0, sms = 0;
-    CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, avsim_step_kernel, 32, smem));
+    CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, avsim_step_kernel, 32 * b->warps, smem));
     CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
     if (per_sm < 1) { fail(AVSIM_ERR_CUDA, "avsim_create: step kernel does not fit on an SM"); avsim_destroy(b); return nullptr; }
-    b->grid = std::min(num_envs, per_sm * sms);   // persistent: a multiple of the SM count, looping over envs
+    // persistent: a multiple of the SM count, looping over envs
+    b->grid = std::min((num_envs + b->warps - 1) / b->warps, per_sm * sms);
     if (avsim_reset(b, nullptr, nullptr) != 0) { avsim_destroy(b); return nullptr; }
     return b;
 }
@@ -166,8 +179,8 @@ extern "C" int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_it
     return AVSIM_OK;
 }
 
-static int launch_forward(avsim_batch *b) {
-    avsim_forward_kernel<<<b->grid, 32, sizeof(EnvS), b->stream>>>(b->model->dm, b->st);
+static int launch_forward(avsim_batch *b, const uint8_t *mask_dev = nullptr) {
+    avsim_forward_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->warps, b->stream>>>(b->model->dm, b->st, mask_dev);
     b->launches++;
     CU(cudaGetLastError());
     return AVSIM_OK;
@@ -180,13 +193,13 @@ extern "C" int avsim_reset(avsim_batch *b, const uint8_t *mask_dev, const float 
     avsim_reset_kernel<<<(n + 127) / 128, 128, 0, b->stream>>>(b->model->dm, b->st, mask_dev, free_pos_dev, b->model->home_dev);
     b->launches++;
     CU(cudaGetLastError());
-    return launch_forward(b);   // physics.forward() + first observation (reference env.py:244-246)
+    return launch_forward(b, mask_dev);   // physics.forward() + first observation of the reset envs (reference env.py:244-246)
 }
 
 extern "C" int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps) {
     if (!b || nsubsteps < 0) return fail(AVSIM_ERR_ARG, "avsim_step: bad arguments");
     CU(cudaSetDevice(b->model->device));
-    avsim_step_kernel<<<b->grid, 32, sizeof(EnvS), b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
+    avsim_step_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->warps, b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
     b->launches++;
     CU(cudaGetLastError());
     return AVSIM_OK;

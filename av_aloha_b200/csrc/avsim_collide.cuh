@@ -12,6 +12,7 @@
 
 #define AV_MPR_TOL 1e-6f
 #define AV_MPR_ITERS 50
+#define AV_SUP_UNROLL 8
 
 struct Shape {
     int type, nvert;
@@ -195,13 +196,24 @@ __device__ inline V3 support_world(const Shape &S, V3 dir, int lane) {
     if (S.type == AV_GEOM_MESH) {
         float bd = -3.0e38f;
         int bi = 0x7fffffff;
-        for (int i = lane; i < S.nvert; i += 32) {
-            float4 p = S.vert[i];
-            float dt = p.x * dl.x + p.y * dl.y + p.z * dl.z;
-            if (dt > bd) { bd = dt; bi = i; }
+        // 8 independent 512-byte row loads in flight per lane before the first use: the scan is bound by L2 latency
+        // (ncu: one third of all stall samples sat on the dependent load->FMA of the rolled loop), not by bandwidth
+        for (int base = lane; base < S.nvert; base += 32 * AV_SUP_UNROLL) {
+            float4 pv[AV_SUP_UNROLL];
+#pragma unroll
+            for (int u = 0; u < AV_SUP_UNROLL; u++) {
+                int i = base + 32 * u;
+                pv[u] = ldg4(S.vert + (i < S.nvert ? i : lane));
+            }
+#pragma unroll
+            for (int u = 0; u < AV_SUP_UNROLL; u++) {
+                int i = base + 32 * u;
+                float dt = pv[u].x * dl.x + pv[u].y * dl.y + pv[u].z * dl.z;
+                if (i < S.nvert && dt > bd) { bd = dt; bi = i; }
+            }
         }
         warp_argmax(bd, bi);
-        float4 p = S.vert[bi];
+        float4 p = ldg4(S.vert + bi);
         pl = v3(p.x, p.y, p.z);
     } else if (S.type == AV_GEOM_BOX) {
         pl = v3(dl.x >= 0 ? S.size.x : -S.size.x, dl.y >= 0 ? S.size.y : -S.size.y, dl.z >= 0 ? S.size.z : -S.size.z);
@@ -215,11 +227,17 @@ __device__ inline V3 support_world(const Shape &S, V3 dir, int lane) {
     }
     return mul(S.mat, pl) + S.pos;
 }
-__device__ inline Sup mpr_support(const Shape &A, const Shape &B, V3 dir, int lane) {
-    Sup s;
+// Deliberately NOT inlined (and mpr_penetration has one call site): the step kernel's instruction footprint is what
+// bounds it (ncu: 'no_instruction' stalls), and MPR inlined at every call site was 190 KB of SASS.
+__device__ __noinline__ void mpr_support_ni(const Shape &A, const Shape &B, float dx, float dy, float dz, int lane, Sup &s) {
+    V3 dir = v3(dx, dy, dz);
     s.v1 = support_world(A, dir, lane);
     s.v2 = support_world(B, -dir, lane);
     s.v = s.v1 - s.v2;
+}
+__device__ __forceinline__ Sup mpr_support(const Shape &A, const Shape &B, V3 dir, int lane) {
+    Sup s;
+    mpr_support_ni(A, B, dir.x, dir.y, dir.z, lane, s);
     return s;
 }
 __device__ __forceinline__ V3 portal_dir(const Sup *p) { return normalized(cross(p[2].v - p[1].v, p[3].v - p[1].v)); }
@@ -286,7 +304,7 @@ __device__ inline V3 find_pos(const Sup *p) {
 }
 
 // returns true (warp-uniform) and depth / direction A->B / position when the shapes intersect
-__device__ inline bool mpr_penetration(const Shape &A, const Shape &B, int lane, float &depth, V3 &dir, V3 &pos) {
+__device__ __noinline__ bool mpr_penetration(const Shape &A, const Shape &B, int lane, float &depth, V3 &dir, V3 &pos) {
     Sup p[4], v4;
     p[0].v1 = A.pos; p[0].v2 = B.pos; p[0].v = A.pos - B.pos;
     if (norm(p[0].v) < 1e-9f) p[0].v.x += 1e-6f;
@@ -347,27 +365,32 @@ __device__ inline M3 rot_axis_angle(V3 ax, float ang) {
     return R;
 }
 
-// warp-cooperative convex pair: up to 5 points (multiccd) sharing the unperturbed normal
+// warp-cooperative convex pair: up to 5 points (multiccd) sharing the unperturbed normal.  q = -1 is the unperturbed
+// run, q = 0..3 the +-1e-3 rad rotations about the two tangent axes through the first contact point.
 __device__ inline void collide_convex(const Shape &A, const Shape &B, bool multiccd, int lane, PrimOut &o) {
-    float depth;
-    V3 dir, pos;
     o.n = 0;
-    if (!mpr_penetration(A, B, lane, depth, dir, pos)) return;
-    if (norm(dir) < 0.5f) return;
-    o.n = 1; o.nrm = dir; o.dist[0] = -depth; o.pos[0] = pos;
-    if (!multiccd) return;
-    V3 t1, t2;
-    make_frame(dir, t1, t2);
-    for (int q = 0; q < 4; q++) {
-        V3 ax = q < 2 ? t1 : t2;
-        float ang = (q & 1) ? -1e-3f : 1e-3f;
-        M3 Rp = rot_axis_angle(ax, ang), Rm = rot_axis_angle(ax, -ang);
-        Shape A2 = A, B2 = B;
-        A2.mat = mul(Rp, A.mat); A2.pos = pos + mul(Rp, A.pos - pos);
-        B2.mat = mul(Rm, B.mat); B2.pos = pos + mul(Rm, B.pos - pos);
+    V3 t1 = v3(0, 0, 0), t2 = v3(0, 0, 0), pos0 = v3(0, 0, 0);
+    Shape A2 = A, B2 = B;
+    int nq = multiccd ? 4 : 0;
+    for (int q = -1; q < nq; q++) {
+        if (q >= 0) {
+            V3 ax = q < 2 ? t1 : t2;
+            float ang = (q & 1) ? -1e-3f : 1e-3f;
+            M3 Rp = rot_axis_angle(ax, ang), Rm = rot_axis_angle(ax, -ang);
+            A2.mat = mul(Rp, A.mat); A2.pos = pos0 + mul(Rp, A.pos - pos0);
+            B2.mat = mul(Rm, B.mat); B2.pos = pos0 + mul(Rm, B.pos - pos0);
+        }
         float dp;
         V3 dr, ps;
-        if (!mpr_penetration(A2, B2, lane, dp, dr, ps) || norm(dr) < 0.5f) continue;
+        bool hit = mpr_penetration(A2, B2, lane, dp, dr, ps) && norm(dr) >= 0.5f;
+        if (q < 0) {
+            if (!hit) return;
+            o.n = 1; o.nrm = dr; o.dist[0] = -dp; o.pos[0] = ps;
+            pos0 = ps;
+            make_frame(dr, t1, t2);
+            continue;
+        }
+        if (!hit) continue;
         bool dup = false;
         for (int c = 0; c < o.n; c++) dup = dup || norm(ps - o.pos[c]) < 1e-4f;
         if (dup) continue;

@@ -34,22 +34,6 @@ __device__ inline void env_store(const DevModel &m, const BatchState &B, EnvS &S
     for (int i = lane; i < m.nu; i += 32) B.ctrl[(size_t)env * m.nu + i] = S.ctrl[i];
 }
 
-__device__ inline void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf) {
-    stage_kinematics(m, S, lane);
-    pf.mark(PF_KIN, lane);
-    stage_inertia(m, S, lane);
-    pf.mark(PF_INERTIA, lane);
-    stage_collision(m, S, lane, B.multiccd != 0, pf);
-    stage_smooth(m, S, lane);
-    pf.mark(PF_SMOOTH, lane);
-    stage_rows_scalar(m, S, lane);
-    pf.mark(PF_ROWS_S, lane);
-    stage_rows_contact(m, S, scratch, lane);
-    pf.mark(PF_ROWS_C, lane);
-    stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters);
-    pf.mark(PF_SOLVE, lane);
-}
-
 __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane, bool with_reward) {
     int latch = B.latch[env];
     int r = stage_reward(m, S, lane, latch);
@@ -81,47 +65,77 @@ __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS 
     }
 }
 
+// A block is W warps (blockDim = 32 x W), one environment per warp, each with its own EnvS slice of dynamic shared
+// memory.  B.sync selects how tightly the warps of a block move together: 0 = free running, 1 = re-aligned at every
+// substep, 2 = every stage in lockstep.  Lockstep keeps all warps of an SM inside the same few KB of code (the kernel
+// is instruction-fetch bound, see profiles/), at the price of waiting for the slowest environment of the block.
+#define AV_RUN(active, sync, call)              \
+    do {                                        \
+        if (active) { call; }                   \
+        if ((sync) >= 2) __syncthreads();       \
+    } while (0)
+
+__device__ __forceinline__ void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf,
+                                            bool active, int sync) {
+    AV_RUN(active, sync, stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane));
+    AV_RUN(active, sync, stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
+    AV_RUN(active, sync, stage_collision(m, S, lane, B.multiccd != 0, pf));
+    AV_RUN(active, sync, stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane); pf.mark(PF_ROWS_S, lane));
+    AV_RUN(active, sync, stage_rows_contact(m, S, scratch, lane); pf.mark(PF_ROWS_C, lane));
+    AV_RUN(active, sync, stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters); pf.mark(PF_SOLVE, lane));
+}
+
 // env.step: ctrl write (reference env.py:204-215), nsub x mj_step (env.py:218), trailing position pass, reward
-__global__ void __launch_bounds__(32) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B, const float *__restrict__ action, int nsub) {
-    EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
-    int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * AV_MAX_WARPS) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
+                                                                      const float *__restrict__ action, int nsub) {
+    int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y, sync = B.sync;
+    EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + warp);
     Prof pf;
-    for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
+    for (int base = blockIdx.x * W; base < B.num_envs; base += gridDim.x * W) {
+        int env = base + warp;
+        bool active = env < B.num_envs;
+        float *scratch = B.scratch + (size_t)(active ? env : 0) * AV_SCRATCH_FLOATS;
         pf.start();
-        env_load(m, B, S, env, lane);
-        pf.mark(PF_LOAD, lane);
-        if (action && lane < m.nj_obs) {
-            float a = action[(size_t)env * m.nj_obs + lane];
-            if (lane == 6 || lane == 13) a = a * (m.act_ctrl_hi[lane] - m.act_ctrl_lo[lane]) + m.act_ctrl_lo[lane];
-            S.ctrl[lane] = a;
+        if (active) {
+            env_load(m, B, S, env, lane);
+            pf.mark(PF_LOAD, lane);
+            if (action && lane < m.nj_obs) {
+                float a = action[(size_t)env * m.nj_obs + lane];
+                if (lane == 6 || lane == 13) a = a * (m.act_ctrl_hi[lane] - m.act_ctrl_lo[lane]) + m.act_ctrl_lo[lane];
+                S.ctrl[lane] = a;
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
         for (int s = 0; s < nsub; s++) {
-            env_forward(m, B, S, scratch, lane, pf);
-            stage_integrate(m, S, lane);
-            pf.mark(PF_INTEGRATE, lane);
+            if (sync >= 1) __syncthreads();
+            env_forward(m, B, S, scratch, lane, pf, active, sync);
+            AV_RUN(active, sync, stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
         }
-        stage_kinematics(m, S, lane);
-        pf.mark(PF_KIN, lane);
-        stage_collision(m, S, lane, B.multiccd != 0, pf);
-        env_store(m, B, S, env, lane);
-        env_outputs(m, B, S, env, lane, true);
-        pf.mark(PF_OUT, lane);
-        __syncwarp();
+        if (active) {
+            stage_kinematics(m, S, lane);
+            pf.mark(PF_KIN, lane);
+            stage_collision(m, S, lane, B.multiccd != 0, pf);
+            env_store(m, B, S, env, lane);
+            env_outputs(m, B, S, env, lane, true);
+            pf.mark(PF_OUT, lane);
+            __syncwarp();
+        }
     }
 }
 
-// physics.forward(): all stages, no integration; dumps stage outputs for the parity tests
-__global__ void __launch_bounds__(32) avsim_forward_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B) {
-    EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
-    int lane = threadIdx.x;
-    for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
+// physics.forward(): all stages, no integration; dumps stage outputs for the parity tests.  mask (nullable) selects envs.
+__global__ void __launch_bounds__(32 * AV_MAX_WARPS) avsim_forward_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
+                                                                         const uint8_t *__restrict__ mask) {
+    int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y;
+    EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + warp);
+    for (int base = blockIdx.x * W; base < B.num_envs; base += gridDim.x * W) {
+        int env = base + warp;
+        if (env >= B.num_envs || (mask && !mask[env])) continue;
         Prof pf;
         pf.start();
         env_load(m, B, S, env, lane);
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
-        env_forward(m, B, S, scratch, lane, pf);
+        env_forward(m, B, S, scratch, lane, pf, true, 0);
         for (int i = lane; i < m.nv; i += 32) {
             B.qacc[(size_t)env * m.nv + i] = S.qacc_smooth[i] + S.acc[i];
             B.qacc_smooth[(size_t)env * m.nv + i] = S.qacc_smooth[i];

@@ -2,6 +2,12 @@
 #pragma once
 
 #define AV_FULL 0xffffffffu
+// Pipeline stages are real functions, not inlined into the kernel: each runs once per substep (call overhead is noise)
+// and the kernel's instruction footprint -- what ncu shows as the dominant stall -- stays the sum of the stages instead
+// of growing with every call site; it also makes cuobjdump / ncu attribute code per stage.
+#ifndef AV_STAGE
+#define AV_STAGE __noinline__
+#endif
 #define AV_MINVAL 1e-15f
 
 struct V3 {
@@ -112,6 +118,15 @@ __device__ __forceinline__ S6 inert_mul(const float *I, S6 v) {
              I[4] * v.a.x + I[5] * v.a.y + I[2] * v.a.z) + cross(mc, v.l);
     f.l = v.l * I[9] - cross(mc, v.a);
     return f;
+}
+
+// read-only model data (hull vertices): non-coherent path
+__device__ __forceinline__ float4 ldg4(const float4 *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
 }
 
 // ---- warp collectives (one warp == one environment)

@@ -170,7 +170,7 @@ __device__ __forceinline__ void qcqp5(const float (&A)[15], const float (&b)[5],
 }
 
 // ------------------------------------------------------------------ K5: contact rows, one contact at a time
-__device__ inline void stage_rows_contact(const DevModel &m, EnvS &S, float *scratch, int lane) {
+__device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *scratch, int lane) {
     int col = lane & 15, half = lane >> 4;
     for (int c = 0; c < S.ncon; c++) {
         int info = S.c_info[c], g1 = info & 0xff, g2 = (info >> 8) & 0xff, dim = (info >> 16) & 0xf;
@@ -307,53 +307,36 @@ __device__ inline void stage_rows_contact(const DevModel &m, EnvS &S, float *scr
 }
 
 // ------------------------------------------------------------------ K6: block projected Gauss-Seidel + noslip
-// one block update in the regularised sweep: (a) ray update, (b) friction rows on the ellipsoid of radius f_n
-__device__ __forceinline__ void contact_update(const CBlk &cb, float (&res)[6], const float (&old)[6], float &lam, float (&f)[6]) {
+// One block update.  Regularised sweep (noslip = false): (a) ray update of the whole 6-vector, (b) friction rows on the
+// ellipsoid of radius f_n.  Noslip sweep: friction rows only, unregularised A, normal force fixed.  Both modes share ONE
+// instance of the QCQP code: the sweep loop is the hottest code of the kernel and has to stay inside the SM's
+// instruction cache (ncu showed 'no_instruction' as the top stall when each mode carried its own copy).
+__device__ __forceinline__ void contact_block_update(const CBlk &cb, int dim, bool noslip, float (&res)[6], const float (&old)[6],
+                                                     float &lam, float (&f)[6]) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) { res[k] += cb.b[k] + cb.R[k] * old[k]; f[k] = old[k]; }
-    if (old[0] < AV_MINVAL) {
-        f[0] = fmaxf(0.f, old[0] - __fdividef(res[0], cb.AR[0]));
+    for (int k = 0; k < 6; k++) { res[k] += cb.b[k] + (noslip ? 0.f : cb.R[k] * old[k]); f[k] = old[k]; }
+    if (!noslip) {
+        if (old[0] < AV_MINVAL) {
+            f[0] = fmaxf(0.f, old[0] - __fdividef(res[0], cb.AR[0]));
 #pragma unroll
-        for (int k = 1; k < 6; k++) f[k] = 0.f;
-    } else {
-        float vAv = 0.f, vr = 0.f;
+            for (int k = 1; k < 6; k++) f[k] = 0.f;
+        } else {
+            float vAv = 0.f, vr = 0.f;
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            vr += old[k] * res[k];
+            for (int k = 0; k < 6; k++) {
+                vr += old[k] * res[k];
 #pragma unroll
-            for (int l = 0; l < 6; l++) vAv += old[k] * cb.AR[TRI(k, l)] * old[l];
-        }
-        if (vAv > AV_MINVAL) {
-            float x = -__fdividef(vr, vAv);
-            if (old[0] + x * old[0] < 0.f) x = -1.f;
+                for (int l = 0; l < 6; l++) vAv += old[k] * cb.AR[TRI(k, l)] * old[l];
+            }
+            if (vAv > AV_MINVAL) {
+                float x = -__fdividef(vr, vAv);
+                if (old[0] + x * old[0] < 0.f) x = -1.f;
 #pragma unroll
-            for (int k = 0; k < 6; k++) f[k] = old[k] + x * old[k];
+                for (int k = 0; k < 6; k++) f[k] = old[k] + x * old[k];
+            }
         }
     }
     if (f[0] < AV_MINVAL) {
-#pragma unroll
-        for (int k = 1; k < 6; k++) f[k] = 0.f;
-    } else {
-        float Ac[15], bc[5], y[5];
-#pragma unroll
-        for (int k = 1; k < 6; k++) {
-            float s = res[k] + cb.AR[TRI(k, 0)] * (f[0] - old[0]);
-#pragma unroll
-            for (int l = 1; l < 6; l++) s -= cb.AR[TRI(k, l)] * old[l];
-            bc[k - 1] = s;
-#pragma unroll
-            for (int l = 1; l <= k; l++) Ac[TRI(k - 1, l - 1)] = cb.AR[TRI(k, l)];
-        }
-        qcqp5(Ac, bc, cb.mu, cb.imu, f[0], cb.Lc, true, lam, y);
-#pragma unroll
-        for (int k = 1; k < 6; k++) f[k] = y[k - 1];
-    }
-}
-// noslip: friction rows only, unregularised A, normal force fixed
-__device__ __forceinline__ void contact_noslip(const CBlk &cb, int dim, const float (&res)[6], const float (&old)[6], float &lam, float (&f)[6]) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) f[k] = old[k];
-    if (old[0] < AV_MINVAL) {
 #pragma unroll
         for (int k = 1; k < 6; k++) f[k] = 0.f;
         return;
@@ -361,21 +344,71 @@ __device__ __forceinline__ void contact_noslip(const CBlk &cb, int dim, const fl
     float Ac[15], bc[5], y[5];
 #pragma unroll
     for (int k = 1; k < 6; k++) {
-        float s = res[k] + cb.b[k];
+        float s = res[k] + (noslip ? 0.f : cb.AR[TRI(k, 0)] * (f[0] - old[0]));
 #pragma unroll
         for (int l = 1; l < 6; l++) {
-            float a = cb.AR[TRI(k, l)] - ((k == l && k < dim) ? cb.R[k] : 0.f);
+            float a = cb.AR[TRI(k, l)] - ((noslip && k == l && k < dim) ? cb.R[k] : 0.f);
             if (l <= k) Ac[TRI(k - 1, l - 1)] = a;
             s -= a * old[l];
         }
         bc[k - 1] = s;
     }
-    qcqp5(Ac, bc, cb.mu, cb.imu, old[0], cb.Lc, false, lam, y);
+    qcqp5(Ac, bc, cb.mu, cb.imu, f[0], cb.Lc, !noslip, lam, y);
 #pragma unroll
     for (int k = 1; k < 6; k++) f[k] = y[k - 1];
 }
 
-__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters) {
+// one Gauss-Seidel sweep over the scalar rows and the contact blocks (the hot loop; its own function so that its code
+// is contiguous and small)
+__device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float *scratch, int lane, bool noslip) {
+    int col = lane & 15, half = lane >> 4;
+    // scalar rows: every lane computes the (uniform) update, lanes < nt apply it
+    for (int r = 0; r < S.nsc; r++) {
+        bool floss = S.sc_lo[r] > -1e37f && S.sc_lo[r] < 0.f;
+        if (noslip && !floss) continue;
+        float f = S.sc_f[r], R = noslip ? 0.f : S.sc_R[r];
+        float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
+        float res = S.sc_b[r] + R * f + ja;
+        float x = fminf(fmaxf(f - res / (S.sc_A[r] + R), S.sc_lo[r]), S.sc_hi[r]);
+        float df = x - f;
+        __syncwarp();
+        int t = S.sc_tree[r];
+        if (lane < m.tree_dofnum[t]) S.acc[m.tree_dofadr[t] + lane] += S.sc_MJ[r * AV_TD + lane] * df;
+        if (lane == 0) S.sc_f[r] = x;
+        __syncwarp();
+    }
+    for (int c = 0; c < S.ncon; c++) {
+        int info = S.c_info[c], dim = (info >> 16) & 0xf;
+        if ((info >> 20) & 1) continue;
+        const float *blk = scratch + c * AV_CBLK;
+        int tr = S.c_tree[c], dof = tr_dof(tr, col);
+        const float *J = blk + AV_CB_J;
+        float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
+        CBlk cb;
+        cblk_load(blk, cb);
+        float res[6], old[6], f[6], df[6];
+        block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
+#pragma unroll
+        for (int k = 0; k < 6; k++) old[k] = S.c_f[6 * c + k];
+        float lam = S.c_lam[c];
+        contact_block_update(cb, dim, noslip, res, old, lam, f);
+#pragma unroll
+        for (int k = 0; k < 6; k++) df[k] = f[k] - old[k];
+        __syncwarp();
+        block_apply(S, j0, j1, j2, df, tr, lane);
+        if (lane < 6) {
+            float fv = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (k == lane) fv = f[k];
+            S.c_f[6 * c + lane] = fv;
+        }
+        if (lane == 6) S.c_lam[c] = lam;
+        __syncwarp();
+    }
+}
+
+__device__ AV_STAGE void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters) {
     int col = lane & 15, half = lane >> 4;
     // acc <- M^-1 J^T f_warm  (constraint part of the acceleration); dual cost of the warm start
     for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
@@ -410,12 +443,13 @@ __device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, i
         float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
         float res[6];
         block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
-        CBlk cb;
-        cblk_load(blk, cb);
+        // R (rows 0 | 1,2 | 3 | 4,5) and b straight from the block: the full CBlk is not needed here
+        float Rn = blk[AV_CB_PAR], Rf = blk[AV_CB_PAR + 1], Rt = blk[AV_CB_PAR + 2], Rr = blk[AV_CB_PAR + 3];
+        float Rk[6] = {Rn, Rf, Rf, Rt, Rr, Rr};
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             float f = S.c_f[6 * c + k];   // dead rows: f = 0
-            cost += f * (0.5f * (res[k] + cb.R[k] * f) + cb.b[k]);
+            cost += f * (0.5f * (res[k] + Rk[k] * f) + blk[AV_CB_B + k]);
         }
     }
     __syncwarp();
@@ -425,52 +459,5 @@ __device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, i
         for (int i = lane; i < AV_NCON * 6; i += 32) S.c_f[i] = 0.f;
         __syncwarp();
     }
-    for (int it = 0; it < iters + noslip_iters; it++) {
-        bool noslip = it >= iters;
-        // scalar rows: every lane computes the (uniform) update, lanes < nt apply it
-        for (int r = 0; r < S.nsc; r++) {
-            bool floss = S.sc_lo[r] > -1e37f && S.sc_lo[r] < 0.f;
-            if (noslip && !floss) continue;
-            float f = S.sc_f[r], R = noslip ? 0.f : S.sc_R[r];
-            float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
-            float res = S.sc_b[r] + R * f + ja;
-            float x = fminf(fmaxf(f - res / (S.sc_A[r] + R), S.sc_lo[r]), S.sc_hi[r]);
-            float df = x - f;
-            __syncwarp();
-            int t = S.sc_tree[r];
-            if (lane < m.tree_dofnum[t]) S.acc[m.tree_dofadr[t] + lane] += S.sc_MJ[r * AV_TD + lane] * df;
-            if (lane == 0) S.sc_f[r] = x;
-            __syncwarp();
-        }
-        for (int c = 0; c < S.ncon; c++) {
-            int info = S.c_info[c], dim = (info >> 16) & 0xf;
-            if ((info >> 20) & 1) continue;
-            const float *blk = scratch + c * AV_CBLK;
-            int tr = S.c_tree[c], dof = tr_dof(tr, col);
-            const float *J = blk + AV_CB_J;
-            float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
-            CBlk cb;
-            cblk_load(blk, cb);
-            float res[6], old[6], f[6], df[6];
-            block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
-#pragma unroll
-            for (int k = 0; k < 6; k++) old[k] = S.c_f[6 * c + k];
-            float lam = S.c_lam[c];
-            if (!noslip) contact_update(cb, res, old, lam, f);
-            else contact_noslip(cb, dim, res, old, lam, f);
-#pragma unroll
-            for (int k = 0; k < 6; k++) df[k] = f[k] - old[k];
-            __syncwarp();
-            block_apply(S, j0, j1, j2, df, tr, lane);
-            if (lane < 6) {
-                float fv = 0.f;
-#pragma unroll
-                for (int k = 0; k < 6; k++)
-                    if (k == lane) fv = f[k];
-                S.c_f[6 * c + lane] = fv;
-            }
-            if (lane == 6) S.c_lam[c] = lam;
-            __syncwarp();
-        }
-    }
+    for (int it = 0; it < iters + noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= iters);
 }

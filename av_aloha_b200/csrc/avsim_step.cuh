@@ -66,7 +66,7 @@ __device__ __forceinline__ int body_mask_has(const DevModel &m, int body, int do
 }
 
 // ------------------------------------------------------------------ K2: kinematics, lane = kinematic tree
-__device__ inline void stage_kinematics(const DevModel &m, EnvS &S, int lane) {
+__device__ AV_STAGE void stage_kinematics(const DevModel &m, EnvS &S, int lane) {
     if (lane < m.ntree) {
         int b0 = m.tree_bodyadr[lane], nb = m.tree_bodynum[lane];
         V3 org = v3(0, 0, 0);
@@ -185,7 +185,7 @@ __device__ inline void chol_block_solve(const float *Lb, int nt, float *x) {
     }
 }
 
-__device__ inline void stage_inertia(const DevModel &m, EnvS &S, int lane) {
+__device__ AV_STAGE void stage_inertia(const DevModel &m, EnvS &S, int lane) {
     for (int i = lane; i < AV_MBLK; i += 32) S.M[i] = 0.f;
     if (lane < m.ntree) {  // composite inertias, leaves to root
         int b0 = m.tree_bodyadr[lane], nb = m.tree_bodynum[lane];
@@ -259,7 +259,7 @@ __device__ inline void add_contact(const DevModel &m, EnvS &S, int slot, int g1,
     S.c_info[slot] = g1 | (g2 << 8) | (dim << 16) | (excluded << 20);
 }
 
-__device__ inline void stage_collision(const DevModel &m, EnvS &S, int lane, bool multiccd, Prof &pf) {
+__device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, int lane, bool multiccd, Prof &pf) {
     if (lane == 0) { S.ncon = 0; S.ncand_p = 0; S.ncand_c = 0; }
     __syncwarp();
     // broadphase: bounding spheres + world AABBs, pair list strided over lanes, warp-aggregated append
@@ -348,7 +348,7 @@ __device__ inline void stage_collision(const DevModel &m, EnvS &S, int lane, boo
 }
 
 // ------------------------------------------------------------------ K3b: velocity, bias, actuation, smooth acceleration
-__device__ inline void stage_smooth(const DevModel &m, EnvS &S, int lane) {
+__device__ AV_STAGE void stage_smooth(const DevModel &m, EnvS &S, int lane) {
     if (lane < m.ntree) {
         int b0 = m.tree_bodyadr[lane], nb = m.tree_bodynum[lane];
         S6 zero = {v3(0, 0, 0), v3(0, 0, 0)};
@@ -463,7 +463,7 @@ __device__ inline void emit_scalar_row(const DevModel &m, EnvS &S, int r, int d1
 }
 
 // rows in MuJoCo's order [equality | friction loss | violated joint limits]; row indices via ballots
-__device__ inline void stage_rows_scalar(const DevModel &m, EnvS &S, int lane) {
+__device__ AV_STAGE void stage_rows_scalar(const DevModel &m, EnvS &S, int lane) {
     const float BIG = 3.0e38f;
     if (lane < m.neq) {
         int e = lane;
@@ -511,7 +511,7 @@ __device__ inline void stage_rows_scalar(const DevModel &m, EnvS &S, int lane) {
 #include "avsim_solve.cuh"
 
 // ------------------------------------------------------------------ K7: Euler with implicit joint damping
-__device__ inline void stage_integrate(const DevModel &m, EnvS &S, int lane) {
+__device__ AV_STAGE void stage_integrate(const DevModel &m, EnvS &S, int lane) {
     float h = m.timestep;
     // total generalized force = smooth + constraint = smooth + M * acc   (acc = M^-1 J^T f)
     float tot = 0.f;
@@ -562,7 +562,7 @@ enum { CLS_LEFT = 1, CLS_RIGHT = 2, CLS_TABLE = 4, CLS_A = 8, CLS_B = 16, CLS_PI
 __device__ __forceinline__ int pair_hit(int c1, int c2, int ma, int mb) {
     return ((c1 & ma) && (c2 & mb)) || ((c2 & ma) && (c1 & mb));
 }
-__device__ inline int stage_reward(const DevModel &m, const EnvS &S, int lane, int &latch) {
+__device__ AV_STAGE int stage_reward(const DevModel &m, const EnvS &S, int lane, int &latch) {
     int flags = 0;  // bit0 tl, 1 tr, 2 a_table, 3 b_table, 4 a_b, 5 pins, 6 a_pinb
     for (int c = lane; c < S.ncon; c += 32) {
         int info = S.c_info[c], c1 = m.geom_class[info & 0xff], c2 = m.geom_class[(info >> 8) & 0xff];

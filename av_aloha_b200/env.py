@@ -1,0 +1,350 @@
+"""Host-side mirror of gym_guided_vision's environment API on top of the CUDA batch (C-ABI, csrc/).
+
+Same names, argument meaning and return conventions as the reference (gym_guided_vision/gym_guided_vision/env.py):
+
+  GuidedVisionEnv.reset / step / get_obs / get_reward / render / set_qpos / step_action / hide_middle_arm /
+  show_middle_arm / close, the five task subclasses, `make_sim_env`, `ENVS` + `register` (same ten ids and kwargs,
+  gym_guided_vision/__init__.py:4-101), plus `GuidedVisionVectorEnv`, a batched environment with gymnasium 0.29
+  `SyncVectorEnv` semantics (what lerobot's `rollout` / `eval_policy` are written against: eval.py:126-176).
+
+Every environment instance owns rows of one `capi.Batch`; all arithmetic (ctrl write, 20 substeps, reward, agent_pos)
+runs in the hand-written kernels.  There is no CPU path: constructing an environment without a CUDA device raises.
+gymnasium is optional (not installed in the build container): when importable the classes subclass gym.Env and use
+gym spaces, otherwise small stand-ins with the same attributes are used.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi, model_io
+
+try:  # pragma: no cover - gymnasium is absent in the build container
+    import gymnasium as gym
+    from gymnasium import spaces
+    _EnvBase = gym.Env
+except Exception:  # noqa: BLE001
+    gym = None
+
+    class _Box:
+        def __init__(self, low, high, shape, dtype):
+            self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), np.dtype(dtype)
+
+        def sample(self):
+            return np.zeros(self.shape, self.dtype)
+
+        def contains(self, x):
+            return np.shape(x) == self.shape
+
+    class _Dict(dict):
+        def __init__(self, d):
+            super().__init__(d)
+            self.spaces = self
+
+    class spaces:  # noqa: N801 - mirrors the gymnasium namespace
+        Box, Dict = _Box, _Dict
+
+    class _EnvBase:
+        metadata: dict = {}
+
+        def reset(self, seed=None, options=None):
+            if seed is not None:
+                self.np_random = np.random.default_rng(seed)
+
+        @property
+        def unwrapped(self):
+            return self
+
+
+# ---- reference constants.py:20-28
+SIM_DT = 0.04
+SIM_PHYSICS_DT = 0.002
+SIM_PHYSICS_ENV_STEP_RATIO = int(SIM_DT / SIM_PHYSICS_DT)
+LEFT_ARM_POSE = [0, -0.082, 1.06, 0, -0.953, 0, 0.02239]
+RIGHT_ARM_POSE = [0, -0.082, 1.06, 0, -0.953, 0, 0.02239]
+MIDDLE_ARM_POSE = [0, -0.8, 0.8, 0, 0.5, 0, 0]
+CAMERAS = ["zed_cam_left", "zed_cam_right", "wrist_cam_left", "wrist_cam_right", "overhead_cam", "worms_eye_cam"]
+RENDER_CAMERA = "overhead_cam"
+
+TASK_OF = {"InsertPeg": "insert_peg", "SlotInsertion": "slot_insertion", "SewNeedle": "sew_needle",
+           "TubeTransfer": "tube_transfer", "HookPackage": "hook_package"}
+
+# ---- object placement of the task resets, as (joint, lo[3], hi[3]) draws in the reference's np.random ORDER, dead draws
+# included (joint None), shared draws as a string alias.  reference env.py:478-493, 517-533, 608-624, 709-723, 796-808.
+_RESET_DRAWS = {
+    "insert_peg": [("peg_joint", [0.1, -0.1, 0.01], [0.2, 0.1, 0.01]), ("hole_joint", [-0.1, -0.1, 0.021], [-0.2, 0.1, 0.021])],
+    "slot_insertion": [("slot_joint", [-0.05, 0.1, 0.0], [0.05, 0.15, 0.0]), (None, [-0.05, 0.1, 0.0], [0.05, 0.15, 0.0]),
+                       ("stick_joint", [-0.08, -0.1, 0.0], [0.08, 0.0, 0.0])],
+    "sew_needle": [("needle_joint", [0.15, -0.025, 0.0], [0.2, 0.1, 0.0]), (None, [0.15, -0.025, 0.0], [0.2, 0.1, 0.0]),
+                   ("wall_joint", [-0.025, -0.025, 0.0], [0.025, 0.1, 0.0])],
+    "tube_transfer": [("ball_joint", [0.05, -0.05, 0.0], [0.1, 0.05, 0.0]), ("tube1_joint", "ball_joint", None),
+                      ("tube2_joint", [-0.1, -0.05, 0.0], [-0.05, 0.05, 0.0])],
+    "hook_package": [("hook_joint", [-0.1, 0.3, 0.2], [0.1, 0.3, 0.3]), ("package_joint", [-0.1, 0.0, 0.0], [0.1, 0.15, 0.0])],
+}
+
+
+def reference_reset_draws(task: str, free_joint_names, rng=None) -> np.ndarray:
+    """Object positions [nfree, 3] of one task reset, consuming `rng` (default: the GLOBAL np.random, like the reference)
+    in exactly the reference's order, dead draws included."""
+    rng = np.random if rng is None else rng
+    pos = {}
+    for joint, lo, hi in _RESET_DRAWS[task]:
+        if isinstance(lo, str):
+            pos[joint] = pos[lo]
+            continue
+        p = rng.uniform(np.asarray(lo, np.float64), np.asarray(hi, np.float64))
+        if joint is not None:
+            pos[joint] = p
+    return np.stack([pos[j] for j in free_joint_names])
+
+
+_MODEL_CACHE: dict = {}
+
+
+def _model(task, num_arms, device):
+    key = (task, num_arms, device)
+    if key not in _MODEL_CACHE:
+        _MODEL_CACHE[key] = capi.Model(model_io.model_path(task, num_arms), device)
+    return _MODEL_CACHE[key]
+
+
+def _check_cameras(cameras):
+    assert all(c in CAMERAS for c in cameras), f"Invalid camera names: {cameras}"
+    if len(cameras):
+        raise NotImplementedError("camera observations need the rasteriser kernel (avsim_render), which is not built yet; "
+                                  "pass cameras=[] (the reference allows it: env.py:868)")
+
+
+class GuidedVisionEnv(_EnvBase):
+    """One environment (reference env.py:32-406).  `task` replaces the reference's `xml` path."""
+
+    metadata = {"render_modes": ["rgb_array"], "render_fps": 1 / SIM_DT}
+    task = None
+    max_reward = 0
+
+    def __init__(self, task: str | None = None, num_arms: int = 3, cameras=(), observation_height: int = 480,
+                 observation_width: int = 640, device: int = 0, solver_iterations: int = 50, seed: int = 0):
+        assert num_arms in [2, 3], f"Invalid number of arms: {num_arms}"
+        self.task = task or self.task
+        self.cameras = list(cameras)
+        _check_cameras(self.cameras)
+        self.num_arms, self.num_joints = num_arms, 14 if num_arms == 2 else 21
+        self.observation_height, self.observation_width = observation_height, observation_width
+        self._model = _model(self.task, num_arms, device)
+        self._batch = capi.Batch(self._model, 1, seed=seed)
+        self._batch.set_options(solver_iters=solver_iterations)
+        self.max_reward = self._model.max_reward
+        self._free_joints = model_io.load_names(self.task, num_arms)["free_joint"]
+        self.observation_space = spaces.Dict({
+            "pixels": spaces.Dict({c: spaces.Box(low=0, high=255, shape=(observation_height, observation_width, 3),
+                                                 dtype=np.uint8) for c in self.cameras}),
+            "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float64)})
+        self.action_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float32)
+        self._agent = np.zeros((1, self.num_joints), np.float32)
+        self._reward = np.zeros((1,), np.int32)
+
+    # -- observation / reward (reference env.py:168-193)
+    def get_obs(self):
+        agent = self._batch.get(capi.AGENT_POS).cpu().numpy()[0].astype(np.float64)
+        return {"pixels": {}, "agent_pos": agent}
+
+    def get_reward(self):
+        return int(self._batch.get(capi.REWARD).cpu().numpy()[0])
+
+    def render(self):
+        raise NotImplementedError("render() needs the rasteriser kernel (avsim_render), which is not built yet")
+
+    # -- stepping (reference env.py:203-226, 255-269)
+    def step_action(self, action):
+        a = np.asarray(action, np.float32).reshape(1, self.num_joints)
+        self._batch.step_host(a, SIM_PHYSICS_ENV_STEP_RATIO, self._agent, self._reward)
+
+    def step(self, action):
+        self.step_action(action)
+        observation = {"pixels": {}, "agent_pos": self._agent[0].astype(np.float64)}
+        reward = int(self._reward[0])
+        return observation, reward, False, False, {"is_success": reward == self.max_reward}
+
+    # -- reset: home pose + task object placement drawn from the GLOBAL np.random in the reference's order
+    def reset(self, seed=None, options=None):
+        super().reset(seed=seed, options=options)
+        fp = reference_reset_draws(self.task, self._free_joints)
+        self._batch.reset(free_pos=fp[None])
+        return self.get_obs(), {"is_success": False}
+
+    def set_qpos(self, qpos):
+        self._batch.set(capi.QPOS, np.asarray(qpos, np.float32).reshape(1, -1))
+        self._batch.forward()
+
+    def hide_middle_arm(self):   # the 2-arm model is compiled with the middle arm parked (reference env.py:60-62,394-395)
+        pass
+
+    def show_middle_arm(self):
+        pass
+
+    def close(self):
+        if getattr(self, "_batch", None) is not None:
+            self._batch.close()
+            self._batch = None
+
+
+class InsertPegEnv(GuidedVisionEnv):
+    task = "insert_peg"
+
+
+class SlotInsertionEnv(GuidedVisionEnv):
+    task = "slot_insertion"
+
+
+class SewNeedleEnv(GuidedVisionEnv):
+    task = "sew_needle"
+
+
+class TubeTransferEnv(GuidedVisionEnv):
+    task = "tube_transfer"
+
+
+class HookPackageEnv(GuidedVisionEnv):
+    task = "hook_package"
+
+
+_TASK_CLASSES = {"insert_peg": InsertPegEnv, "slot_insertion": SlotInsertionEnv, "sew_needle": SewNeedleEnv,
+                 "tube_transfer": TubeTransferEnv, "hook_package": HookPackageEnv}
+
+
+def make_sim_env(task_name, **kwargs):
+    """reference env.py:18-30"""
+    for key, cls in _TASK_CLASSES.items():
+        if f"sim_{key}" in task_name:
+            return cls(**kwargs)
+    raise NotImplementedError
+
+
+# ---- registry (reference gym_guided_vision/__init__.py:4-101): same ids, same kwargs
+ENVS = []
+for _name in TASK_OF:
+    for _arms in (2, 3):
+        ENVS.append({"id": f"gym_guided_vision/{_name}-{_arms}Arms-v0", "task": TASK_OF[_name],
+                     "kwargs": {"num_arms": _arms, "cameras": CAMERAS if _arms == 3 else CAMERAS[:4],
+                                "observation_height": 480, "observation_width": 640}})
+
+
+def make(env_id: str, max_episode_steps: int | None = None, **kwargs):
+    """`gym.make` for the ten ids without needing gymnasium; kwargs override the registered defaults."""
+    spec = next((e for e in ENVS if e["id"] == env_id), None)
+    if spec is None:
+        raise KeyError(f"unknown environment id {env_id!r}")
+    kw = dict(spec["kwargs"])
+    kw.update(kwargs)
+    env = _TASK_CLASSES[spec["task"]](**kw)
+    env._max_episode_steps = max_episode_steps
+    return env
+
+
+def register():
+    """Register the ten ids with gymnasium (when it is installed) under the reference's names, pointing at this backend."""
+    if gym is None:
+        raise RuntimeError("gymnasium is not installed")
+    for e in ENVS:
+        cls = _TASK_CLASSES[e["task"]].__name__
+        gym.register(id=e["id"], entry_point=f"av_aloha_b200.env:{cls}", kwargs=e["kwargs"], nondeterministic=True)
+
+
+class GuidedVisionVectorEnv:
+    """B environments in lockstep behind gymnasium-0.29 `SyncVectorEnv` semantics.
+
+    What lerobot's rollout uses (lerobot/scripts/eval.py:126-176, 259-263, 321): `num_envs`, `reset(seed=list|int|None)`,
+    `step(actions[B, nj] f32) -> (obs, reward f64[B], terminated bool[B], truncated bool[B], info)`, truncation at
+    `max_episode_steps` followed by AUTO-RESET (the returned observation is the reset one; the last real observation and
+    info go to info["final_observation"][i] / info["final_info"][i], masks in info["_final_info"]), `call(name)`,
+    `unwrapped.metadata`, `close()`.  Environments are sharded across ranks by the caller (one instance per GPU).
+    """
+
+    metadata = GuidedVisionEnv.metadata
+
+    def __init__(self, task: str, num_envs: int, num_arms: int = 3, cameras=(), max_episode_steps: int = 300,
+                 device: int = 0, solver_iterations: int = 20, seed: int = 0, reference_rng: bool = False,
+                 observation_height: int = 480, observation_width: int = 640):
+        self.task = TASK_OF.get(task, task)
+        self.cameras = list(cameras)
+        _check_cameras(self.cameras)
+        self.num_envs, self.num_arms = int(num_envs), num_arms
+        self.num_joints = 14 if num_arms == 2 else 21
+        self._max_episode_steps = int(max_episode_steps)
+        self.reference_rng = reference_rng
+        self._model = _model(self.task, num_arms, device)
+        self._batch = capi.Batch(self._model, self.num_envs, seed=seed)
+        self._batch.set_options(solver_iters=solver_iterations)
+        self.max_reward = self._model.max_reward
+        self._free_joints = model_io.load_names(self.task, num_arms)["free_joint"]
+        self._elapsed = np.zeros(self.num_envs, np.int64)
+        self._agent = np.zeros((self.num_envs, self.num_joints), np.float32)
+        self._reward = np.zeros((self.num_envs,), np.int32)
+        self.single_observation_space = spaces.Dict({
+            "pixels": spaces.Dict({}),
+            "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float64)})
+        self.single_action_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float32)
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _obs(self):
+        return {"pixels": {}, "agent_pos": self._agent.astype(np.float64)}
+
+    def _reset_rows(self, mask):
+        fp = None
+        if self.reference_rng:   # host draws in the reference's np.random order, env by env (SyncVectorEnv loops envs)
+            fp = np.zeros((self.num_envs, len(self._free_joints), 3))
+            for e in np.nonzero(mask)[0]:
+                fp[e] = reference_reset_draws(self.task, self._free_joints)
+        self._batch.reset(mask=None if mask.all() else mask.astype(np.uint8), free_pos=fp)
+        self._elapsed[mask] = 0
+
+    def reset(self, seed=None, options=None):
+        self._reset_rows(np.ones(self.num_envs, bool))
+        self._agent[:] = self._batch.get(capi.AGENT_POS).cpu().numpy()
+        return self._obs(), {}
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, np.float32).reshape(self.num_envs, self.num_joints)
+        self._batch.step_host(a, SIM_PHYSICS_ENV_STEP_RATIO, self._agent, self._reward)
+        self._elapsed += 1
+        reward = self._reward.astype(np.float64)
+        terminated = np.zeros(self.num_envs, bool)
+        truncated = self._elapsed >= self._max_episode_steps
+        info = {}
+        if truncated.any():
+            final_obs = np.empty(self.num_envs, object)
+            final_info = np.empty(self.num_envs, object)
+            agent64 = self._agent.astype(np.float64)
+            for e in np.nonzero(truncated)[0]:
+                final_obs[e] = {"pixels": {}, "agent_pos": agent64[e].copy()}
+                final_info[e] = {"is_success": bool(self._reward[e] == self.max_reward), "TimeLimit.truncated": True}
+            info = {"final_observation": final_obs, "_final_observation": truncated.copy(),
+                    "final_info": final_info, "_final_info": truncated.copy()}
+            self._reset_rows(truncated)
+            fresh = self._batch.get(capi.AGENT_POS).cpu().numpy()
+            self._agent[truncated] = fresh[truncated]
+        else:
+            info = {"is_success": self._reward == self.max_reward, "_is_success": np.ones(self.num_envs, bool)}
+        return self._obs(), reward, terminated, truncated, info
+
+    def call(self, name, *args, **kwargs):
+        v = getattr(self, name)
+        if callable(v):
+            v = v(*args, **kwargs)
+            return v if isinstance(v, tuple) and len(v) == self.num_envs else tuple([v] * self.num_envs)
+        return tuple([v] * self.num_envs)
+
+    def render(self):
+        raise NotImplementedError("render() needs the rasteriser kernel (avsim_render), which is not built yet")
+
+    def success_and_max_reward(self):
+        """Per-env (reward == max_reward, reward) of the last step as CUDA tensors: the payload of the one collective of the
+        path (rank-sharded rollouts all_gather these at episode end)."""
+        return self._batch.get(capi.SUCCESS), self._batch.get(capi.REWARD)
+
+    def close(self):
+        if getattr(self, "_batch", None) is not None:
+            self._batch.close()
+            self._batch = None

@@ -2,10 +2,14 @@
 """bench.py -- env-steps/sec of the batched env.step() hot path (BASELINE.json metric).
 
 Workload (BASELINE.json configs[1]): SlotInsertion-3Arms-v0, 4096 environments per GPU in
-lockstep, no render, synthetic scripted joint-target actions (home -> reach above the stick -> close -> lift, plus
-per-env N(0, 0.01 rad) noise, seed 1234); one "step" = one env.step over the whole batch = 20 physics substeps of
-2 ms + reward + agent_pos (reference gym_guided_vision/env.py:203-226).  Episodes are 300 steps
-(sim_slot_insertion_3arms.yaml:17); the batch is reset (device-side Philox draw) when an episode ends.
+lockstep, no render.  Actions are a synthetic scripted policy that performs the task (av_aloha_b200/workload.py: reach,
+pinch a slot rail with the left hand, grasp the stick with the right, lift, carry over the slot, lower into the gap;
+waypoints IK-solved per environment for object placements drawn from the reference's reset ranges, + N(0, 0.01 rad)
+joint noise, seed 1234).  One "step" = one env.step over the whole batch = 20 physics substeps of 2 ms + reward +
+agent_pos (reference gym_guided_vision/env.py:203-226), including the auto-reset of the environments whose 300-step
+episode (sim_slot_insertion_3arms.yaml:17) ended on that step.  Episodes are STAGGERED: environment e starts at script
+phase (e * 300) // B, so every timed step sees the whole episode's mix of free motion, grasping and insertion and
+costs the episode average (an untimed 300-step pre-roll brings the batch to that steady state).
 
 Arms:
   default            : the CUDA path through the C-ABI (libavsim.so).  `value` = device-resident actions;
@@ -39,42 +43,24 @@ HOME = np.array([0, -0.082, 1.06, 0, -0.953, 0, 0.02239] * 2 + [0, -0.8, 0.8, 0,
 METRIC = "env-steps/sec SlotInsertion-3Arms batch=4096"
 
 
-def script_actions(T, B, seed, xp=np):
-    """Joint-target script [T, B, 21] float32: reach (0-100), close gripper (100-130), lift (130-200), hold."""
-    rng = np.random.default_rng(seed)
-    home = HOME.copy()
-    home[6] = home[13] = 1.0                          # gripper open (normalised)
-    # a reach pose that brings both grippers down toward the table centre where stick / slot are placed
-    reach = home.copy()
-    reach[0:6] = [0.10, 0.55, 0.65, 0.0, 0.35, 0.0]
-    reach[7:13] = [-0.10, 0.55, 0.65, 0.0, 0.35, 0.0]
-    lift = reach.copy()
-    lift[1] -= 0.35; lift[8] -= 0.35
-    noise = rng.normal(0.0, 0.01, size=(B, 21))
-    noise[:, [6, 13]] = 0.0
-    offs = rng.normal(0.0, 0.08, size=(B, 21)) * np.array([1, 1, 1, 0, 1, 0, 0] * 2 + [0.3] * 7)
-    acts = np.empty((T, B, 21), np.float32)
-    for t in range(T):
-        if t < 100:
-            s = t / 100.0
-            a = home + s * (reach - home)
-            g = 1.0
-        elif t < 130:
-            a = reach.copy()
-            g = 1.0 - (t - 100) / 30.0
-        elif t < 200:
-            s = (t - 130) / 70.0
-            a = reach + s * (lift - reach)
-            g = 0.0
-        else:
-            a = lift.copy()
-            g = 0.0
-        w = min(1.0, t / 100.0)
-        row = a[None, :] + noise + w * offs
-        row[:, 6] = g
-        row[:, 13] = g
-        acts[t] = row
-    return acts
+def make_workload(B, seed):
+    """(object positions [B,2,3] f64, staggered actions [T,B,21] f32, reset masks [T,B] u8, phases [B])."""
+    from av_aloha_b200 import workload
+
+    obj = workload.sample_object_positions(B, seed)
+    acts = workload.slot_insertion_script(EPISODE_LEN, obj, seed)
+    phase = (np.arange(B) * EPISODE_LEN) // B
+    idx = (np.arange(EPISODE_LEN)[:, None] + phase[None, :]) % EPISODE_LEN          # script index of env e at loop step t
+    stag = np.take_along_axis(acts, idx[:, :, None], axis=0)
+    masks = (idx == 0).astype(np.uint8)                                              # episode of env e (re)starts at step t
+    return obj, np.ascontiguousarray(stag), masks, phase
+
+
+def script_actions(T, B, seed):
+    """un-staggered stream [T, B, 21] (tools/ and tests use it)"""
+    from av_aloha_b200 import workload
+
+    return workload.slot_insertion_script(T, workload.sample_object_positions(B, seed), seed)
 
 
 class ClockSampler:
@@ -135,36 +121,42 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle)
 def cpu_steps_per_sec(n_envs, n_steps, threads, solver_iters, seed=1234):
-    """The CPU path (fp64 oracle) on `threads` host threads: n_envs environments x n_steps env.steps of the bench
-    workload (same script, same solver sweep count).  ctypes releases the GIL, so threads run in parallel."""
+    """The CPU path (fp64 oracle) on `threads` host threads: a sample of n_envs environments of the bench workload, their
+    episode phases spread evenly over the 300-step script.  Each environment is first rolled (untimed) from reset to
+    its phase, then n_steps consecutive env.steps are timed.  ctypes releases the GIL, so threads run in parallel."""
     from concurrent.futures import ThreadPoolExecutor
 
-    from av_aloha_b200 import model_io
+    from av_aloha_b200 import model_io, workload
     from oracle.oracle import OracleEnv, OracleModel
 
     path = model_io.model_path(TASK, ARMS)
     om = OracleModel(path)
-    acts = script_actions(EPISODE_LEN, n_envs, seed).astype(np.float64)
-    rng = np.random.default_rng(seed)
+    obj = workload.sample_object_positions(n_envs, seed)
+    acts = workload.slot_insertion_script(EPISODE_LEN, obj, seed).astype(np.float64)
+    phase = (np.arange(n_envs) * EPISODE_LEN) // n_envs
     envs = []
     for e in range(n_envs):
         o = OracleEnv(om)
         o.set_options(max_iter=solver_iters, tol=0.0)
-        fp = np.array([[rng.uniform(-0.05, 0.05), rng.uniform(0.1, 0.15), 0.0],
-                       [rng.uniform(-0.08, 0.08), rng.uniform(-0.1, 0.0), 0.0]])
-        o.reset(free_pos=fp)
+        o.reset(free_pos=obj[e])
         envs.append(o)
-    # sample the script across the episode so free motion and contact phases are both represented
-    ts = np.linspace(0, EPISODE_LEN - 1, n_steps).astype(int)
 
-    def run(e):
-        for t in ts:
+    def preroll(e):
+        for t in range(phase[e]):
             envs[e].step(acts[t, e])
 
-    t0 = time.perf_counter()
+    def run(e):
+        for k in range(n_steps):
+            t = (phase[e] + k) % EPISODE_LEN
+            if t == 0:
+                envs[e].reset(free_pos=obj[e])
+            envs[e].step(acts[t, e])
+
     with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(preroll, range(n_envs)))
+        t0 = time.perf_counter()
         list(ex.map(run, range(n_envs)))
-    dt = time.perf_counter() - t0
+        dt = time.perf_counter() - t0
     return n_envs * n_steps / dt, dt
 
 
@@ -173,7 +165,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_envs = max(cores, 8)
+    n_envs = 2 * max(cores, 4)
     per_step_envs = n_envs
     vals = []
     total = args.warmup + args.steps
@@ -185,11 +177,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step_envs / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"SlotInsertion-3Arms-v0 no render, scripted reach/grasp actions, sample of {n_envs} envs "
-                               f"x {total} env.steps spread over the 300-step episode (of the B=4096 workload)",
+        "config": {"workload": f"SlotInsertion-3Arms-v0 no render, scripted grasp/insert policy, sample of {n_envs} envs "
+                               f"x {total} consecutive env.steps, episode phases spread over the 300-step script "
+                               f"(of the B=4096 staggered workload)",
                    "solver_iters": args.solver_iters, "nsubsteps": 20},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_envs} envs x {total} env.steps, fp64 CPU restatement (MuJoCo not installable offline)"},
+                         "sample": f"{n_envs} envs x {total} env.steps at staggered episode phases, fp64 CPU restatement of the "
+                                   f"pipeline (MuJoCo not installable offline), {args.solver_iters} PGS sweeps + 3 noslip"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -215,8 +209,11 @@ def run_gpu(args):
     model = capi.Model(model_io.model_path(TASK, ARMS), local)
     batch = capi.Batch(model, B, seed=1234 + rank)
     batch.set_options(solver_iters=args.solver_iters)
-    acts_np = script_actions(EPISODE_LEN, B, 1234 + rank)
+    obj, acts_np, masks_np, phase = make_workload(B, 1234 + rank)
     acts = torch.as_tensor(acts_np, device=dev)                       # [T, B, 21] resident in HBM
+    masks = torch.as_tensor(masks_np, device=dev)                     # [T, B] u8: envs whose episode restarts at step t
+    mask_any = masks_np.any(axis=1)
+    fp_dev = torch.as_tensor(obj.astype(np.float32), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def barrier():
@@ -227,25 +224,35 @@ def run_gpu(args):
     state = {"t": 0}
 
     def advance():
-        if state["t"] == EPISODE_LEN:
-            batch.reset()
-            state["t"] = 0
-        t = state["t"]
+        t = state["t"] % EPISODE_LEN
         state["t"] += 1
         return t
 
-    def dev_step():
-        batch.step(acts[advance()])
+    def dev_step(t):
+        if mask_any[t]:
+            batch.reset(mask=masks[t], free_pos=fp_dev)
+        batch.step(acts[t])
 
     agent_out = np.empty((B, model.njoints), np.float32)
     rew_out = np.empty((B,), np.int32)
 
-    def host_step():
-        batch.step_host(acts_np[advance()], agent_pos_out=agent_out, reward_out=rew_out)
+    def host_step(t):
+        if mask_any[t]:
+            batch.reset(mask=masks[t], free_pos=fp_dev)
+        batch.step_host(acts_np[t], agent_pos_out=agent_out, reward_out=rew_out)
+
+    # ---- untimed pre-roll: one full script length brings every environment through its first wrap (reset at script
+    # index 0), after which the batch holds the steady-state mix of episode phases
+    batch.reset(free_pos=fp_dev)
+    p0 = time.perf_counter()
+    for _ in range(args.preroll):
+        dev_step(advance())
+    torch.cuda.synchronize()
+    preroll_s = time.perf_counter() - p0
 
     # ---- device-resident arm: per-step CUDA events on the launching (current) stream, L2 flushed between steps
     for _ in range(args.warmup):
-        dev_step()
+        dev_step(advance())
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -257,9 +264,8 @@ def run_gpu(args):
     for k in range(args.steps):
         flush.zero_()
         t = advance()
-        a = acts[t]
         ev[k][0].record()
-        batch.step(a)
+        dev_step(t)
         ev[k][1].record()
     barrier()
     wall = time.perf_counter() - w0
@@ -270,16 +276,17 @@ def run_gpu(args):
     n_bad = int((status & 1).sum().item())
     n_ovf = int((status & 2 != 0).sum().item())
     ncon_mean = float(batch.get(capi.NCON).float().mean().item())
-    rew_max = int(batch.get(capi.REWARD).max().item())
+    rew = batch.get(capi.REWARD)
+    rew_max, rew_mean = int(rew.max().item()), float(rew.float().mean().item())
 
     # ---- end-to-end arm: host numpy buffers through avsim_step_host, copies inside the timed region
     for _ in range(min(args.warmup, 3)):
-        host_step()
+        host_step(advance())
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        host_step()
+        host_step(advance())
     e1.record()
     barrier()
     e2e_ms = float(e0.elapsed_time(e1))
@@ -306,8 +313,9 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kern_avg_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"SlotInsertion-3Arms-v0 batch={B}/GPU lockstep, no render, scripted reach/grasp joint targets "
-                                   f"+ N(0,0.01) noise, 300-step episodes", "batch_per_gpu": B, "nsubsteps": 20,
+            "config": {"workload": f"SlotInsertion-3Arms-v0 batch={B}/GPU lockstep, no render, scripted grasp/lift/insert policy "
+                                   f"(IK-solved joint targets + N(0,0.01) noise), 300-step episodes staggered over the batch, "
+                                   f"auto-reset inside the step", "batch_per_gpu": B, "nsubsteps": 20,
                        "solver_iters": args.solver_iters, "noslip_iters": 3, "parallelism": f"env-sharded x{world}",
                        "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
                        "timing": "sum of per-step CUDA event pairs on the launching stream, max over ranks"},
@@ -319,14 +327,15 @@ def run_gpu(args):
                          "note": "latency/FP32-ALU bound by construction (SURVEY.md 8d): 1032 algorithmic bytes per env-step"},
             "clocks": clocks,
             "health": {"blown_up_envs": n_bad, "contact_overflow_envs": n_ovf, "ncon_mean": ncon_mean,
-                       "reward_max": rew_max, "successes": n_succ, "wall_s": wall},
+                       "reward_max": rew_max, "reward_mean": rew_mean, "successes": n_succ, "wall_s": wall,
+                       "preroll_steps": args.preroll, "preroll_s": preroll_s},
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
-            n_envs, n_steps = max(cores, 8), 12
+            n_envs, n_steps = 2 * max(cores, 4), 10
             v, dt = cpu_steps_per_sec(n_envs, n_steps, cores, args.solver_iters)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n_envs} envs x {n_steps} env.steps spread over the episode, {dt:.1f} s, "
+                                    "sample": f"{n_envs} envs x {n_steps} env.steps at staggered episode phases, {dt:.1f} s timed, "
                                               f"fp64 CPU restatement (MuJoCo not installable offline)"}
         print(json.dumps(line))
     batch.close()
@@ -343,6 +352,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--solver-iters", type=int, default=20, dest="solver_iters")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--preroll", type=int, default=EPISODE_LEN, help="untimed steps that bring the staggered batch to steady state")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -235,6 +235,7 @@ typedef struct ora_data {
     double qacc[NV_MAX], qfrc_constraint[NV_MAX];
     int solver_iters;
     int reward;
+    long *pair_hist;   /* optional [npair] histogram of pairs reaching the narrowphase (diagnostics) */
 } ora_data;
 
 ora_data *ora_data_new(const ora_model *m) {
@@ -250,7 +251,12 @@ void ora_data_free(ora_data *d) {
     if (!d) return;
     free(d->A);
     free(d->MinvJT);
+    free(d->pair_hist);
     free(d);
+}
+long *ora_pair_hist(ora_data *d) {
+    if (!d->pair_hist) d->pair_hist = (long *)calloc((size_t)d->m->npair, sizeof(long));
+    return d->pair_hist;
 }
 void ora_set_options(ora_data *d, int max_iter, double tol, int noslip_iter, int multiccd, int warmstart) {
     d->opt.max_iter = max_iter; d->opt.tol = tol; d->opt.noslip_iter = noslip_iter; d->opt.multiccd = multiccd;

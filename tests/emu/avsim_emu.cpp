@@ -96,7 +96,7 @@ int *emu_i(EmuBatch *b, int k) {
 }
 void emu_forward(EmuBatch *b) {
     for (int e = 0; e < b->st.num_envs; e++)
-        emu::run_block(e, b->st.num_envs, [&]() { avsim_forward_kernel(b->pk.dm, b->st); });
+        emu::run_block(e, b->st.num_envs, [&]() { avsim_forward_kernel(b->pk.dm, b->st, nullptr); });
 }
 void emu_step(EmuBatch *b, const float *action, int nsub) {
     for (int e = 0; e < b->st.num_envs; e++)

@@ -18,6 +18,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__
@@ -68,6 +69,7 @@ static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::exchange(0); }
+static inline void __syncthreads() { emu::exchange(0); }   // one warp per emulated block
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::exchange((uint32_t)v)[src & 31]; }
 static inline float __shfl_sync(unsigned, float v, int src) { return u2f(emu::exchange(f2u(v))[src & 31]); }
 static inline float __shfl_sync(unsigned, float v, int src, int width) {

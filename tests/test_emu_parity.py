@@ -1,0 +1,60 @@
+"""CPU-only check of the step kernel's SOURCE: csrc/*.cuh compiled for the host by the warp-emulation harness
+(tests/emu, 32 cooperative fibers per warp) against the fp64 oracle.  Same tolerances as the GPU parity tests
+(tests/test_gpu_parity.py); the harness is test infrastructure, not a product path."""
+import numpy as np
+import pytest
+
+HOME = np.array([0, -0.082, 1.06, 0, -0.953, 0, 0.02239] * 2 + [0, -0.8, 0.8, 0, 0.5, 0, 0])
+
+
+@pytest.fixture(scope="module")
+def ctx(slot_model_path):
+    from oracle.oracle import OracleEnv, OracleModel
+    from tests.emu.emu import EmuBatch
+    return EmuBatch, OracleModel(slot_model_path), OracleEnv, slot_model_path
+
+
+def _fp(B, rng):
+    return np.stack([np.array([[rng.uniform(-0.05, 0.05), rng.uniform(0.1, 0.15), 0.0],
+                               [rng.uniform(-0.08, 0.08), rng.uniform(-0.1, 0.0), 0.0]]) for _ in range(B)])
+
+
+def test_forward_random_state_converged(ctx):
+    """random joint offsets + velocities, objects resting on the table: contacts, equality, friction-loss rows all live"""
+    EmuBatch, om, OracleEnv, path = ctx
+    B = 4
+    rng = np.random.default_rng(0)
+    fp = _fp(B, rng)
+    eb = EmuBatch(path, B)
+    eb.set_options(150)
+    eb.reset(fp)
+    eb.qpos[:, :23] += rng.normal(0, 0.05, size=(B, 23)).astype(np.float32)
+    eb.qvel[:] = rng.normal(0, 0.3, size=(B, eb.nv))
+    eb.forward()
+    for e in range(B):
+        o = OracleEnv(om)
+        o.reset(free_pos=fp[e])
+        o.qpos[:] = eb.qpos[e]
+        o.qvel[:] = eb.qvel[e]
+        o.forward()
+        assert o.ncon == eb.ncon[e]
+        scale = max(1.0, np.abs(o.qacc).max())
+        tol = 1e-2 if o.ncon else 1e-4
+        assert np.abs(eb.qfrc_bias[e] - o.qfrc_bias).max() <= 1e-4 * max(1.0, np.abs(o.qfrc_bias).max())
+        assert np.abs(eb.qacc[e] - o.qacc).max() <= tol * scale
+
+
+def test_one_env_step_resting_contacts(ctx):
+    EmuBatch, om, OracleEnv, path = ctx
+    fp = np.array([[[0.01, 0.12, 0.0], [0.02, -0.05, 0.0]]])
+    eb = EmuBatch(path, 1)
+    eb.set_options(50)
+    eb.reset(fp)
+    act = HOME.copy()
+    act[6] = act[13] = 1.0
+    o = OracleEnv(om)
+    o.reset(free_pos=fp[0])
+    eb.step(act[None].astype(np.float32), 20)
+    r = o.step(act)
+    assert eb.ncon[0] == o.ncon and eb.reward[0] == r and eb.status[0] == 0
+    assert np.abs(eb.qpos[0] - o.qpos).max() <= 1e-4

@@ -1,0 +1,96 @@
+"""CPU-only checks of the host side: reset draw order against vectors produced by executing the reference's own reset
+code (tools/gen_reset_golden.py), the registry surface, the C-ABI library's exports, and model tables against the
+constants the reference states."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "reset_golden.json")
+
+
+@pytest.mark.parametrize("task", ["insert_peg", "slot_insertion", "sew_needle", "tube_transfer", "hook_package"])
+def test_reset_draws_follow_reference_rng_order(task):
+    from av_aloha_b200 import env, model_io
+    gold = json.load(open(GOLD))[task]
+    free = model_io.load_names(task, 3)["free_joint"]
+    assert sorted(free) == sorted(gold["joints"])
+    for case in gold["cases"]:
+        np.random.seed(case["seed"])
+        for ep in case["episodes"]:                      # consecutive resets share the global stream, dead draws included
+            fp = env.reference_reset_draws(task, free)
+            for k, j in enumerate(free):
+                assert np.array_equal(fp[k], np.array(ep[j][:3])), (task, j)
+                assert ep[j][3:] == [1.0, 0.0, 0.0, 0.0]
+
+
+def test_device_reset_ranges_match_reference_ranges():
+    """the Philox device reset samples the same boxes the reference samples (model tables reset_lo / reset_hi)"""
+    from av_aloha_b200 import env, model_io
+    for task, draws in env._RESET_DRAWS.items():
+        avm = model_io.load_avm(model_io.model_path(task, 3))
+        free = model_io.load_names(task, 3)["free_joint"]
+        table = {j: (lo, hi) for j, lo, hi in draws if j is not None}
+        for k, j in enumerate(free):
+            lo, hi = table[j]
+            if isinstance(lo, str):
+                lo, hi = table[lo]
+                assert avm["reset_draw"][k] == free.index(table[j][0])      # shares the other joint's draw
+            assert np.allclose(avm["reset_lo"][k], lo) and np.allclose(avm["reset_hi"][k], hi)
+
+
+def test_registry_matches_reference_ids():
+    from av_aloha_b200 import env
+    ids = [e["id"] for e in env.ENVS]
+    assert len(ids) == 10 and len(set(ids)) == 10
+    for name in ("InsertPeg", "SlotInsertion", "SewNeedle", "TubeTransfer", "HookPackage"):
+        for arms in (2, 3):
+            e = next(x for x in env.ENVS if x["id"] == f"gym_guided_vision/{name}-{arms}Arms-v0")
+            assert e["kwargs"]["num_arms"] == arms
+            assert len(e["kwargs"]["cameras"]) == (6 if arms == 3 else 4)
+            assert (e["kwargs"]["observation_height"], e["kwargs"]["observation_width"]) == (480, 640)
+    assert env.SIM_PHYSICS_ENV_STEP_RATIO == 20
+    assert env.GuidedVisionEnv.metadata["render_fps"] == pytest.approx(25.0)
+
+
+def test_cabi_exports_every_declared_symbol():
+    """libavsim.so loads without a GPU and exports every function include/avsim.h declares (no compute call here)."""
+    from av_aloha_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "avsim.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(avsim_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/avsim.h but not exported"
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    # error path without a device: null arguments are rejected, message is readable
+    lib.avsim_last_error.restype = ctypes.c_char_p
+    lib.avsim_model_dim.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    assert lib.avsim_model_dim(None, b"nq") < 0
+    assert b"null" in lib.avsim_last_error()
+
+
+def test_model_tables_match_reference_constants():
+    """sizes and actuation constants SURVEY.md 8 / Appendix B derive from aloha_sim.xml"""
+    from av_aloha_b200 import model_io
+    for task, nq, nv in (("slot_insertion", 37, 35), ("tube_transfer", 44, 41), ("hook_package", 37, 35)):
+        for arms in (2, 3):
+            m = model_io.load_avm(model_io.model_path(task, arms))
+            assert len(m["qpos0"]) == nq and len(m["dof_damping"]) == nv and len(m["act_kp"]) == 21
+            assert m["timestep"][0] == 0.002 and m["impratio"][0] == 100 and m["noslip_iterations"][0] == 3
+            assert m["num_arms"][0] == arms
+    m = model_io.load_avm(model_io.model_path("slot_insertion", 3))
+    assert np.allclose(m["act_kp"][:7], [43, 265, 227, 78, 37, 10.4, 2000])
+    assert np.allclose(m["act_ctrl_lo"][6], 0.002) and np.allclose(m["act_ctrl_hi"][6], 0.037)
+    assert np.allclose(sorted(set(np.round(m["dof_frictionloss"][m["dof_frictionloss"] > 0], 3))), [1.15, 2.0])
+    assert (m["dof_frictionloss"] > 0).sum() == 6 and len(m["eq_dof1"]) == 2
+    # home pose of the middle arm parks out of view in the 2-arm model (reference env.py:60-62)
+    m2 = model_io.load_avm(model_io.model_path("slot_insertion", 2))
+    names = model_io.load_names("slot_insertion", 2)
+    b = names["body"].index("middle_base_link")
+    assert np.allclose(m2["body_pos"][b], [0, -2.4, -0.4])
