@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("AVSIM_LIB") or os.path.join(_HERE, "csrc", "libavsim.
 
 # avsim_field
 QPOS, QVEL, CTRL, WARMSTART, AGENT_POS, REWARD, SUCCESS, NCON, CONTACTS, STATUS, LATCH, QACC, XPOS, QFRC_BIAS, \
-    QACC_SMOOTH, MASS_DIAG = range(16)
+    QACC_SMOOTH, MASS_DIAG, ENV_CYCLES = range(17)
 MAX_CONTACTS = 40
 
 SYMBOLS = [
@@ -146,7 +146,7 @@ class Batch:
             SUCCESS: (None, torch.int32), NCON: (None, torch.int32), CONTACTS: ((MAX_CONTACTS, 16), torch.float32),
             STATUS: (None, torch.int32), LATCH: (None, torch.int32), QACC: (m.nv, torch.float32),
             XPOS: ((m.nbody, 3), torch.float32), QFRC_BIAS: (m.nv, torch.float32), QACC_SMOOTH: (m.nv, torch.float32),
-            MASS_DIAG: (m.nv, torch.float32),
+            MASS_DIAG: (m.nv, torch.float32), ENV_CYCLES: (None, torch.int64),
         }
 
     def close(self):

@@ -14,11 +14,9 @@
 #include "avsim_kernels.cuh"
 #include "avsim_model_pack.h"
 
+#define AV_SORT_MAX 8192
 #ifndef AV_DEFAULT_WARPS
-#define AV_DEFAULT_WARPS 1
-#endif
-#ifndef AV_DEFAULT_SYNC
-#define AV_DEFAULT_SYNC 0
+#define AV_DEFAULT_WARPS 14
 #endif
 
 static thread_local char g_err[512] = "";
@@ -101,7 +99,7 @@ struct avsim_batch {
     const avsim_model *model;
     BatchState st;
     cudaStream_t stream;
-    int grid, warps;
+    int grid, fwd_grid, warps;
     int64_t launches = 0;
     std::vector<void *> allocs;
     float *h_action = nullptr, *h_agent = nullptr;   // pinned staging for the host-buffer path
@@ -134,7 +132,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
               dalloc(b, &s.status, B) && dalloc(b, &s.latch, B) && dalloc(b, &s.ncon, B) && dalloc(b, &s.episode, B) &&
               dalloc(b, &s.contacts, B * AV_NCON * 16) && dalloc(b, &s.qacc, B * d.nv) && dalloc(b, &s.xpos, B * 3 * d.nbody) &&
               dalloc(b, &s.qfrc_bias, B * d.nv) && dalloc(b, &s.qacc_smooth, B * d.nv) && dalloc(b, &s.mass_diag, B * d.nv) &&
-              dalloc(b, &s.scratch, B * AV_SCRATCH_FLOATS) && dalloc(b, &b->d_action, B * d.nj_obs);
+              dalloc(b, &s.scratch, B * AV_SCRATCH_FLOATS) && dalloc(b, &s.env_cycles, B) && dalloc(b, &s.order, B) && dalloc(b, &s.queue, 1) && dalloc(b, &b->d_action, B * d.nj_obs);
     if (!ok) { fail(AVSIM_ERR_CUDA, "avsim_create: device allocation failed"); avsim_destroy(b); return nullptr; }
     if (cudaMallocHost(&b->h_action, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
         cudaMallocHost(&b->h_agent, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
@@ -143,20 +141,23 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
         avsim_destroy(b);
         return nullptr;
     }
-    // block shape: W warps = W environments per block (diagnostic overrides: AVSIM_WARPS, AVSIM_SYNC)
-    const char *ew = getenv("AVSIM_WARPS"), *es = getenv("AVSIM_SYNC");
-    b->warps = ew ? atoi(ew) : AV_DEFAULT_WARPS;
-    s.sync = es ? atoi(es) : AV_DEFAULT_SYNC;
-    if (b->warps < 1 || b->warps > AV_MAX_WARPS) { fail(AVSIM_ERR_ARG, "avsim_create: AVSIM_WARPS out of range"); avsim_destroy(b); return nullptr; }
-    int smem = (int)sizeof(EnvS) * b->warps;
-    CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int per_sm = 0, sms = 0;
-    CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, avsim_step_kernel, 32 * b->warps, smem));
+    // step kernel: persistent blocks of W warps (W environments in lockstep, see avsim_kernels.cuh); W x sizeof(EnvS)
+    // of dynamic shared memory.  Diagnostic overrides: AVSIM_WARPS (warps per block), AVSIM_BLOCKS (blocks per SM).
+    const char *ew = getenv("AVSIM_WARPS"), *eb = getenv("AVSIM_BLOCKS");
+    int sms = 0, smem_sm = 0, smem_blk = 0;
     CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
-    if (per_sm < 1) { fail(AVSIM_ERR_CUDA, "avsim_create: step kernel does not fit on an SM"); avsim_destroy(b); return nullptr; }
-    // persistent: a multiple of the SM count, looping over envs
+    CUP(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device));
+    CUP(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+    int esz = (int)sizeof(EnvS);
+    b->warps = ew ? atoi(ew) : AV_DEFAULT_WARPS;
+    b->warps = std::max(1, std::min(b->warps, std::min(AV_MAX_WARPS, (smem_blk - 64) / esz)));
+    int per_sm = eb ? atoi(eb) : std::max(1, smem_sm / (b->warps * esz + 1024));
+    per_sm = std::max(1, std::min(per_sm, smem_sm / (b->warps * esz + 1024)));
+    CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->warps * esz));
+    CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
+    CUP(cudaFuncSetAttribute(avsim_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SORT_MAX * (int)sizeof(unsigned long long)));
     b->grid = std::min((num_envs + b->warps - 1) / b->warps, per_sm * sms);
+    b->fwd_grid = std::min(num_envs, 8 * sms);
     if (avsim_reset(b, nullptr, nullptr) != 0) { avsim_destroy(b); return nullptr; }
     return b;
 }
@@ -180,7 +181,7 @@ extern "C" int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_it
 }
 
 static int launch_forward(avsim_batch *b, const uint8_t *mask_dev = nullptr) {
-    avsim_forward_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->warps, b->stream>>>(b->model->dm, b->st, mask_dev);
+    avsim_forward_kernel<<<b->fwd_grid, 32, sizeof(EnvS), b->stream>>>(b->model->dm, b->st, mask_dev);
     b->launches++;
     CU(cudaGetLastError());
     return AVSIM_OK;
@@ -199,8 +200,13 @@ extern "C" int avsim_reset(avsim_batch *b, const uint8_t *mask_dev, const float 
 extern "C" int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps) {
     if (!b || nsubsteps < 0) return fail(AVSIM_ERR_ARG, "avsim_step: bad arguments");
     CU(cudaSetDevice(b->model->device));
+    // queue order: costliest environment of the previous step first (single-block sort up to 8192 environments)
+    int n = b->st.num_envs, n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    if (n2 <= AV_SORT_MAX) avsim_order_kernel<<<1, 1024, n2 * sizeof(unsigned long long), b->stream>>>(b->st, n2);
+    else avsim_identity_order_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->st);
     avsim_step_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->warps, b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
-    b->launches++;
+    b->launches += 2;
     CU(cudaGetLastError());
     return AVSIM_OK;
 }
@@ -231,6 +237,7 @@ static int field_ptr(avsim_batch *b, int field, void **p, size_t *bytes) {
     case AVSIM_QFRC_BIAS: *p = s.qfrc_bias; *bytes = B * d.nv * 4; break;
     case AVSIM_QACC_SMOOTH: *p = s.qacc_smooth; *bytes = B * d.nv * 4; break;
     case AVSIM_MASS_DIAG: *p = s.mass_diag; *bytes = B * d.nv * 4; break;
+    case AVSIM_ENV_CYCLES: *p = s.env_cycles; *bytes = B * 8; break;
     default: return fail(AVSIM_ERR_ARG, "unknown field");
     }
     return AVSIM_OK;

@@ -21,7 +21,8 @@
 #define AV_NCON 40      // max contacts per environment (== AVSIM_MAX_CONTACTS)
 #define AV_NSC 20       // max scalar constraint rows (equality + friction loss + joint limits)
 #define AV_NCAND 64     // broadphase survivors per class
-#define AV_MAX_WARPS 8  // warps (= environments) per block
+#define AV_MAX_WARPS 14  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
+#define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
 #define AV_JW 16        // columns of a contact Jacobian block: 8 dofs of tree1 | 8 dofs of tree2
 
 enum { AV_JNT_FREE = 0, AV_JNT_SLIDE = 2, AV_JNT_HINGE = 3 };
@@ -75,9 +76,11 @@ struct BatchState {
     float *contacts;                                // [B][AV_NCON][16]
     float *qacc, *xpos, *qfrc_bias, *qacc_smooth, *mass_diag;  // debug dumps of the last forward pass
     float *scratch;                                 // [B][AV_SCRATCH_FLOATS]
+    int *order;                                     // [B] environments in the order the step kernel hands them out (costliest first)
+    int *queue;                                     // [1] head of that work queue
+    long long *env_cycles;                          // [B] SM cycles the last step kernel spent on each environment
     uint64_t seed;
     int solver_iters, noslip_iters, multiccd;
-    int sync;   // 0 free-running warps, 1 block re-aligned per substep, 2 per stage (avsim_kernels.cuh)
 };
 
 // per-contact solver block in global scratch (avsim_solve.cuh): AR 21 | Lc 15 | b 6 | R 4 | mu 3 | 1/mu 3 | J[6][16]

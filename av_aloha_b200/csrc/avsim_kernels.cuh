@@ -5,6 +5,9 @@
 #include "avsim_step.cuh"
 
 extern __shared__ float4 av_smem_raw[];
+#ifndef AV_SHARED
+#define AV_SHARED __shared__   // the host emulation harness maps it to `static` (one variable per block)
+#endif
 
 __device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane) {
     for (int i = lane; i < m.nq; i += 32) S.qpos[i] = B.qpos[(size_t)env * m.nq + i];
@@ -16,15 +19,9 @@ __device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S,
             st3(S.xpos + 3 * b, ld3(m.body_xpos0 + 3 * b));
             Q4 q = ldq(m.body_xquat0 + 4 * b);
             stq(S.xquat + 4 * b, q);
-            stm3(S.xmat + 9 * b, q2m(q));
-        }
-    for (int g = lane; g < m.ngeom; g += 32)
-        if (m.geom_static[g]) {
-            st3(S.gpos + 3 * g, ld3(m.geom_xpos0 + 3 * g));
-            st3(S.gaabb + 3 * g, ld3(m.geom_xaabb0 + 3 * g));
         }
     // padding of the per-tree 8x8 blocks must be finite: block_apply multiplies it by exact zeros
-    for (int i = lane; i < AV_MBLK; i += 32) { S.Minv[i] = 0.f; S.L[i] = 0.f; }
+    for (int i = lane; i < AV_MBLK; i += 32) S.Minv[i] = 0.f;
     if (lane == 0) { S.status = 0; S.ncon = 0; S.nsc = 0; }
     __syncwarp();
 }
@@ -34,6 +31,7 @@ __device__ inline void env_store(const DevModel &m, const BatchState &B, EnvS &S
     for (int i = lane; i < m.nu; i += 32) B.ctrl[(size_t)env * m.nu + i] = S.ctrl[i];
 }
 
+// with_reward = false: called right after a solve (forward kernel): contact forces are valid and the reward is kept
 __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane, bool with_reward) {
     int latch = B.latch[env];
     int r = stage_reward(m, S, lane, latch);
@@ -60,42 +58,61 @@ __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS 
         o[1] = S.c_pos[3 * c]; o[2] = S.c_pos[3 * c + 1]; o[3] = S.c_pos[3 * c + 2];
         o[4] = S.c_frame[9 * c]; o[5] = S.c_frame[9 * c + 1]; o[6] = S.c_frame[9 * c + 2];
         o[7] = (float)(info & 0xff); o[8] = (float)((info >> 8) & 0xff); o[9] = (float)((info >> 16) & 0xf);
-        o[10] = (float)((info >> 20) & 1); o[11] = S.c_f[6 * c];
+        o[10] = (float)((info >> 20) & 1); o[11] = with_reward ? 0.f : S.c_f[6 * c];
         o[12] = o[13] = o[14] = o[15] = 0.f;
     }
 }
 
-// A block is W warps (blockDim = 32 x W), one environment per warp, each with its own EnvS slice of dynamic shared
-// memory.  B.sync selects how tightly the warps of a block move together: 0 = free running, 1 = re-aligned at every
-// substep, 2 = every stage in lockstep.  Lockstep keeps all warps of an SM inside the same few KB of code (the kernel
-// is instruction-fetch bound, see profiles/), at the price of waiting for the slowest environment of the block.
-#define AV_RUN(active, sync, call)              \
-    do {                                        \
-        if (active) { call; }                   \
-        if ((sync) >= 2) __syncthreads();       \
-    } while (0)
-
-__device__ __forceinline__ void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf,
-                                            bool active, int sync) {
-    AV_RUN(active, sync, stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane));
-    AV_RUN(active, sync, stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
-    AV_RUN(active, sync, stage_collision(m, S, lane, B.multiccd != 0, pf));
-    AV_RUN(active, sync, stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane); pf.mark(PF_ROWS_S, lane));
-    AV_RUN(active, sync, stage_rows_contact(m, S, scratch, lane); pf.mark(PF_ROWS_C, lane));
-    AV_RUN(active, sync, stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters); pf.mark(PF_SOLVE, lane));
+__device__ __forceinline__ void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf) {
+    stage_kinematics(m, S, lane);
+    pf.mark(PF_KIN, lane);
+    stage_inertia(m, S, lane);
+    pf.mark(PF_INERTIA, lane);
+    stage_collision(m, S, lane, B.multiccd != 0, pf);
+    stage_smooth(m, S, lane);
+    pf.mark(PF_SMOOTH, lane);
+    stage_rows_scalar(m, S, lane);
+    pf.mark(PF_ROWS_S, lane);
+    stage_rows_contact(m, S, scratch, lane);
+    pf.mark(PF_ROWS_C, lane);
+    stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters);
+    pf.mark(PF_SOLVE, lane);
 }
 
-// env.step: ctrl write (reference env.py:204-215), nsub x mj_step (env.py:218), trailing position pass, reward
-__global__ void __launch_bounds__(32 * AV_MAX_WARPS) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
-                                                                      const float *__restrict__ action, int nsub) {
-    int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y, sync = B.sync;
+// env.step: ctrl write (reference env.py:204-215), nsub x mj_step (env.py:218), trailing position pass, reward.
+//
+// Block = W warps = W environments, each with its own EnvS slice, moving through the pipeline STAGE BY STAGE in lockstep
+// (__syncthreads between stages).  Why: the kernel is bound by instruction fetch, not by data -- ncu showed
+// 'no_instruction' as the dominant stall and throughput independent of the number of resident warps, because every
+// free-running warp streams its own ~200 KB of code per substep through the SM's instruction cache.  In lockstep all
+// warps of the SM execute the same stage, so a fetched line serves W warps.
+// Work distribution: a queue (B.order / B.queue) instead of a static stride, handed out W entries at a time.
+// Environments differ ~5x in cost; avsim_order_kernel sorts the queue by the cycles each environment took in the
+// previous step (costliest first), which (a) fills the tail of the launch with cheap environments and (b) puts
+// environments of similar cost into the same block, so the lockstep barriers wait for little.
+#define AV_STAGE_SYNC(call)      \
+    do {                         \
+        if (active) { call; }    \
+        __syncthreads();         \
+    } while (0)
+
+__global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
+                                                                          const float *__restrict__ action, int nsub) {
+    const int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y;
     EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + warp);
+    AV_SHARED int s_base;
     Prof pf;
-    for (int base = blockIdx.x * W; base < B.num_envs; base += gridDim.x * W) {
-        int env = base + warp;
-        bool active = env < B.num_envs;
-        float *scratch = B.scratch + (size_t)(active ? env : 0) * AV_SCRATCH_FLOATS;
+    for (;;) {
+        if (warp == 0 && lane == 0) s_base = atomicAdd(B.queue, W);
+        __syncthreads();
+        const int base = s_base;
+        __syncthreads();
+        if (base >= B.num_envs) break;
+        const bool active = base + warp < B.num_envs;
+        const int env = active ? B.order[base + warp] : 0;
+        float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
         pf.start();
+        long long c0 = clock64();
         if (active) {
             env_load(m, B, S, env, lane);
             pf.mark(PF_LOAD, lane);
@@ -107,35 +124,37 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS) avsim_step_kernel(const __g
             __syncwarp();
         }
         for (int s = 0; s < nsub; s++) {
-            if (sync >= 1) __syncthreads();
-            env_forward(m, B, S, scratch, lane, pf, active, sync);
-            AV_RUN(active, sync, stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
+            AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
+            AV_STAGE_SYNC(stage_collision(m, S, lane, B.multiccd != 0, pf));
+            AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane); pf.mark(PF_ROWS_S, lane);
+                          stage_rows_contact(m, S, scratch, lane); pf.mark(PF_ROWS_C, lane));
+            AV_STAGE_SYNC(stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters); pf.mark(PF_SOLVE, lane));
+            AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
         }
+        AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane));
+        AV_STAGE_SYNC(stage_collision(m, S, lane, B.multiccd != 0, pf));
         if (active) {
-            stage_kinematics(m, S, lane);
-            pf.mark(PF_KIN, lane);
-            stage_collision(m, S, lane, B.multiccd != 0, pf);
             env_store(m, B, S, env, lane);
             env_outputs(m, B, S, env, lane, true);
             pf.mark(PF_OUT, lane);
+            if (lane == 0) B.env_cycles[env] = clock64() - c0;
             __syncwarp();
         }
     }
 }
 
 // physics.forward(): all stages, no integration; dumps stage outputs for the parity tests.  mask (nullable) selects envs.
-__global__ void __launch_bounds__(32 * AV_MAX_WARPS) avsim_forward_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
+__global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
                                                                          const uint8_t *__restrict__ mask) {
-    int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y;
-    EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + warp);
-    for (int base = blockIdx.x * W; base < B.num_envs; base += gridDim.x * W) {
-        int env = base + warp;
-        if (env >= B.num_envs || (mask && !mask[env])) continue;
+    int lane = threadIdx.x;
+    EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
+    for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
+        if (mask && !mask[env]) continue;
         Prof pf;
         pf.start();
         env_load(m, B, S, env, lane);
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
-        env_forward(m, B, S, scratch, lane, pf, true, 0);
+        env_forward(m, B, S, scratch, lane, pf);
         for (int i = lane; i < m.nv; i += 32) {
             B.qacc[(size_t)env * m.nv + i] = S.qacc_smooth[i] + S.acc[i];
             B.qacc_smooth[(size_t)env * m.nv + i] = S.qacc_smooth[i];
@@ -147,6 +166,39 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS) avsim_forward_kernel(const 
         env_outputs(m, B, S, env, lane, false);
         __syncwarp();
     }
+}
+
+// Sorts environments by the cycles they took in the previous step (descending) into B.order and rewinds the queue.
+// One block, bitonic sort of (cycles, env) keys in shared memory; n2 = num_envs rounded up to a power of two.
+__global__ void avsim_order_kernel(BatchState B, int n2) {
+    extern __shared__ unsigned long long av_keys[];
+    int n = B.num_envs;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned long long c = i < n ? (unsigned long long)B.env_cycles[i] : 0ull;
+        if (c > 0xffffffffffull) c = 0xffffffffffull;
+        // key = cycles << 20 | (0xfffff - env): descending sort keeps ties in ascending env order; padding sorts last
+        av_keys[i] = i < n ? ((c << 20) | (unsigned long long)(0xfffff - i)) : 0ull;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                int l = i ^ j;
+                if (l > i) {
+                    unsigned long long a = av_keys[i], b = av_keys[l];
+                    bool desc = (i & k) == 0;
+                    if (desc ? a < b : a > b) { av_keys[i] = b; av_keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) B.order[i] = 0xfffff - (int)(av_keys[i] & 0xfffff);
+    if (threadIdx.x == 0) *B.queue = 0;
+}
+__global__ void avsim_identity_order_kernel(BatchState B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.num_envs) B.order[i] = i;
+    if (i == 0) *B.queue = 0;
 }
 
 // ---- Philox4x32-10 counter RNG for device-side reset draws

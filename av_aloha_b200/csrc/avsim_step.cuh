@@ -34,29 +34,53 @@ struct Prof {
 };
 #endif
 
+// Shared-memory slice of one environment.  Arrays whose lifetimes do not overlap inside a substep share storage (the
+// slice size sets how many environments fit on an SM, and the kernel is latency-bound: more resident warps = more
+// throughput).  Stage order: kinematics -> inertia -> collision -> smooth -> rows_scalar -> rows_contact -> solve ->
+// integrate.  Lifetimes:
+//   crb   : composite inertias (inertia) | cacc,cfrc (smooth) | Cholesky factor L (end of inertia; integrate)
+//   u1    : broadphase candidates + world AABBs (kinematics..collision) | cvel, cdofdot (smooth)
+//   u2    : cinert, xipos (kinematics..smooth) | contact forces, multipliers, tree descriptors, J staging (rows_contact..solve)
+//   u3    : geom centres (kinematics..collision) | scalar constraint rows (rows_scalar..solve)
 struct EnvS {
     float qpos[AV_NQ], qvel[AV_NVP], ctrl[24], warm[AV_NVP];
-    float xpos[AV_NB * 3], xquat[AV_NB * 4], xmat[AV_NB * 9], xipos[AV_NB * 3];
+    float xpos[AV_NB * 3], xquat[AV_NB * 4];
     float torig[AV_NTREE * 3];
-    float cdof[AV_NV * 6], cdofdot[AV_NV * 6];
-    float cinert[AV_NB * 10];
-    float crb[AV_NB * 12];  // composite inertias (10/body) in stage_inertia; cacc|cfrc (6+6/body) in stage_smooth
-    float cvel[AV_NB * 6];
-    float M[AV_MBLK], L[AV_MBLK], Minv[AV_MBLK];
+    float cdof[AV_NV * 6];
+    union {
+        float crb[AV_NB * 12];
+        float L[AV_MBLK];
+    };
+    float M[AV_MBLK], Minv[AV_MBLK];
     float qfrc_smooth[AV_NVP], qacc_smooth[AV_NVP], acc[AV_NVP], qfrc_bias[AV_NVP];
-    float gpos[AV_NG * 3], gaabb[AV_NG * 3];  // world centre + world-axis half extents of every geom
-    // contacts
-    float c_pos[AV_NCON * 3], c_frame[AV_NCON * 9], c_dist[AV_NCON], c_mu[AV_NCON * 3], c_f[AV_NCON * 6], c_lam[AV_NCON];
+    union {
+        struct { float gaabb[AV_NG * 3]; int cand_p[AV_NCAND], cand_c[AV_NCAND]; };
+        struct { float cvel[AV_NB * 6], cdofdot[AV_NV * 6]; };
+    };
+    union {
+        struct { float cinert[AV_NB * 10], xipos[AV_NB * 3]; };
+        struct {
+            __align__(16) float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
+            float c_f[AV_NCON * 6], c_lam[AV_NCON];
+            int c_tree[AV_NCON];  // packed dof ranges / tree ids of the two kinematic trees (tr_pack)
+        };
+    };
+    union {
+        float gpos[AV_NG * 3];  // world centre of every geom
+        struct {
+            int sc_dof1[AV_NSC], sc_dof2[AV_NSC], sc_tree[AV_NSC];
+            float sc_c1[AV_NSC], sc_c2[AV_NSC], sc_b[AV_NSC], sc_R[AV_NSC], sc_f[AV_NSC], sc_lo[AV_NSC], sc_hi[AV_NSC],
+                sc_A[AV_NSC], sc_aref[AV_NSC], sc_MJ[AV_NSC * AV_TD];
+        };
+    };
+    // contacts (collision .. outputs)
+    float c_pos[AV_NCON * 3], c_frame[AV_NCON * 9], c_dist[AV_NCON], c_mu[AV_NCON * 3];
     int c_info[AV_NCON];  // geom1 | geom2 << 8 | dim << 16 | excluded << 20
-    int c_tree[AV_NCON];  // packed dof ranges / tree ids of the two kinematic trees (tr_pack)
-    // scalar rows
-    int sc_dof1[AV_NSC], sc_dof2[AV_NSC], sc_tree[AV_NSC];
-    float sc_c1[AV_NSC], sc_c2[AV_NSC], sc_b[AV_NSC], sc_R[AV_NSC], sc_f[AV_NSC], sc_lo[AV_NSC], sc_hi[AV_NSC],
-        sc_A[AV_NSC], sc_aref[AV_NSC], sc_MJ[AV_NSC * AV_TD];
-    __align__(16) float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
-    int cand_p[AV_NCAND], cand_c[AV_NCAND];
     int ncon, nsc, ncand_p, ncand_c, status;
 };
+static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");
+
+__device__ __forceinline__ M3 body_mat(const EnvS &S, int b) { return q2m(ldq(S.xquat + 4 * b)); }
 
 __device__ __forceinline__ int body_mask_has(const DevModel &m, int body, int dof) {
     // is `dof` on the path from the tree root to `body`?
@@ -72,7 +96,7 @@ __device__ AV_STAGE void stage_kinematics(const DevModel &m, EnvS &S, int lane) 
         V3 org = v3(0, 0, 0);
         for (int b = b0; b < b0 + nb; b++) {
             int p = m.body_parent[b];
-            M3 Rp = ldm3(S.xmat + 9 * p);
+            M3 Rp = body_mat(S, p);
             V3 pos = ld3(S.xpos + 3 * p) + mul(Rp, ld3(m.body_pos + 3 * b));
             Q4 quat = qmul(ldq(S.xquat + 4 * p), ldq(m.body_quat + 4 * b));
             int j0 = m.body_jntadr[b], nj = m.body_jntnum[b];
@@ -100,7 +124,7 @@ __device__ AV_STAGE void stage_kinematics(const DevModel &m, EnvS &S, int lane) 
             }
             quat = qnormalize(quat);
             M3 R = q2m(quat);
-            st3(S.xpos + 3 * b, pos); stq(S.xquat + 4 * b, quat); stm3(S.xmat + 9 * b, R);
+            st3(S.xpos + 3 * b, pos); stq(S.xquat + 4 * b, quat);
             if (b == b0) { org = pos; st3(S.torig + 3 * lane, org); }
             // dof axes about the tree origin
             int d0 = m.body_dofadr[b];
@@ -141,17 +165,21 @@ __device__ AV_STAGE void stage_kinematics(const DevModel &m, EnvS &S, int lane) 
         }
     }
     __syncwarp();
-    for (int g = lane; g < m.ngeom; g += 32)
-        if (!m.geom_static[g]) {
-            int b = m.geom_body[g];
-            M3 Rb = ldm3(S.xmat + 9 * b);
-            st3(S.gpos + 3 * g, ld3(S.xpos + 3 * b) + mul(Rb, ld3(m.geom_pos + 3 * g)));
-            M3 Rg = mul(Rb, ldm3(m.geom_mat + 9 * g));
-            V3 h = ld3(m.geom_aabb + 3 * g);
-            st3(S.gaabb + 3 * g, v3(fabsf(Rg.m[0]) * h.x + fabsf(Rg.m[1]) * h.y + fabsf(Rg.m[2]) * h.z,
-                                    fabsf(Rg.m[3]) * h.x + fabsf(Rg.m[4]) * h.y + fabsf(Rg.m[5]) * h.z,
-                                    fabsf(Rg.m[6]) * h.x + fabsf(Rg.m[7]) * h.y + fabsf(Rg.m[8]) * h.z));
+    for (int g = lane; g < m.ngeom; g += 32) {
+        if (m.geom_static[g]) {   // world-welded geoms: compile-time pose (re-written every substep: the slots are shared)
+            st3(S.gpos + 3 * g, ld3(m.geom_xpos0 + 3 * g));
+            st3(S.gaabb + 3 * g, ld3(m.geom_xaabb0 + 3 * g));
+            continue;
         }
+        int b = m.geom_body[g];
+        M3 Rb = body_mat(S, b);
+        st3(S.gpos + 3 * g, ld3(S.xpos + 3 * b) + mul(Rb, ld3(m.geom_pos + 3 * g)));
+        M3 Rg = mul(Rb, ldm3(m.geom_mat + 9 * g));
+        V3 h = ld3(m.geom_aabb + 3 * g);
+        st3(S.gaabb + 3 * g, v3(fabsf(Rg.m[0]) * h.x + fabsf(Rg.m[1]) * h.y + fabsf(Rg.m[2]) * h.z,
+                                fabsf(Rg.m[3]) * h.x + fabsf(Rg.m[4]) * h.y + fabsf(Rg.m[5]) * h.z,
+                                fabsf(Rg.m[6]) * h.x + fabsf(Rg.m[7]) * h.y + fabsf(Rg.m[8]) * h.z));
+    }
     __syncwarp();
 }
 
@@ -236,7 +264,7 @@ __device__ inline Shape load_shape(const DevModel &m, const EnvS &S, int g) {
     } else {
         int b = m.geom_body[g];
         s.pos = ld3(S.gpos + 3 * g);
-        s.mat = mul(ldm3(S.xmat + 9 * b), ldm3(m.geom_mat + 9 * g));
+        s.mat = mul(body_mat(S, b), ldm3(m.geom_mat + 9 * g));
     }
     if (s.type == AV_GEOM_MESH) {
         int h = m.geom_hull[g];

@@ -45,7 +45,8 @@ enum avsim_field {
     AVSIM_XPOS = 12,       /* f32 [nbody*3] data.xpos of the last forward pass                                 */
     AVSIM_QFRC_BIAS = 13,  /* f32 [nv]                                                                          */
     AVSIM_QACC_SMOOTH = 14,/* f32 [nv]                                                                          */
-    AVSIM_MASS_DIAG = 15   /* f32 [nv]      diagonal of the joint-space inertia                                */
+    AVSIM_MASS_DIAG = 15,  /* f32 [nv]      diagonal of the joint-space inertia                                */
+    AVSIM_ENV_CYCLES = 16  /* i64 [1]       SM cycles the last avsim_step spent on this environment (load-balance diagnostics) */
 };
 #define AVSIM_MAX_CONTACTS 40
 

@@ -45,6 +45,7 @@ void run_block(int block, int grid, const std::function<void()> &body) {
 #include "../../av_aloha_b200/csrc/avsim_ik.cuh"
 #include "../../av_aloha_b200/csrc/avsim_model_pack.h"
 
+unsigned long long av_keys[8192];
 float4 av_smem_raw[(sizeof(EnvS) + 15) / 16 + 1];
 
 struct EmuBatch {
@@ -52,6 +53,8 @@ struct EmuBatch {
     BatchState st;
     std::vector<float> f[16];
     std::vector<int> iv[8];
+    std::vector<long long> cyc;
+    std::vector<int> order, queue;
 };
 
 extern "C" {
@@ -70,6 +73,8 @@ EmuBatch *emu_create(const char *path, int num_envs) {
     s.agent_pos = F(4, B * d.nj_obs); s.contacts = F(5, B * AV_NCON * 16); s.qacc = F(6, B * d.nv);
     s.xpos = F(7, B * 3 * d.nbody); s.qfrc_bias = F(8, B * d.nv); s.qacc_smooth = F(9, B * d.nv);
     s.mass_diag = F(10, B * d.nv); s.scratch = F(11, B * AV_SCRATCH_FLOATS);
+    b->cyc.assign(B, 0); s.env_cycles = b->cyc.data();
+    b->order.resize(B); b->queue.assign(1, 0); s.order = b->order.data(); s.queue = b->queue.data();
     s.reward = I(0, B); s.status = I(1, B); s.latch = I(2, B); s.ncon = I(3, B); s.episode = I(4, B);
     return b;
 }
@@ -99,8 +104,10 @@ void emu_forward(EmuBatch *b) {
         emu::run_block(e, b->st.num_envs, [&]() { avsim_forward_kernel(b->pk.dm, b->st, nullptr); });
 }
 void emu_step(EmuBatch *b, const float *action, int nsub) {
-    for (int e = 0; e < b->st.num_envs; e++)
-        emu::run_block(e, b->st.num_envs, [&]() { avsim_step_kernel(b->pk.dm, b->st, action, nsub); });
+    int n2 = 1;
+    while (n2 < b->st.num_envs) n2 <<= 1;
+    emu::run_block(0, 1, [&]() { avsim_order_kernel(b->st, n2); });   // same queue order as the device
+    emu::run_block(0, 1, [&]() { avsim_step_kernel(b->pk.dm, b->st, action, nsub); });   // one block drains the queue
 }
 void emu_reset(EmuBatch *b, const float *free_pos) {
     int nb = (b->st.num_envs + 31) / 32;

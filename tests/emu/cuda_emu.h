@@ -22,6 +22,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__
+#define AV_SHARED static
 #define __grid_constant__
 static inline float __fdividef(float a, float b) { return a / b; }
 #define __align__(n) alignas(n)
@@ -93,6 +94,8 @@ static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pre
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline long long clock64() { return 0; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }   // fibers never preempt between collectives
 using std::isfinite;
 using std::max;
 using std::min;

@@ -103,10 +103,12 @@ def main():
             k_null = np.array([10.0, 10.0, 10.0, 10.0, 5.0, 5.0, 5.0])[:n]
             ctl = ref_diff_ik.DiffIK(physics=phys, joints=joints, actuators=joints, eef_site="site", damping=1.0e-4,
                                      k_null=k_null, q0=HOME[arm].astype(np.float64), max_angvel=3.14, iterations=10, **kw)
+            ctl1 = ref_diff_ik.DiffIK(physics=phys, joints=joints, actuators=joints, eef_site="site", damping=1.0e-4,
+                                      k_null=k_null, q0=HOME[arm].astype(np.float64), max_angvel=3.14, iterations=1, **kw)
             Nd = 48
             qs = f32(np.clip(HOME[arm] + rng.normal(0, 0.35, size=(Nd, n)), lo, hi))
             tgt_q = np.clip(qs + rng.normal(0, 0.15, size=(Nd, n)), lo, hi)
-            pos = np.zeros((Nd, 3)); quat = np.zeros((Nd, 4)); res = np.zeros((Nd, n))
+            pos = np.zeros((Nd, 3)); quat = np.zeros((Nd, 4)); res = np.zeros((Nd, n)); res1 = np.zeros((Nd, n))
             for i in range(Nd):
                 Tt = fk(tgt_q[i].copy())
                 pos[i] = Tt[:3, 3]
@@ -116,6 +118,8 @@ def main():
                     quat[i] = random_quat_wxyz(rng)
                 pos[i], quat[i] = f32(pos[i]), f32(quat[i])
                 res[i] = ctl.run(qs[i].copy(), pos[i].copy(), quat[i].copy())
+                res1[i] = ctl1.run(qs[i].copy(), pos[i].copy(), quat[i].copy())      # the single-iteration map
+            out[f"diffik_{tag}_out1_{arm}"] = res1
             out[f"diffik_{tag}_q_{arm}"], out[f"diffik_{tag}_pos_{arm}"] = qs, pos
             out[f"diffik_{tag}_quat_{arm}"], out[f"diffik_{tag}_out_{arm}"] = quat, res
         # ---- GradIK (sim parameters sim_env.py:89-124); 6-dof weights padded for the 7-dof arm
@@ -125,10 +129,14 @@ def main():
                                  joint_center_weight=cw, joint_displacement_weight=np.array(n * [50.0]),
                                  position_threshold=0.001, rotation_threshold=0.001, max_pos_diff=0.1, max_rot_diff=0.3,
                                  joint_p=0.9)
+        import copy
+        ctl8 = copy.copy(ctl)
+        ctl8.max_iterations = 8          # the first iterations pin the algorithm tightly (see tests/test_ik_golden.py)
         Ng = 32
         qs = f32(np.clip(HOME[arm] + rng.normal(0, 0.3, size=(Ng, n)), lo, hi))
         tgt_q = np.clip(qs + rng.normal(0, 0.12, size=(Ng, n)), lo, hi)
-        pos = np.zeros((Ng, 3)); quat = np.zeros((Ng, 4)); res = np.zeros((Ng, n))
+        pos = np.zeros((Ng, 3)); quat = np.zeros((Ng, 4)); res = np.zeros((Ng, n)); res8 = np.zeros((Ng, n))
+        lim_pos = np.zeros((Ng, 3)); lim_mat = np.zeros((Ng, 3, 3)); best_cost = np.zeros(Ng)
         for i in range(Ng):
             Tt = fk(tgt_q[i].copy())
             pos[i] = Tt[:3, 3]
@@ -138,6 +146,16 @@ def main():
                 quat[i] = random_quat_wxyz(rng)
             pos[i], quat[i] = f32(pos[i]), f32(quat[i])
             res[i] = ctl.run(qs[i].copy(), pos[i].copy(), quat[i].copy())
+            res8[i] = ctl8.run(qs[i].copy(), pos[i].copy(), quat[i].copy())
+            # the limited target and the cost of the reference's best iterate (best = q_start + (out - q_start) / joint_p)
+            Tc = fk(qs[i].copy())
+            lp, lm = ref_tu.limit_pose(Tc[:3, 3].copy(), Tc[:3, :3].copy(), pos[i].copy(),
+                                       ref_tu.quat2mat(ref_tu.wxyz_to_xyzw(quat[i].copy())), 0.1, 0.3)
+            lim_pos[i], lim_mat[i] = lp, lm
+            best = qs[i] + (res[i] - qs[i]) / 0.9
+            best_cost[i] = ctl.cost_fn(best, qs[i].copy(), lp, np.ascontiguousarray(lm))
+        out[f"gradik_out8_{arm}"], out[f"gradik_limpos_{arm}"], out[f"gradik_limmat_{arm}"] = res8, lim_pos, lim_mat
+        out[f"gradik_bestcost_{arm}"] = best_cost
         out[f"gradik_q_{arm}"], out[f"gradik_pos_{arm}"], out[f"gradik_quat_{arm}"], out[f"gradik_out_{arm}"] = qs, pos, quat, res
         print(f"arm {arm}: done", flush=True)
     # ---- transform_utils primitives (a13)

@@ -1,16 +1,16 @@
-"""Step the scripted SlotInsertion batch n times (for ncu captures): python tools/run_steps.py B iters nsteps [t0]."""
+"""Step the steady-state bench workload n times (for ncu captures): python tools/run_steps.py B iters nsteps"""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
-import bench
-from av_aloha_b200 import capi, model_io
+import steady
+from av_aloha_b200 import capi
 
 B, iters, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-model = capi.Model(model_io.model_path("slot_insertion", 3), 0)
-batch = capi.Batch(model, B, seed=1234)
-batch.set_options(solver_iters=iters)
-acts = torch.as_tensor(bench.script_actions(300, B, 1234), device="cuda")
-for t in range(n):
-    batch.step(acts[t % 300])
+model, batch, acts, masks, mask_any, fp, t0 = steady.restore(B, iters)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for k in range(n):
+    steady.step(batch, acts, masks, mask_any, fp, t0 + k)
+e1.record()
 torch.cuda.synchronize()
-print("done", n, "steps; ncon mean", batch.get(capi.NCON).float().mean().item())
+print(f"done {n} steps, {e0.elapsed_time(e1) / n:.1f} ms/step; ncon mean", batch.get(capi.NCON).float().mean().item())

@@ -1,46 +1,25 @@
-"""Time block-shape / sync variants of the step kernel on the same mid-episode state:
-   python tools/variant_bench.py [B] [iters] [t0] -- variants are (AVSIM_WARPS, AVSIM_SYNC) pairs."""
+"""Time block-shape (warps per lockstep block : blocks per SM) variants of the step kernel on the steady-state bench workload:
+   python tools/variant_bench.py [B] [iters] [blocks,blocks,...]"""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
-import bench
-from av_aloha_b200 import capi, model_io
+import steady
+from av_aloha_b200 import capi
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-t0 = int(sys.argv[3]) if len(sys.argv) > 3 else 150
-variants = [tuple(int(x) for x in v.split(':')) for v in (sys.argv[4].split(',') if len(sys.argv) > 4 else ['1:0'])]
-model = capi.Model(model_io.model_path("slot_insertion", 3), 0)
-acts = torch.as_tensor(bench.script_actions(300, B, 1234), device="cuda")
-
-
-def make(w, s):
-    os.environ["AVSIM_WARPS"], os.environ["AVSIM_SYNC"] = str(w), str(s)
-    b = capi.Batch(model, B, seed=1234)
-    b.set_options(solver_iters=iters)
-    return b
-
-
-b0 = make(1, 0)
+variants = [tuple(int(x) for x in v.split(":")) for v in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["14:1", "7:2", "4:3", "2:7", "1:14"])]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for t in range(t0):
-    b0.step(acts[t])
-e1.record(); torch.cuda.synchronize()
-print(f"advance to t={t0}: {e0.elapsed_time(e1) / t0:.1f} ms/step avg (warps=1 sync=0)")
-state = {f: b0.get(f).clone() for f in (capi.QPOS, capi.QVEL, capi.CTRL, capi.WARMSTART)}
-ref = None
-for w, s in variants:
-    b = make(w, s)
-    for f, v in state.items():
-        b.set(f, v)
+for nw, nb in variants:
+    os.environ["AVSIM_WARPS"], os.environ["AVSIM_BLOCKS"] = str(nw), str(nb)
+    model, batch, acts, masks, mask_any, fp, t0 = steady.restore(B, iters)
     ts = []
-    for k in range(4):
-        e0.record(); b.step(acts[t0 + k]); e1.record(); torch.cuda.synchronize()
+    for k in range(5):
+        e0.record(); steady.step(batch, acts, masks, mask_any, fp, t0 + k); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    q = b.get(capi.QPOS)
-    if ref is None:
-        ref = q.clone()
-    print(f"warps={w} sync={s}: {sum(ts[1:]) / 3:7.1f} ms/step  -> {B / (sum(ts[1:]) / 3) * 1e3:8.0f} env-steps/s   "
-          f"max|dqpos| vs first variant {float((q - ref).abs().max()):.2e}  ncon {b.get(capi.NCON).float().mean().item():.1f}", flush=True)
-    b.close()
+    ms = sum(ts[2:]) / 3
+    print(f"warps/block={nw} blocks/SM={nb}: {ms:7.1f} ms/step -> {B / ms * 1e3:8.0f} env-steps/s  (first {ts[0]:.0f} ms)  ncon {batch.get(capi.NCON).float().mean().item():.1f}", flush=True)
+    cyc = batch.get(capi.ENV_CYCLES).double()
+    print(f"      per-env SM cycles of the last step: mean {cyc.mean().item():.3e}  p50 {cyc.median().item():.3e}  p90 {cyc.quantile(0.9).item():.3e} "
+          f"p99 {cyc.quantile(0.99).item():.3e}  max {cyc.max().item():.3e}  (kernel {ms * 1.965e6:.3e} cycles)", flush=True)
+    batch.close()
