@@ -16,7 +16,7 @@
 
 #define AV_SORT_MAX 8192
 #ifndef AV_DEFAULT_WARPS
-#define AV_DEFAULT_WARPS 14
+#define AV_DEFAULT_WARPS 6
 #endif
 
 static thread_local char g_err[512] = "";

@@ -83,6 +83,7 @@ struct BatchState {
     int solver_iters, noslip_iters, multiccd;
 };
 
-// per-contact solver block in global scratch (avsim_solve.cuh): AR 21 | Lc 15 | b 6 | R 4 | mu 3 | 1/mu 3 | J[6][16]
-#define AV_CBLK (52 + 6 * AV_JW)
+// per-contact block in global scratch (avsim_solve.cuh): AR 21 | Lc 15 | b 6 | R 4 | mu 3 | 1/mu 3 | J[6][16] |
+// geometry (pos 3, frame 9, dist 1, friction 3) written by the narrowphase, read once by the row assembly
+#define AV_CBLK (52 + 6 * AV_JW + 16)
 #define AV_SCRATCH_FLOATS (AV_NCON * AV_CBLK)

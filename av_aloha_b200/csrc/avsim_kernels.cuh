@@ -32,7 +32,7 @@ __device__ inline void env_store(const DevModel &m, const BatchState &B, EnvS &S
 }
 
 // with_reward = false: called right after a solve (forward kernel): contact forces are valid and the reward is kept
-__device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane, bool with_reward) {
+__device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, const float *scratch, int env, int lane, bool with_reward) {
     int latch = B.latch[env];
     int r = stage_reward(m, S, lane, latch);
     if (!with_reward) { r = B.reward[env]; latch = B.latch[env]; }
@@ -54,9 +54,10 @@ __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS 
     for (int c = lane; c < S.ncon; c += 32) {
         float *o = B.contacts + ((size_t)env * AV_NCON + c) * 16;
         int info = S.c_info[c];
-        o[0] = S.c_dist[c];
-        o[1] = S.c_pos[3 * c]; o[2] = S.c_pos[3 * c + 1]; o[3] = S.c_pos[3 * c + 2];
-        o[4] = S.c_frame[9 * c]; o[5] = S.c_frame[9 * c + 1]; o[6] = S.c_frame[9 * c + 2];
+        const float *geo = scratch + c * AV_CBLK + AV_CB_GEO;
+        o[0] = geo[12];
+        o[1] = geo[0]; o[2] = geo[1]; o[3] = geo[2];
+        o[4] = geo[3]; o[5] = geo[4]; o[6] = geo[5];
         o[7] = (float)(info & 0xff); o[8] = (float)((info >> 8) & 0xff); o[9] = (float)((info >> 16) & 0xf);
         o[10] = (float)((info >> 20) & 1); o[11] = with_reward ? 0.f : S.c_f[6 * c];
         o[12] = o[13] = o[14] = o[15] = 0.f;
@@ -68,7 +69,7 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
     pf.mark(PF_KIN, lane);
     stage_inertia(m, S, lane);
     pf.mark(PF_INERTIA, lane);
-    stage_collision(m, S, lane, B.multiccd != 0, pf);
+    stage_collision(m, S, scratch, lane, B.multiccd != 0, pf);
     stage_smooth(m, S, lane);
     pf.mark(PF_SMOOTH, lane);
     stage_rows_scalar(m, S, lane);
@@ -125,17 +126,17 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
         }
         for (int s = 0; s < nsub; s++) {
             AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
-            AV_STAGE_SYNC(stage_collision(m, S, lane, B.multiccd != 0, pf));
+            AV_STAGE_SYNC(stage_collision(m, S, scratch, lane, B.multiccd != 0, pf));
             AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane); pf.mark(PF_ROWS_S, lane);
                           stage_rows_contact(m, S, scratch, lane); pf.mark(PF_ROWS_C, lane));
             AV_STAGE_SYNC(stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters); pf.mark(PF_SOLVE, lane));
             AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
         }
         AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane));
-        AV_STAGE_SYNC(stage_collision(m, S, lane, B.multiccd != 0, pf));
+        AV_STAGE_SYNC(stage_collision(m, S, scratch, lane, B.multiccd != 0, pf));
         if (active) {
             env_store(m, B, S, env, lane);
-            env_outputs(m, B, S, env, lane, true);
+            env_outputs(m, B, S, scratch, env, lane, true);
             pf.mark(PF_OUT, lane);
             if (lane == 0) B.env_cycles[env] = clock64() - c0;
             __syncwarp();
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const 
             B.mass_diag[(size_t)env * m.nv + i] = S.M[t * AV_TD * AV_TD + dl * AV_TD + dl];
         }
         for (int i = lane; i < 3 * m.nbody; i += 32) B.xpos[(size_t)env * 3 * m.nbody + i] = S.xpos[i];
-        env_outputs(m, B, S, env, lane, false);
+        env_outputs(m, B, S, scratch, env, lane, false);
         __syncwarp();
     }
 }

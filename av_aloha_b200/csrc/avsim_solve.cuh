@@ -21,7 +21,7 @@
 #define AV_CB_B 36
 #define AV_CB_PAR 42
 #define AV_CB_J 52
-// AV_CBLK (avsim_dev.h) = 52 + 6 * AV_JW = 148 floats
+// AV_CB_GEO = 148: contact geometry; AV_CBLK (avsim_dev.h) = 164 floats = 656 bytes
 
 #define TRI(i, j) ((i) >= (j) ? (i) * ((i) + 1) / 2 + (j) : (j) * ((j) + 1) / 2 + (i))
 
@@ -182,8 +182,9 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
         int tr = tr_pack(m, t1, t2);
         int t = col < 8 ? t1 : t2, dl = col & 7, dof = tr_dof(tr, col);
         float j0 = 0.f, j1 = 0.f, j2 = 0.f;
-        V3 p = ld3(S.c_pos + 3 * c);
-        V3 fn = ld3(S.c_frame + 9 * c), ft1 = ld3(S.c_frame + 9 * c + 3), ft2 = ld3(S.c_frame + 9 * c + 6);
+        const float *geo = scratch + c * AV_CBLK + AV_CB_GEO;
+        V3 p = ld3(geo);
+        V3 fn = ld3(geo + 3), ft1 = ld3(geo + 6), ft2 = ld3(geo + 9);
         if (dof >= 0) {
             float sgn = 0.f;
             if (m.body_tree[b2] == t && ((m.body_treemask[b2] >> dl) & 1)) sgn += 1.f;
@@ -229,10 +230,10 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
         for (int k = 0; k < 2; k++) solref[k] = 0.5f * (m.geom_solref[2 * g1 + k] + m.geom_solref[2 * g2 + k]);
 #pragma unroll
         for (int k = 0; k < 5; k++) solimp[k] = 0.5f * (m.geom_solimp[5 * g1 + k] + m.geom_solimp[5 * g2 + k]);
-        float dist = S.c_dist[c];
+        float dist = geo[12];
         kbi(m, solref, solimp, dist, K, B, imp);
         float Rn = fmaxf(AV_MINVAL, (1.f - imp) / imp * (m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2]));
-        float mu0 = S.c_mu[3 * c], mu1 = S.c_mu[3 * c + 1], mu2 = S.c_mu[3 * c + 2];
+        float mu0 = geo[13], mu1 = geo[14], mu2 = geo[15];
         float Rf = Rn / m.impratio;
         float R[6] = {Rn, Rf, Rf, Rf * mu0 * mu0 / (mu1 * mu1), Rf * mu0 * mu0 / (mu2 * mu2), Rf * mu0 * mu0 / (mu2 * mu2)};
         if (lane < 6) {
@@ -291,7 +292,7 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
 #pragma unroll
             for (int k = 0; k < 6; k++) f[k] = 0.f;
         } else {
-            float mu0 = S.c_mu[3 * c], mu1 = S.c_mu[3 * c + 1], mu2 = S.c_mu[3 * c + 2];
+            float mu0 = blk[AV_CB_GEO + 13], mu1 = blk[AV_CB_GEO + 14], mu2 = blk[AV_CB_GEO + 15];
             float mu[5] = {mu0, mu0, mu1, mu2, mu2};
             float s = 0.f;
 #pragma unroll

@@ -13,6 +13,8 @@
 #pragma once
 #include "avsim_collide.cuh"
 
+#define AV_CB_GEO (52 + 6 * AV_JW)   // offset of the contact geometry inside a scratch block (layout: avsim_solve.cuh)
+
 // ---- optional per-stage cycle counters (-DAVSIM_PROFILE; read back with avsim_stage_cycles)
 enum { PF_LOAD = 0, PF_KIN, PF_INERTIA, PF_BROAD, PF_PRIM, PF_CONVEX, PF_SMOOTH, PF_ROWS_S, PF_ROWS_C, PF_SOLVE, PF_INTEGRATE,
        PF_OUT, PF_N };
@@ -73,8 +75,7 @@ struct EnvS {
                 sc_A[AV_NSC], sc_aref[AV_NSC], sc_MJ[AV_NSC * AV_TD];
         };
     };
-    // contacts (collision .. outputs)
-    float c_pos[AV_NCON * 3], c_frame[AV_NCON * 9], c_dist[AV_NCON], c_mu[AV_NCON * 3];
+    // contacts (collision .. outputs); position / frame / distance / friction live in the contact's global scratch block
     int c_info[AV_NCON];  // geom1 | geom2 << 8 | dim << 16 | excluded << 20
     int ncon, nsc, ncand_p, ncand_c, status;
 };
@@ -274,20 +275,21 @@ __device__ inline Shape load_shape(const DevModel &m, const EnvS &S, int g) {
     return s;
 }
 
-__device__ inline void add_contact(const DevModel &m, EnvS &S, int slot, int g1, int g2, float dist, V3 pos, V3 nrm) {
+__device__ inline void add_contact(const DevModel &m, EnvS &S, float *scratch, int slot, int g1, int g2, float dist, V3 pos, V3 nrm) {
     V3 t1, t2;
     make_frame(nrm, t1, t2);
-    st3(S.c_pos + 3 * slot, pos);
-    st3(S.c_frame + 9 * slot, nrm); st3(S.c_frame + 9 * slot + 3, t1); st3(S.c_frame + 9 * slot + 6, t2);
-    S.c_dist[slot] = dist;
+    float *geo = scratch + slot * AV_CBLK + AV_CB_GEO;
+    st3(geo, pos);
+    st3(geo + 3, nrm); st3(geo + 6, t1); st3(geo + 9, t2);
+    geo[12] = dist;
     int dim = max(m.geom_condim[g1], m.geom_condim[g2]);
-    for (int k = 0; k < 3; k++) S.c_mu[3 * slot + k] = fmaxf(m.geom_friction[3 * g1 + k], m.geom_friction[3 * g2 + k]);
+    for (int k = 0; k < 3; k++) geo[13 + k] = fmaxf(m.geom_friction[3 * g1 + k], m.geom_friction[3 * g2 + k]);
     float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]), gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
     int excluded = !(dist < margin - gap);
     S.c_info[slot] = g1 | (g2 << 8) | (dim << 16) | (excluded << 20);
 }
 
-__device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, int lane, bool multiccd, Prof &pf) {
+__device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd, Prof &pf) {
     if (lane == 0) { S.ncon = 0; S.ncand_p = 0; S.ncand_c = 0; }
     __syncwarp();
     // broadphase: bounding spheres + world AABBs, pair list strided over lanes, warp-aggregated append
@@ -338,7 +340,7 @@ __device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, int lane, b
         int total = __shfl_sync(AV_FULL, incl, 31), start = S.ncon + incl - o.n;
         __syncwarp();
         for (int c = 0; c < o.n; c++) {
-            if (start + c < AV_NCON) add_contact(m, S, start + c, g1, g2, o.dist[c], o.pos[c], o.nrm);
+            if (start + c < AV_NCON) add_contact(m, S, scratch, start + c, g1, g2, o.dist[c], o.pos[c], o.nrm);
             else S.status |= 2;
         }
         if (lane == 0) S.ncon = min(AV_NCON, S.ncon + total);
@@ -365,7 +367,7 @@ __device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, int lane, b
             int n0 = S.ncon;
             __syncwarp();
             if (lane < o.n) {
-                if (n0 + lane < AV_NCON) add_contact(m, S, n0 + lane, g1, g2, o.dist[lane], o.pos[lane], o.nrm);
+                if (n0 + lane < AV_NCON) add_contact(m, S, scratch, n0 + lane, g1, g2, o.dist[lane], o.pos[lane], o.nrm);
                 else S.status |= 2;
             }
             if (lane == 0) S.ncon = min(AV_NCON, n0 + o.n);

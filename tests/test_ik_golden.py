@@ -159,4 +159,5 @@ def test_gpu_gradik(gold, gpu_model, arm):
               joint_displacement_weight=(50.0,) * n)
     args = (gold[f"gradik_q_{arm}"], gold[f"gradik_pos_{arm}"], gold[f"gradik_quat_{arm}"])
     ctl, ctl8 = kinematics.GradIK(gpu_model, arm, **kw), kinematics.GradIK(gpu_model, arm, **dict(kw, max_iterations=8))
-    _check_gradik(ctl.run(*args), ctl8.run(*args), gold, arm, gpu_model.table)
+    from av_aloha_b200 import model_io
+    _check_gradik(ctl.run(*args), ctl8.run(*args), gold, arm, model_io.load_avm(gpu_model.avm_path))
