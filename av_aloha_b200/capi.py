@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("AVSIM_LIB") or os.path.join(_HERE, "csrc", "libavsim.
 # avsim_field
 QPOS, QVEL, CTRL, WARMSTART, AGENT_POS, REWARD, SUCCESS, NCON, CONTACTS, STATUS, LATCH, QACC, XPOS, QFRC_BIAS, \
     QACC_SMOOTH, MASS_DIAG, ENV_CYCLES = range(17)
-MAX_CONTACTS = 40
+MAX_CONTACTS = 64
 
 SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",

@@ -18,7 +18,7 @@
 #define AV_NTREE 6
 #define AV_TD 8         // max dofs per kinematic tree
 #define AV_MBLK (AV_NTREE * AV_TD * AV_TD)
-#define AV_NCON 40      // max contacts per environment (== AVSIM_MAX_CONTACTS)
+#define AV_NCON 64      // max contacts per environment (== AVSIM_MAX_CONTACTS)
 #define AV_NSC 20       // max scalar constraint rows (equality + friction loss + joint limits)
 #define AV_NCAND 64     // broadphase survivors per class
 #define AV_MAX_WARPS 14  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory

@@ -289,34 +289,8 @@ __device__ inline void add_contact(const DevModel &m, EnvS &S, float *scratch, i
     S.c_info[slot] = g1 | (g2 << 8) | (dim << 16) | (excluded << 20);
 }
 
-__device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd, Prof &pf) {
-    if (lane == 0) { S.ncon = 0; S.ncand_p = 0; S.ncand_c = 0; }
-    __syncwarp();
-    // broadphase: bounding spheres + world AABBs, pair list strided over lanes, warp-aggregated append
-    for (int base = 0; base < m.npair; base += 32) {
-        int p = base + lane, hit = 0, pk = 0;
-        if (p < m.npair) {
-            pk = m.pair_geom[p];
-            int g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
-            V3 d = ld3(S.gpos + 3 * g2) - ld3(S.gpos + 3 * g1);
-            V3 h = ld3(S.gaabb + 3 * g1) + ld3(S.gaabb + 3 * g2);
-            float rs = m.pair_rsum[p];
-            hit = dot(d, d) <= rs * rs && fabsf(d.x) <= h.x && fabsf(d.y) <= h.y && fabsf(d.z) <= h.z;
-        }
-        int isconv = ((pk >> 16) & 0xff) == AV_PAIR_CONVEX;
-        unsigned mp = __ballot_sync(AV_FULL, hit && !isconv), mc = __ballot_sync(AV_FULL, hit && isconv);
-        int np = S.ncand_p, nc = S.ncand_c;
-        __syncwarp();
-        if (hit) {
-            unsigned below = (1u << lane) - 1u;
-            if (!isconv) { int s = np + __popc(mp & below); if (s < AV_NCAND) S.cand_p[s] = pk; else S.status |= 2; }
-            else { int s = nc + __popc(mc & below); if (s < AV_NCAND) S.cand_c[s] = pk; else S.status |= 2; }
-        }
-        if (lane == 0) { S.ncand_p = min(AV_NCAND, np + __popc(mp)); S.ncand_c = min(AV_NCAND, nc + __popc(mc)); }
-        __syncwarp();
-    }
-    pf.mark(PF_BROAD, lane);
-    // primitive pairs: one candidate per lane
+// primitive candidates (sphere / box pairs): one candidate per lane; drains S.cand_p
+__device__ inline void narrow_primitive(const DevModel &m, EnvS &S, float *scratch, int lane) {
     for (int base = 0; base < S.ncand_p; base += 32) {
         int k = base + lane;
         PrimOut o;
@@ -346,8 +320,12 @@ __device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, float *scra
         if (lane == 0) S.ncon = min(AV_NCON, S.ncon + total);
         __syncwarp();
     }
-    pf.mark(PF_PRIM, lane);
-    // convex pairs: oriented-box rejection per lane, then warp-cooperative MPR one pair at a time
+    if (lane == 0) S.ncand_p = 0;
+    __syncwarp();
+}
+// convex candidates (mesh hulls, cylinders): oriented-box rejection per lane, then warp-cooperative MPR one pair at a
+// time; drains S.cand_c
+__device__ inline void narrow_convex(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd) {
     for (int base = 0; base < S.ncand_c; base += 32) {
         int k = base + lane, keep = 0;
         if (k < S.ncand_c) {
@@ -374,6 +352,49 @@ __device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, float *scra
             __syncwarp();
         }
     }
+    if (lane == 0) S.ncand_c = 0;
+    __syncwarp();
+}
+
+// The pair table lists all primitive pairs before all convex pairs (model compiler), so draining the primitive list
+// before the convex one -- whenever a list reaches a warp's worth of candidates, and at the end -- yields contacts in
+// pair-table order: the same order the oracle's single loop produces.  The lists can therefore never overflow.
+__device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd, Prof &pf) {
+    if (lane == 0) { S.ncon = 0; S.ncand_p = 0; S.ncand_c = 0; }
+    __syncwarp();
+    // broadphase: bounding spheres + world AABBs, pair list strided over lanes, warp-aggregated append
+    for (int base = 0; base < m.npair; base += 32) {
+        int p = base + lane, hit = 0, pk = 0;
+        if (p < m.npair) {
+            pk = m.pair_geom[p];
+            int g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
+            V3 d = ld3(S.gpos + 3 * g2) - ld3(S.gpos + 3 * g1);
+            V3 h = ld3(S.gaabb + 3 * g1) + ld3(S.gaabb + 3 * g2);
+            float rs = m.pair_rsum[p];
+            hit = dot(d, d) <= rs * rs && fabsf(d.x) <= h.x && fabsf(d.y) <= h.y && fabsf(d.z) <= h.z;
+        }
+        int isconv = ((pk >> 16) & 0xff) == AV_PAIR_CONVEX;
+        unsigned mp = __ballot_sync(AV_FULL, hit && !isconv), mc = __ballot_sync(AV_FULL, hit && isconv);
+        if (!(mp | mc)) continue;
+        int np = S.ncand_p, nc = S.ncand_c;
+        __syncwarp();
+        if (hit) {
+            unsigned below = (1u << lane) - 1u;
+            if (!isconv) S.cand_p[np + __popc(mp & below)] = pk;
+            else S.cand_c[nc + __popc(mc & below)] = pk;
+        }
+        if (lane == 0) { S.ncand_p = np + __popc(mp); S.ncand_c = nc + __popc(mc); }
+        __syncwarp();
+        if (S.ncand_p >= 32) narrow_primitive(m, S, scratch, lane);
+        if (S.ncand_c >= 32) {
+            narrow_primitive(m, S, scratch, lane);
+            narrow_convex(m, S, scratch, lane, multiccd);
+        }
+    }
+    pf.mark(PF_BROAD, lane);
+    narrow_primitive(m, S, scratch, lane);
+    pf.mark(PF_PRIM, lane);
+    narrow_convex(m, S, scratch, lane, multiccd);
     pf.mark(PF_CONVEX, lane);
 }
 

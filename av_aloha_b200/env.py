@@ -91,7 +91,11 @@ def reference_reset_draws(task: str, free_joint_names, rng=None) -> np.ndarray:
         if isinstance(lo, str):
             pos[joint] = pos[lo]
             continue
-        p = rng.uniform(np.asarray(lo, np.float64), np.asarray(hi, np.float64))
+        lo_a, hi_a = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+        # == legacy np.random.uniform(lo, hi) bit for bit (lo + (hi - lo) * u), also for the reference's reversed range
+        # x in [-0.1, -0.2] (env.py:485), which numpy's new Generator.uniform refuses
+        u = rng.random_sample(3) if hasattr(rng, "random_sample") else rng.random(3)
+        p = lo_a + (hi_a - lo_a) * u
         if joint is not None:
             pos[joint] = p
     return np.stack([pos[j] for j in free_joint_names])

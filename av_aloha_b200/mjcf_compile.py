@@ -514,6 +514,10 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
             if not ((G["contype"][i] & G["conaffinity"][j]) or (G["contype"][j] & G["conaffinity"][i])):
                 continue
             pairs.append((i, j))
+    # primitive pairs (sphere / box on both sides) first, then the convex ones, each group in geom order: the CUDA
+    # narrowphase drains a primitive and a convex candidate list and must emit contacts in this table's order
+    prim = lambda g: G["type"][g] in (GEOM_SPHERE, GEOM_BOX)
+    pairs = [p for p in pairs if prim(p[0]) and prim(p[1])] + [p for p in pairs if not (prim(p[0]) and prim(p[1]))]
     pairs = np.array(pairs, np.int32).reshape(-1, 2)
 
     # ---- equality, actuators

@@ -48,7 +48,7 @@ enum avsim_field {
     AVSIM_MASS_DIAG = 15,  /* f32 [nv]      diagonal of the joint-space inertia                                */
     AVSIM_ENV_CYCLES = 16  /* i64 [1]       SM cycles the last avsim_step spent on this environment (load-balance diagnostics) */
 };
-#define AVSIM_MAX_CONTACTS 40
+#define AVSIM_MAX_CONTACTS 64
 
 /* ---- model: replaces mjcf.from_path + Physics.from_mjcf_model (reference env.py:53-56).
  * `avm_path` is a compiled model table produced by av_aloha_b200/mjcf_compile.py from the reference's MJCF. */

@@ -55,7 +55,7 @@ class EmuBatch:
         self.B = num_envs
         d = lambda k: lib().emu_dim(self.ptr, k)
         self.nq, self.nv, self.nu, self.nbody, self.nj, self.nfree = (d(k) for k in range(6))
-        self._w = dict(qpos=self.nq, qvel=self.nv, ctrl=self.nu, warm=self.nv, agent_pos=self.nj, contacts=40 * 16,
+        self._w = dict(qpos=self.nq, qvel=self.nv, ctrl=self.nu, warm=self.nv, agent_pos=self.nj, contacts=64 * 16,
                        qacc=self.nv, xpos=3 * self.nbody, qfrc_bias=self.nv, qacc_smooth=self.nv, mass_diag=self.nv)
 
     def __getattr__(self, name):

@@ -58,3 +58,36 @@ def test_one_env_step_resting_contacts(ctx):
     r = o.step(act)
     assert eb.ncon[0] == o.ncon and eb.reward[0] == r and eb.status[0] == 0
     assert np.abs(eb.qpos[0] - o.qpos).max() <= 1e-4
+
+
+def test_mixed_primitive_and_convex_contacts_keep_oracle_order(ctx):
+    """stick wedged under the left fingers (mesh-hull contacts, MPR + multiccd) while the slot rests on the table
+    (box-box contacts): same contact list in the same order as the oracle, and one env.step at a fixed, unconverged
+    sweep count agrees -- which it only can if both walk the contacts in the same order"""
+    EmuBatch, om, OracleEnv, path = ctx
+    fp = np.array([[[0.0, 0.12, -0.002], [0.06, -0.011, 0.133]]])
+    eb = EmuBatch(path, 1)
+    eb.set_options(30)
+    eb.reset(fp)
+    o = OracleEnv(om)
+    o.set_options(max_iter=30, tol=0.0)
+    o.reset(free_pos=fp[0])
+    o.forward()
+    assert o.ncon == eb.ncon[0] and o.ncon >= 6
+    oc = o.contacts()
+    ec = eb.contacts[0].reshape(-1, 16)[: o.ncon]
+    assert np.array_equal(ec[:, 7:9].astype(int), oc[:, 13:15].astype(int))          # geom pairs, in order
+    mesh = set(np.nonzero(np.array([7 == t for t in _geom_types(path)]))[0])
+    assert any(int(g) in mesh for g in oc[:, 13]) and any(int(g) not in mesh and int(h) not in mesh for g, h in oc[:, 13:15])
+    assert np.abs(ec[:, 0] - oc[:, 0]).max() <= 1e-5 and np.abs(ec[:, 1:4] - oc[:, 1:4]).max() <= 1e-4
+    act = HOME.copy()
+    act[6] = act[13] = 1.0
+    eb.step(act[None].astype(np.float32), 20)
+    r = o.step(act)
+    assert eb.ncon[0] == o.ncon and eb.reward[0] == r
+    assert np.abs(eb.qpos[0] - o.qpos).max() <= 2e-4
+
+
+def _geom_types(path):
+    from av_aloha_b200 import model_io
+    return model_io.load_avm(path)["geom_type"]

@@ -1,0 +1,117 @@
+"""GPU tests of the gym_guided_vision-facing host mirror (av_aloha_b200/env.py) against the oracle and against the
+contract lerobot's rollout relies on (gymnasium 0.29 SyncVectorEnv semantics)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HOME = np.array([0, -0.082, 1.06, 0, -0.953, 0, 0.02239] * 2 + [0, -0.8, 0.8, 0, 0.5, 0, 0])
+
+
+def _hold(nj):
+    a = HOME[:nj].copy()
+    a[6] = a[13] = 1.0
+    return a.astype(np.float32)
+
+
+def test_single_env_api_and_oracle_parity():
+    from av_aloha_b200 import env, model_io
+    from oracle.oracle import OracleEnv, OracleModel
+
+    e = env.make("gym_guided_vision/SlotInsertion-3Arms-v0", cameras=[])
+    assert e.num_joints == 21 and e.max_reward == 4 and e.action_space.shape == (21,)
+    np.random.seed(1000)                                    # the yaml seed; reset consumes the GLOBAL np.random like the reference
+    obs, info = e.reset(seed=1000)
+    assert info == {"is_success": False} and obs["agent_pos"].dtype == np.float64 and obs["agent_pos"].shape == (21,)
+    assert obs["pixels"] == {}
+    np.random.seed(1000)
+    fp = env.reference_reset_draws("slot_insertion", model_io.load_names("slot_insertion", 3)["free_joint"])
+    o = OracleEnv(OracleModel(model_io.model_path("slot_insertion", 3)))
+    o.reset(free_pos=fp)
+    assert np.abs(obs["agent_pos"] - o.agent_pos()[:21]).max() <= 1e-6
+    assert np.abs(obs["agent_pos"][[6, 13]] - 1.0).max() <= 1e-6      # grippers open, normalised (env.py:233-242)
+    a = _hold(21)
+    for _ in range(3):
+        obs, reward, terminated, truncated, info = e.step(a)
+        r = o.step(a.astype(np.float64))
+    assert (reward, terminated, truncated) == (r, False, False) and info == {"is_success": reward == 4}
+    assert np.abs(obs["agent_pos"] - o.agent_pos()[:21]).max() <= 1e-4
+    # set_qpos + step_action (env.py:251-269)
+    e.set_qpos(o.qpos)
+    e.step_action(a)
+    assert isinstance(e.get_reward(), int)
+    with pytest.raises(NotImplementedError):
+        e.render()
+    e.close()
+
+
+def test_two_arm_env_matches_oracle():
+    from av_aloha_b200 import env, model_io
+    from oracle.oracle import OracleEnv, OracleModel
+
+    e = env.InsertPegEnv(num_arms=2, cameras=[])
+    assert e.num_joints == 14
+    np.random.seed(5)
+    obs, _ = e.reset()
+    np.random.seed(5)
+    fp = env.reference_reset_draws("insert_peg", model_io.load_names("insert_peg", 2)["free_joint"])
+    o = OracleEnv(OracleModel(model_io.model_path("insert_peg", 2)))
+    o.reset(free_pos=fp)
+    a = _hold(14)
+    for _ in range(2):
+        obs, reward, *_ = e.step(a)
+        r = o.step(np.concatenate([a, HOME[14:]]).astype(np.float64))
+    assert reward == r and obs["agent_pos"].shape == (14,)
+    assert np.abs(obs["agent_pos"] - o.agent_pos()[:14]).max() <= 1e-4
+    e.close()
+
+
+def test_vector_env_syncvectorenv_semantics():
+    from av_aloha_b200 import env
+
+    B, T = 6, 3
+    v = env.GuidedVisionVectorEnv("slot_insertion", B, num_arms=3, cameras=[], max_episode_steps=T, seed=3)
+    assert v.num_envs == B and v.call("_max_episode_steps")[0] == T and v.unwrapped.metadata["render_fps"] == pytest.approx(25)
+    obs, info = v.reset(seed=list(range(B)))
+    assert obs["agent_pos"].shape == (B, 21) and obs["agent_pos"].dtype == np.float64
+    acts = np.tile(_hold(21), (B, 1))
+    for t in range(T):
+        obs, reward, terminated, truncated, info = v.step(acts)
+        assert reward.shape == (B,) and reward.dtype == np.float64
+        assert terminated.dtype == bool and not terminated.any()
+        if t < T - 1:
+            assert not truncated.any() and "final_info" not in info
+    # last step of the episode: truncation, final_info with is_success, observation already from the auto-reset
+    assert truncated.all() and info["_final_info"].all()
+    assert all(set(fi) >= {"is_success"} for fi in info["final_info"])
+    assert all(fo["agent_pos"].shape == (21,) for fo in info["final_observation"])
+    assert np.abs(obs["agent_pos"][:, [6, 13]] - 1.0).max() <= 1e-6           # fresh episode: grippers open at home
+    obs2, *_ = v.step(acts)                                                    # and stepping continues
+    assert np.isfinite(obs2["agent_pos"]).all()
+    succ, rew = v.success_and_max_reward()
+    assert succ.shape == (B,) and rew.shape == (B,)
+    v.close()
+
+
+def test_device_reset_stays_in_reference_ranges_and_masks():
+    import torch
+    from av_aloha_b200 import capi, model_io
+
+    model = capi.Model(model_io.model_path("hook_package", 2), 0)
+    B = 512
+    b = capi.Batch(model, B, seed=11)
+    b.reset()
+    q0 = b.get(capi.QPOS).cpu().numpy()
+    lo, hi = model.table("reset_lo"), model.table("reset_hi")
+    fq = model.table("free_qadr")
+    for k in range(model.nfree):
+        p = q0[:, fq[k]:fq[k] + 3]
+        assert (p >= np.minimum(lo[k], hi[k]) - 1e-6).all() and (p <= np.maximum(lo[k], hi[k]) + 1e-6).all()
+        assert np.allclose(q0[:, fq[k] + 3:fq[k] + 7], [1, 0, 0, 0])
+        assert p[:, 0].std() > 0.01                                       # environments get different draws
+    mask = np.zeros(B, np.uint8)
+    mask[::2] = 1
+    b.reset(mask=mask)                                                     # second episode for the even environments only
+    q1 = b.get(capi.QPOS).cpu().numpy()
+    assert np.array_equal(q1[1::2], q0[1::2]) and not np.array_equal(q1[::2], q0[::2])
+    b.close()
