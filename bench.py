@@ -41,6 +41,7 @@ EPISODE_LEN = 300
 ALGO_BYTES_PER_ENV_STEP = 1032   # fp32 state read + written per env.step
 HOME = np.array([0, -0.082, 1.06, 0, -0.953, 0, 0.02239] * 2 + [0, -0.8, 0.8, 0, 0.5, 0, 0], np.float64)
 METRIC = "env-steps/sec SlotInsertion-3Arms batch=4096"
+NCU_DRAM_BYTES_PER_LAUNCH = 845.2e6   # dram read 54.1 MB + write 791.2 MB per launch at B=4096 (profiles/r1_step_kernel_ncu.txt)
 
 
 def make_workload(B, seed):
@@ -323,8 +324,10 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(B * model.njoints * 4 + B * 4), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": how, "kernel": "avsim_step_kernel",
-                         "note": "latency/FP32-ALU bound by construction (SURVEY.md 8d): 1032 algorithmic bytes per env-step"},
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if B == 4096 else None, "peak_source": how, "kernel": "avsim_step_kernel",
+                         "note": "instruction-issue / latency bound by construction (SURVEY.md 8d): 1032 algorithmic bytes per "
+                                 "env-step x 4096 envs per launch; traffic = dram read+write of one launch from "
+                                 "profiles/r1_step_kernel_ncu.txt (solver scratch spilling out of L2)"},
             "clocks": clocks,
             "health": {"blown_up_envs": n_bad, "contact_overflow_envs": n_ovf, "ncon_mean": ncon_mean,
                        "reward_max": rew_max, "reward_mean": rew_mean, "successes": n_succ, "wall_s": wall,
@@ -332,7 +335,7 @@ def run_gpu(args):
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
-            n_envs, n_steps = 2 * max(cores, 4), 10
+            n_envs, n_steps = 2 * max(cores, 4), 150
             v, dt = cpu_steps_per_sec(n_envs, n_steps, cores, args.solver_iters)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_envs} envs x {n_steps} env.steps at staggered episode phases, {dt:.1f} s timed, "
