@@ -23,6 +23,9 @@
 #define AV_NCAND 64     // broadphase survivors per class
 #define AV_MAX_WARPS 14  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
 #define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
+#ifndef AV_BULK_PREFETCH
+#define AV_BULK_PREFETCH 0 // 1: TMA bulk prefetch of contact blocks in the solver sweep (measured slower, see avsim_solve.cuh)
+#endif
 #define AV_JW 16        // columns of a contact Jacobian block: 8 dofs of tree1 | 8 dofs of tree2
 
 enum { AV_JNT_FREE = 0, AV_JNT_SLIDE = 2, AV_JNT_HINGE = 3 };

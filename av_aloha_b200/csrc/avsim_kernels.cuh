@@ -9,6 +9,20 @@ extern __shared__ float4 av_smem_raw[];
 #define AV_SHARED __shared__   // the host emulation harness maps it to `static` (one variable per block)
 #endif
 
+// once per kernel and warp: the two mbarriers of the solver's contact-block double buffer
+__device__ inline void env_pipe_init(EnvS &S, int lane) {
+#if AV_BULK_PREFETCH
+    if (lane == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        S.cuse[0] = S.cuse[1] = 0;
+    }
+    __syncwarp();
+#else
+    (void)S; (void)lane;
+#endif
+}
+
 __device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane) {
     for (int i = lane; i < m.nq; i += 32) S.qpos[i] = B.qpos[(size_t)env * m.nq + i];
     for (int i = lane; i < m.nv; i += 32) { S.qvel[i] = B.qvel[(size_t)env * m.nv + i]; S.warm[i] = B.warm[(size_t)env * m.nv + i]; }
@@ -103,6 +117,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
     EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + warp);
     AV_SHARED int s_base;
     Prof pf;
+    env_pipe_init(S, lane);
     for (;;) {
         if (warp == 0 && lane == 0) s_base = atomicAdd(B.queue, W);
         __syncthreads();
@@ -149,6 +164,7 @@ __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const 
                                                                          const uint8_t *__restrict__ mask) {
     int lane = threadIdx.x;
     EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
+    env_pipe_init(S, lane);
     for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
         if (mask && !mask[env]) continue;
         Prof pf;

@@ -129,6 +129,42 @@ __device__ __forceinline__ float4 ldg4(const float4 *p) {
 #endif
 }
 
+// ---- bulk asynchronous copy (TMA engine, 1-D) of one contact block from the L2-resident scratch into shared memory,
+// completion signalled on an mbarrier.  Used by the solver sweep to prefetch the next contact's block while the
+// current one is being updated.  The host emulation harness replaces these with plain copies.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// generic-proxy accesses (this warp's earlier loads / stores) ordered before the async proxy touches the same memory
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded wait: returns false if the phase did not complete (the caller then reads the block from global memory)
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned parity) {
+    for (int spin = 0; spin < 4096; spin++) {
+        unsigned ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+#else
+static inline void mbar_init(unsigned long long *, int) {}
+static inline void fence_proxy_async() {}
+static inline void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }
+static inline bool mbar_wait(unsigned long long *, unsigned) { return true; }
+#endif
+
 // ---- warp collectives (one warp == one environment)
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

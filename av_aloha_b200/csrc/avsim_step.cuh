@@ -14,6 +14,7 @@
 #include "avsim_collide.cuh"
 
 #define AV_CB_GEO (52 + 6 * AV_JW)   // offset of the contact geometry inside a scratch block (layout: avsim_solve.cuh)
+static_assert((AV_CB_GEO * 4) % 16 == 0 && (AV_CBLK * 4) % 16 == 0, "bulk copies move 16-byte multiples");
 
 // ---- optional per-stage cycle counters (-DAVSIM_PROFILE; read back with avsim_stage_cycles)
 enum { PF_LOAD = 0, PF_KIN, PF_INERTIA, PF_BROAD, PF_PRIM, PF_CONVEX, PF_SMOOTH, PF_ROWS_S, PF_ROWS_C, PF_SOLVE, PF_INTEGRATE,
@@ -77,6 +78,13 @@ struct EnvS {
     };
     // contacts (collision .. outputs); position / frame / distance / friction live in the contact's global scratch block
     int c_info[AV_NCON];  // geom1 | geom2 << 8 | dim << 16 | excluded << 20
+    // optional solver pipeline (-DAV_BULK_PREFETCH=1): double buffer for the contact block being updated / prefetched by
+    // bulk async copies, its two mbarriers and how often each buffer has been filled (phase parity)
+#if AV_BULK_PREFETCH
+    __align__(16) float cbuf[2][AV_CB_GEO];
+    unsigned long long mbar[2];
+    unsigned cuse[2];
+#endif
     int ncon, nsc, ncand_p, ncand_c, status;
 };
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");

@@ -39,7 +39,7 @@ enum avsim_field {
     AVSIM_SUCCESS = 6,     /* i32 [1]       reward == max_reward         (env.py:224)                          */
     AVSIM_NCON = 7,        /* i32 [1]       data.ncon                                                          */
     AVSIM_CONTACTS = 8,    /* f32 [AVSIM_MAX_CONTACTS][16]: dist,pos3,normal3,geom1,geom2,dim,excluded,force_n,pad4 */
-    AVSIM_STATUS = 9,      /* i32 [1]       bit0 = numerical blow-up (auto-reset), bit1 = contact overflow     */
+    AVSIM_STATUS = 9,      /* i32 [1]       bit0 numerical blow-up, bit1 contact overflow (> 64), bit2 scalar-row overflow, bit3 block prefetch timed out */
     AVSIM_LATCH = 10,      /* i32 [1]       SewNeedle _threaded_needle   (env.py:602,631,673)                  */
     AVSIM_QACC = 11,       /* f32 [nv]      data.qacc of the last forward pass                                 */
     AVSIM_XPOS = 12,       /* f32 [nbody*3] data.xpos of the last forward pass                                 */
