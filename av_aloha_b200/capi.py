@@ -22,7 +22,7 @@ MAX_CONTACTS = 64
 SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
-    "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles",
+    "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render",
 ]
 
 
@@ -64,6 +64,7 @@ def load_library():
     L.avsim_get.argtypes = [vp, i32, vp]
     L.avsim_set.argtypes = [vp, i32, vp]
     L.avsim_step_host.argtypes = [vp, vp, i32, vp, vp]
+    L.avsim_render.argtypes = [vp, C.POINTER(C.c_int), i32, i32, i32, vp]
     L.avsim_launch_count.restype = C.c_int64; L.avsim_launch_count.argtypes = [vp]
     L.avsim_diffik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(DiffIKParams), vp, vp]
     L.avsim_gradik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(GradIKParams), vp, vp]
@@ -197,6 +198,15 @@ class Batch:
 
     def forward(self):
         check(self.lib.avsim_forward(self.ptr))
+
+    def render(self, cam_ids, height=480, width=640, out=None):
+        """uint8 CUDA tensor [B, ncam, H, W, 3] of the current state (cam_ids: indices into the model's camera list)."""
+        t = self.torch
+        ids = (C.c_int * len(cam_ids))(*[int(c) for c in cam_ids])
+        if out is None:
+            out = t.empty((self.num_envs, len(cam_ids), height, width, 3), dtype=t.uint8, device=self.dev)
+        check(self.lib.avsim_render(self.ptr, ids, len(cam_ids), height, width, C.c_void_p(out.data_ptr())))
+        return out
 
     def get(self, field, out=None):
         t = self.torch

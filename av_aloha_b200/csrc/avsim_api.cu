@@ -13,6 +13,7 @@
 #include "avsim_ik.cuh"
 #include "avsim_kernels.cuh"
 #include "avsim_model_pack.h"
+#include "avsim_render.cuh"
 
 #define AV_SORT_MAX 8192
 #ifndef AV_DEFAULT_WARPS
@@ -91,6 +92,7 @@ extern "C" int avsim_model_dim(const avsim_model *m, const char *what) {
     if (w == "max_reward") return d.max_reward;
     if (w == "task_id") return d.task_id;
     if (w == "num_arms") return d.num_arms;
+    if (w == "ncam") return d.ncam;
     return fail(AVSIM_ERR_ARG, "avsim_model_dim: unknown dimension '%s'", what);
 }
 
@@ -105,6 +107,8 @@ struct avsim_batch {
     float *h_action = nullptr, *h_agent = nullptr;   // pinned staging for the host-buffer path
     int32_t *h_reward = nullptr;
     float *d_action = nullptr;
+    float *d_rpose = nullptr;   // render: world pose of every geom and camera, [B][ngeom + ncam][12]
+    int *d_camids = nullptr;
 };
 
 template <typename T>
@@ -143,7 +147,8 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     }
     // step kernel: persistent blocks of W warps (W environments in lockstep, see avsim_kernels.cuh); W x sizeof(EnvS)
     // of dynamic shared memory.  Diagnostic overrides: AVSIM_WARPS (warps per block), AVSIM_BLOCKS (blocks per SM).
-    const char *ew = getenv("AVSIM_WARPS"), *eb = getenv("AVSIM_BLOCKS");
+    const char *ew = getenv("AVSIM_WARPS"), *eb = getenv("AVSIM_BLOCKS"), *es = getenv("AVSIM_SYNC");
+    s.sync = es ? atoi(es) : 3;
     int sms = 0, smem_sm = 0, smem_blk = 0;
     CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
     CUP(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device));
@@ -155,6 +160,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     per_sm = std::max(1, std::min(per_sm, smem_sm / (b->warps * esz + 1024)));
     CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->warps * esz));
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
+    CUP(cudaFuncSetAttribute(avsim_render_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SORT_MAX * (int)sizeof(unsigned long long)));
     b->grid = std::min((num_envs + b->warps - 1) / b->warps, per_sm * sms);
     b->fwd_grid = std::min(num_envs, 8 * sms);
@@ -293,6 +299,30 @@ extern "C" int avsim_step_host(avsim_batch *b, const float *action_host, int nsu
     CU(cudaStreamSynchronize(b->stream));
     if (agent_pos_host) memcpy(agent_pos_host, b->h_agent, na * sizeof(float));
     if (reward_host) memcpy(reward_host, b->h_reward, b->st.num_envs * sizeof(int32_t));
+    return AVSIM_OK;
+}
+
+// render: replaces physics.render(h, w, camera_id) per configured camera (reference env.py:180-188, 195-200)
+extern "C" int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev) {
+    if (!b || !cam_ids_host || !dst_dev || ncam < 1 || ncam > 8 || H < 1 || W < 4 || (W % 4))
+        return fail(AVSIM_ERR_ARG, "avsim_render: bad arguments (1..8 cameras, width a multiple of 4)");
+    const DevModel &d = b->model->dm;
+    for (int k = 0; k < ncam; k++)
+        if (cam_ids_host[k] < 0 || cam_ids_host[k] >= d.ncam) return fail(AVSIM_ERR_ARG, "avsim_render: camera id out of range");
+    CU(cudaSetDevice(b->model->device));
+    size_t n = (size_t)b->st.num_envs;
+    if (!b->d_rpose) {
+        if (!dalloc(b, &b->d_rpose, n * (d.ngeom + d.ncam) * 12) || !dalloc(b, &b->d_camids, 8))
+            return fail(AVSIM_ERR_CUDA, "avsim_render: device allocation failed");
+    }
+    CU(cudaMemcpyAsync(b->d_camids, cam_ids_host, ncam * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    avsim_render_prep_kernel<<<b->fwd_grid, 32, sizeof(EnvS), b->stream>>>(d, b->st, b->d_rpose, d.ncam, d.cam_body, d.cam_pos, d.cam_quat);
+    CU(cudaGetLastError());
+    dim3 grid(((W + AV_RT_W - 1) / AV_RT_W) * ((H + AV_RT_H - 1) / AV_RT_H), ncam, (unsigned)n);
+    avsim_render_kernel<<<grid, AV_RT_W * AV_RT_H, 0, b->stream>>>(d, b->d_rpose, d.geom_rgba, d.geom_visible, d.cam_fovy, b->d_camids, ncam,
+                                                               d.ncam, H, W, dst_dev);
+    b->launches += 2;
+    CU(cudaGetLastError());
     return AVSIM_OK;
 }
 

@@ -67,6 +67,10 @@ struct DevModel {
     const int *obs_qadr, *finger_qadr, *free_qadr;
     const float *reset_lo, *reset_hi;        // [nfree*3] uniform ranges of the task reset
     const int *reset_draw;                   // Philox stream layout (which draw feeds which coordinate)
+    // cameras / render colours (K9)
+    int ncam;
+    const int *cam_body, *geom_visible;
+    const float *cam_pos, *cam_quat, *cam_fovy, *geom_rgba;
     // IK tables
     const int *ik_ndof;
     const float *ik_w0, *ik_p0, *ik_site0, *ik_range;
@@ -84,6 +88,7 @@ struct BatchState {
     long long *env_cycles;                          // [B] SM cycles the last step kernel spent on each environment
     uint64_t seed;
     int solver_iters, noslip_iters, multiccd;
+    int sync;   // lockstep granularity of a block's warps: 2 = barrier after every stage, 1 = once per substep, 0 = none
 };
 
 // per-contact block in global scratch (avsim_solve.cuh): AR 21 | Lc 15 | b 6 | R 4 | mu 3 | 1/mu 3 | J[6][16] |

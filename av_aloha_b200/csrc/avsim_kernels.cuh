@@ -105,10 +105,10 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
 // Environments differ ~5x in cost; avsim_order_kernel sorts the queue by the cycles each environment took in the
 // previous step (costliest first), which (a) fills the tail of the launch with cheap environments and (b) puts
 // environments of similar cost into the same block, so the lockstep barriers wait for little.
-#define AV_STAGE_SYNC(call)      \
-    do {                         \
-        if (active) { call; }    \
-        __syncthreads();         \
+#define AV_STAGE_SYNC(call)              \
+    do {                                 \
+        if (active) { call; }            \
+        if (B.sync >= 2) __syncthreads(); \
     } while (0)
 
 __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
@@ -140,11 +140,18 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
             __syncwarp();
         }
         for (int s = 0; s < nsub; s++) {
+            if (B.sync == 1) __syncthreads();
             AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
             AV_STAGE_SYNC(stage_collision(m, S, scratch, lane, B.multiccd != 0, pf));
             AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane); pf.mark(PF_ROWS_S, lane);
                           stage_rows_contact(m, S, scratch, lane); pf.mark(PF_ROWS_C, lane));
-            AV_STAGE_SYNC(stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters); pf.mark(PF_SOLVE, lane));
+            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane));
+            for (int it = 0; it < B.solver_iters + B.noslip_iters; it++) {   // sync 3: the sweeps in lockstep too
+                if (active) solve_sweep(m, S, scratch, lane, it >= B.solver_iters);
+                if (B.sync >= 3) __syncthreads();
+            }
+            pf.mark(PF_SOLVE, lane);
+            if (B.sync == 2) __syncthreads();
             AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
         }
         AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane));

@@ -242,6 +242,9 @@ inline bool pack_model(const char *avm_path, PackedModel &out) {
     PF(act_kp, "act_kp"); PF(act_kv, "act_kv"); PF(act_ctrl_lo, "act_ctrl_lo"); PF(act_ctrl_hi, "act_ctrl_hi");
     PI(obs_qadr, "obs_qadr"); PI(finger_qadr, "finger_qadr"); PI(free_qadr, "free_qadr");
     PF(reset_lo, "reset_lo"); PF(reset_hi, "reset_hi"); PI(reset_draw, "reset_draw");
+    d.ncam = a.len("cam_body");
+    PI(cam_body, "cam_body"); PI(geom_visible, "geom_visible");
+    PF(cam_pos, "cam_pos"); PF(cam_quat, "cam_quat"); PF(cam_fovy, "cam_fovy"); PF(geom_rgba, "geom_rgba");
     PI(ik_ndof, "ik_ndof"); PF(ik_w0, "ik_w0"); PF(ik_p0, "ik_p0"); PF(ik_site0, "ik_site0"); PF(ik_range, "ik_range");
 #undef PF
 #undef PI

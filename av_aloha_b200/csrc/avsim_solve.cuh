@@ -439,7 +439,9 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
 #endif
 }
 
-__device__ AV_STAGE void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters) {
+// warm start: acc <- M^-1 J^T f_warm, kept only if it beats f = 0.  The sweeps themselves are driven by the caller
+// (stage_solve below, or the step kernel with a block barrier per sweep).
+__device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *scratch, int lane) {
     int col = lane & 15, half = lane >> 4;
     // acc <- M^-1 J^T f_warm  (constraint part of the acceleration); dual cost of the warm start
     for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
@@ -490,5 +492,8 @@ __device__ AV_STAGE void stage_solve(const DevModel &m, EnvS &S, float *scratch,
         for (int i = lane; i < AV_NCON * 6; i += 32) S.c_f[i] = 0.f;
         __syncwarp();
     }
+}
+__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters) {
+    stage_solve_begin(m, S, scratch, lane);
     for (int it = 0; it < iters + noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= iters);
 }

@@ -113,9 +113,11 @@ def _model(task, num_arms, device):
 
 def _check_cameras(cameras):
     assert all(c in CAMERAS for c in cameras), f"Invalid camera names: {cameras}"
-    if len(cameras):
-        raise NotImplementedError("camera observations need the rasteriser kernel (avsim_render), which is not built yet; "
-                                  "pass cameras=[] (the reference allows it: env.py:868)")
+
+
+def _camera_ids(task, num_arms, cameras):
+    names = model_io.load_names(task, num_arms)["camera"]
+    return [names.index(c) for c in cameras]
 
 
 class GuidedVisionEnv(_EnvBase):
@@ -145,17 +147,26 @@ class GuidedVisionEnv(_EnvBase):
         self.action_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float32)
         self._agent = np.zeros((1, self.num_joints), np.float32)
         self._reward = np.zeros((1,), np.int32)
+        self._cam_ids = _camera_ids(self.task, num_arms, self.cameras)
+        self._render_cam = _camera_ids(self.task, num_arms, [RENDER_CAMERA])
+
+    def _pixels(self):
+        if not self.cameras:
+            return {}
+        img = self._batch.render(self._cam_ids, self.observation_height, self.observation_width).cpu().numpy()
+        return {c: img[0, k] for k, c in enumerate(self.cameras)}
 
     # -- observation / reward (reference env.py:168-193)
     def get_obs(self):
         agent = self._batch.get(capi.AGENT_POS).cpu().numpy()[0].astype(np.float64)
-        return {"pixels": {}, "agent_pos": agent}
+        return {"pixels": self._pixels(), "agent_pos": agent}
 
     def get_reward(self):
         return int(self._batch.get(capi.REWARD).cpu().numpy()[0])
 
     def render(self):
-        raise NotImplementedError("render() needs the rasteriser kernel (avsim_render), which is not built yet")
+        """225 x 300 frame of the overhead camera (reference env.py:195-200)"""
+        return self._batch.render(self._render_cam, 225, 300).cpu().numpy()[0, 0]
 
     # -- stepping (reference env.py:203-226, 255-269)
     def step_action(self, action):
@@ -164,7 +175,7 @@ class GuidedVisionEnv(_EnvBase):
 
     def step(self, action):
         self.step_action(action)
-        observation = {"pixels": {}, "agent_pos": self._agent[0].astype(np.float64)}
+        observation = {"pixels": self._pixels(), "agent_pos": self._agent[0].astype(np.float64)}
         reward = int(self._reward[0])
         return observation, reward, False, False, {"is_success": reward == self.max_reward}
 
@@ -283,8 +294,12 @@ class GuidedVisionVectorEnv:
         self._elapsed = np.zeros(self.num_envs, np.int64)
         self._agent = np.zeros((self.num_envs, self.num_joints), np.float32)
         self._reward = np.zeros((self.num_envs,), np.int32)
+        self.observation_height, self.observation_width = observation_height, observation_width
+        self._cam_ids = _camera_ids(self.task, num_arms, self.cameras)
+        self._render_cam = _camera_ids(self.task, num_arms, [RENDER_CAMERA])
         self.single_observation_space = spaces.Dict({
-            "pixels": spaces.Dict({}),
+            "pixels": spaces.Dict({c: spaces.Box(low=0, high=255, shape=(observation_height, observation_width, 3),
+                                                 dtype=np.uint8) for c in self.cameras}),
             "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float64)})
         self.single_action_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float32)
 
@@ -292,8 +307,14 @@ class GuidedVisionVectorEnv:
     def unwrapped(self):
         return self
 
+    def _pixels(self):
+        if not self.cameras:
+            return {}
+        img = self._batch.render(self._cam_ids, self.observation_height, self.observation_width).cpu().numpy()
+        return {c: img[:, k] for k, c in enumerate(self.cameras)}
+
     def _obs(self):
-        return {"pixels": {}, "agent_pos": self._agent.astype(np.float64)}
+        return {"pixels": self._pixels(), "agent_pos": self._agent.astype(np.float64)}
 
     def _reset_rows(self, mask):
         fp = None
@@ -321,8 +342,9 @@ class GuidedVisionVectorEnv:
             final_obs = np.empty(self.num_envs, object)
             final_info = np.empty(self.num_envs, object)
             agent64 = self._agent.astype(np.float64)
+            last_px = self._pixels()                      # the last real frames, rendered before the auto-reset
             for e in np.nonzero(truncated)[0]:
-                final_obs[e] = {"pixels": {}, "agent_pos": agent64[e].copy()}
+                final_obs[e] = {"pixels": {c: v[e].copy() for c, v in last_px.items()}, "agent_pos": agent64[e].copy()}
                 final_info[e] = {"is_success": bool(self._reward[e] == self.max_reward), "TimeLimit.truncated": True}
             info = {"final_observation": final_obs, "_final_observation": truncated.copy(),
                     "final_info": final_info, "_final_info": truncated.copy()}
@@ -341,7 +363,9 @@ class GuidedVisionVectorEnv:
         return tuple([v] * self.num_envs)
 
     def render(self):
-        raise NotImplementedError("render() needs the rasteriser kernel (avsim_render), which is not built yet")
+        """tuple of 225 x 300 overhead frames, one per environment (what `env.call("render")` returns, eval.py:259-263)"""
+        img = self._batch.render(self._render_cam, 225, 300).cpu().numpy()
+        return tuple(img[e, 0] for e in range(self.num_envs))
 
     def success_and_max_reward(self):
         """Per-env (reward == max_reward, reward) of the last step as CUDA tensors: the payload of the one collective of the

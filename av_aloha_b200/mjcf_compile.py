@@ -257,6 +257,12 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
     for d in root.findall("default"):
         defaults.ingest(d)
 
+    # ---- materials (render colours; textures are not reproduced: the table's wood texture becomes one flat colour)
+    materials = {}
+    for a in root.findall("asset"):
+        for el in a.findall("material"):
+            materials[el.attrib["name"]] = _f(el.attrib["rgba"], 4) if "rgba" in el.attrib else np.array([0.62, 0.50, 0.38, 1.0])
+
     # ---- mesh assets
     mesh_assets = {}
     for a in root.findall("asset"):
@@ -446,7 +452,7 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
     g_keep = [i for i, at in enumerate(geoms) if int(at["contype"]) or int(at["conaffinity"])]
     hull_names = []
     G = dict(type=[], body=[], pos=[], quat=[], size=[], rbound=[], aabb=[], condim=[], friction=[], solref=[],
-             solimp=[], gap=[], margin=[], hull=[], contype=[], conaffinity=[], name=[])
+             solimp=[], gap=[], margin=[], hull=[], contype=[], conaffinity=[], name=[], rgba=[], visible=[])
     for gi in g_keep:
         at = geoms[gi]
         gt, sz = geom_shape(at)
@@ -479,6 +485,15 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
         G["gap"].append(float(at["gap"])); G["margin"].append(float(at["margin"])); G["hull"].append(hid)
         G["contype"].append(int(at["contype"])); G["conaffinity"].append(int(at["conaffinity"]))
         G["name"].append(at.get("name", ""))
+        # render colour / visibility of the physics geoms (K9 draws them as stand-ins for the visual meshes): group 3
+        # 'collision' geoms of the robot take the black of the visual meshes they stand for; pin-* sensors and the
+        # 0.6 mm pad spheres are not drawn
+        rgba = materials[at["material"]] if at.get("material") in materials else _f(at.get("rgba", "0.5 0.5 0.5 1"), 4)
+        is_robot_hull = gt == GEOM_MESH and int(at.get("group", 0)) == 3
+        if is_robot_hull:
+            rgba = np.array([0.15, 0.15, 0.15, 1.0])
+        vis = not (at.get("name", "").startswith("pin-") or (gt == GEOM_SPHERE and sz[0] < 0.002))
+        G["rgba"].append(rgba); G["visible"].append(int(vis))
     ngeom = len(g_keep)
 
     hull_adr, hull_num, hull_verts = [], [], []
@@ -567,6 +582,7 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
         geom_condim=np.array(G["condim"], np.int32), geom_friction=np.array(G["friction"]),
         geom_solref=np.array(G["solref"]), geom_solimp=np.array(G["solimp"]), geom_gap=np.array(G["gap"]),
         geom_margin=np.array(G["margin"]), geom_hull=np.array(G["hull"], np.int32),
+        geom_rgba=np.array(G["rgba"]), geom_visible=np.array(G["visible"], np.int32),
         hull_adr=np.array(hull_adr, np.int32), hull_num=np.array(hull_num, np.int32), hull_vert=hull_verts,
         pair_geom=pairs,
         eq_dof1=np.array(eq_dof1, np.int32), eq_dof2=np.array(eq_dof2, np.int32),

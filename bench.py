@@ -256,14 +256,15 @@ def run_gpu(args):
         dev_step(advance())
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     l0 = batch.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     w0 = time.perf_counter()
     for k in range(args.steps):
-        flush.zero_()
+        if not args.no_flush:
+            flush.zero_()
         t = advance()
         ev[k][0].record()
         dev_step(t)
@@ -277,6 +278,8 @@ def run_gpu(args):
     n_bad = int((status & 1).sum().item())
     n_ovf = int((status & 2 != 0).sum().item())
     ncon_mean = float(batch.get(capi.NCON).float().mean().item())
+    cyc = batch.get(capi.ENV_CYCLES).double()
+    cyc_stats = {"mean": float(cyc.mean().item()), "p99": float(cyc.quantile(0.99).item()), "max": float(cyc.max().item())}
     rew = batch.get(capi.REWARD)
     rew_max, rew_mean = int(rew.max().item()), float(rew.float().mean().item())
 
@@ -331,7 +334,8 @@ def run_gpu(args):
             "clocks": clocks,
             "health": {"blown_up_envs": n_bad, "contact_overflow_envs": n_ovf, "ncon_mean": ncon_mean,
                        "reward_max": rew_max, "reward_mean": rew_mean, "successes": n_succ, "wall_s": wall,
-                       "preroll_steps": args.preroll, "preroll_s": preroll_s},
+                       "preroll_steps": args.preroll, "preroll_s": preroll_s,
+                       "step_ms_min": float(min(kern_ms)), "step_ms_max": float(max(kern_ms)), "env_sm_cycles": cyc_stats},
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
@@ -355,6 +359,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--solver-iters", type=int, default=20, dest="solver_iters")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-clocks", action="store_true", dest="no_clocks", help="diagnostic: do not poll nvidia-smi during the run")
+    ap.add_argument("--no-flush", action="store_true", dest="no_flush", help="diagnostic: do not flush L2 between timed steps")
     ap.add_argument("--preroll", type=int, default=EPISODE_LEN, help="untimed steps that bring the staggered batch to steady state")
     args = ap.parse_args()
     if args.impl == "reference":

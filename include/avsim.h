@@ -54,7 +54,7 @@ enum avsim_field {
  * `avm_path` is a compiled model table produced by av_aloha_b200/mjcf_compile.py from the reference's MJCF. */
 avsim_model *avsim_model_load(const char *avm_path, int device);
 void avsim_model_free(avsim_model *m);
-int avsim_model_dim(const avsim_model *m, const char *what); /* "nq","nv","nu","nbody","ngeom","njoints","max_reward","task_id","num_arms" */
+int avsim_model_dim(const avsim_model *m, const char *what); /* "nq","nv","nu","nbody","ngeom","njoints","max_reward","task_id","num_arms","ncam" */
 
 /* ---- batch of environments in lockstep: replaces B x GuidedVisionEnv instances under SyncVectorEnv
  * (reference lerobot/common/envs/factory.py:50-56).  `stream` is a cudaStream_t (0 = default stream). */
@@ -79,6 +79,11 @@ int avsim_forward(avsim_batch *b);
 
 int avsim_get(avsim_batch *b, int field, void *dst_dev);
 int avsim_set(avsim_batch *b, int field, const void *src_dev);
+
+/* render: replaces physics.render(height, width, camera_id) for each configured camera (reference env.py:180-188, 195-200).
+ * cam_ids_host: indices into the model's camera list (names in the model's .json sidecar), dst_dev: u8 [B][ncam][H][W][3].
+ * Ray-cast of the physics geoms (mesh geoms as oriented bounding boxes of their hulls); W must be a multiple of 4. */
+int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev);
 
 /* host-buffer convenience path used by the gym-facing wrapper (e2e metric): copies happen inside the call. */
 int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host);

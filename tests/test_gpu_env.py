@@ -40,8 +40,8 @@ def test_single_env_api_and_oracle_parity():
     e.set_qpos(o.qpos)
     e.step_action(a)
     assert isinstance(e.get_reward(), int)
-    with pytest.raises(NotImplementedError):
-        e.render()
+    frame = e.render()                                       # 225 x 300 overhead frame (env.py:195-200)
+    assert frame.shape == (225, 300, 3) and frame.dtype == np.uint8
     e.close()
 
 

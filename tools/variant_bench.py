@@ -10,15 +10,17 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 variants = [tuple(int(x) for x in v.split(":")) for v in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["14:1", "7:2", "4:3", "2:7", "1:14"])]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for nw, nb in variants:
-    os.environ["AVSIM_WARPS"], os.environ["AVSIM_BLOCKS"] = str(nw), str(nb)
+for v in variants:
+    nw, nb = v[0], v[1]
+    sync = v[2] if len(v) > 2 else 2
+    os.environ["AVSIM_WARPS"], os.environ["AVSIM_BLOCKS"], os.environ["AVSIM_SYNC"] = str(nw), str(nb), str(sync)
     model, batch, acts, masks, mask_any, fp, t0 = steady.restore(B, iters)
     ts = []
     for k in range(5):
         e0.record(); steady.step(batch, acts, masks, mask_any, fp, t0 + k); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = sum(ts[2:]) / 3
-    print(f"warps/block={nw} blocks/SM={nb}: {ms:7.1f} ms/step -> {B / ms * 1e3:8.0f} env-steps/s  (first {ts[0]:.0f} ms)  ncon {batch.get(capi.NCON).float().mean().item():.1f}", flush=True)
+    print(f"warps/block={nw} blocks/SM={nb} sync={sync}: {ms:7.1f} ms/step -> {B / ms * 1e3:8.0f} env-steps/s  (first {ts[0]:.0f} ms)  ncon {batch.get(capi.NCON).float().mean().item():.1f}", flush=True)
     cyc = batch.get(capi.ENV_CYCLES).double()
     print(f"      per-env SM cycles of the last step: mean {cyc.mean().item():.3e}  p50 {cyc.median().item():.3e}  p90 {cyc.quantile(0.9).item():.3e} "
           f"p99 {cyc.quantile(0.99).item():.3e}  max {cyc.max().item():.3e}  (kernel {ms * 1.965e6:.3e} cycles)", flush=True)
