@@ -367,6 +367,36 @@ class GuidedVisionVectorEnv:
         img = self._batch.render(self._render_cam, 225, 300).cpu().numpy()
         return tuple(img[e, 0] for e in range(self.num_envs))
 
+    # -- teleop pose-action step (reference data_collection_scripts/sim_env.py:277-312): 23-dim actions
+    # [L pos3 quat4(wxyz) grip | R pos3 quat4 grip | M pos3 quat4]; GradIK for the two manipulators (sim_env.py:89-124),
+    # DiffIK for the camera arm (125-138), gripper ctrl = unnorm(1 - g); everything stays on the device
+    def step_pose(self, actions):
+        import torch
+        from . import kinematics
+
+        if self.num_arms != 3:
+            raise ValueError("pose actions drive all three arms")
+        if not hasattr(self, "_ik"):
+            self._ik = (kinematics.GradIK(self._model, "left", **kinematics.GRADIK_SIM),
+                        kinematics.GradIK(self._model, "right", **kinematics.GRADIK_SIM),
+                        kinematics.DiffIK(self._model, "middle", **kinematics.DIFFIK_SIM))
+        dev = self._batch.dev
+        a = torch.as_tensor(np.asarray(actions, np.float32) if not torch.is_tensor(actions) else actions,
+                            dtype=torch.float32, device=dev).reshape(self.num_envs, 23)
+        q = self._batch.get(capi.AGENT_POS)                      # joint positions (grippers normalised; not used by the IK)
+        left = self._ik[0].run(q[:, 0:6].contiguous(), a[:, 0:3].contiguous(), a[:, 3:7].contiguous())
+        right = self._ik[1].run(q[:, 7:13].contiguous(), a[:, 8:11].contiguous(), a[:, 11:15].contiguous())
+        middle = self._ik[2].run(q[:, 14:21].contiguous(), a[:, 16:19].contiguous(), a[:, 19:23].contiguous())
+        joint = torch.cat([left, 1.0 - a[:, 7:8], right, 1.0 - a[:, 15:16], middle], dim=1).contiguous()
+        self._batch.step(joint, SIM_PHYSICS_ENV_STEP_RATIO)
+        self._agent[:] = self._batch.get(capi.AGENT_POS).cpu().numpy()
+        self._reward[:] = self._batch.get(capi.REWARD).cpu().numpy()
+        self._elapsed += 1
+        obs = self._obs()
+        obs["qvel"] = self._batch.get(capi.QVEL).cpu().numpy().astype(np.float64)
+        obs["ctrl"] = self._batch.get(capi.CTRL).cpu().numpy().astype(np.float64)
+        return obs, self._reward.astype(np.float64), np.zeros(self.num_envs, bool), np.zeros(self.num_envs, bool), {}
+
     def success_and_max_reward(self):
         """Per-env (reward == max_reward, reward) of the last step as CUDA tensors: the payload of the one collective of the
         path (rank-sharded rollouts all_gather these at episode end)."""

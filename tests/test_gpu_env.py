@@ -115,3 +115,38 @@ def test_device_reset_stays_in_reference_ranges_and_masks():
     q1 = b.get(capi.QPOS).cpu().numpy()
     assert np.array_equal(q1[1::2], q0[1::2]) and not np.array_equal(q1[::2], q0[::2])
     b.close()
+
+
+def test_teleop_pose_action_step_tracks_targets():
+    """sim_env.py:277-312: pose actions -> GradIK / DiffIK -> joint targets -> 20 substeps; holding the home poses keeps
+    the arms at home, and moving the left target 3 cm moves the left end effector towards it"""
+    from av_aloha_b200 import env, kinematics, model_io
+
+    B = 4
+    v = env.GuidedVisionVectorEnv("slot_insertion", B, num_arms=3, cameras=[], seed=1, solver_iterations=30)
+    v.reset()
+    home = {"left": env.LEFT_ARM_POSE[:6], "right": env.RIGHT_ARM_POSE[:6], "middle": env.MIDDLE_ARM_POSE}
+    poses = {}
+    for arm, q in home.items():
+        T = kinematics.create_fk_fn(v._model, arm)(np.asarray(q, np.float64))
+        R = T[:3, :3]
+        w = 0.5 * np.sqrt(max(0.0, 1 + np.trace(R)))
+        quat = np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
+        poses[arm] = (T[:3, 3], quat)
+    act = np.concatenate([poses["left"][0], poses["left"][1], [0.0], poses["right"][0], poses["right"][1], [0.0],
+                          poses["middle"][0], poses["middle"][1]])
+    acts = np.tile(act, (B, 1))
+    for _ in range(3):
+        obs, rew, term, trunc, info = v.step_pose(acts)
+    assert obs["agent_pos"].shape == (B, 21) and obs["qvel"].shape[0] == B and obs["ctrl"].shape == (B, 21)
+    assert np.abs(obs["agent_pos"][:, :6] - np.array(home["left"])).max() < 0.02
+    assert np.abs(obs["agent_pos"][:, 14:21] - np.array(home["middle"])).max() < 0.05
+    assert np.abs(obs["agent_pos"][:, [6, 13]] - 1.0).max() < 0.05        # g = 0 -> ctrl = unnorm(1): open
+    acts2 = acts.copy()
+    acts2[:, 2] += 0.03                                                     # raise the left target by 3 cm
+    for _ in range(15):
+        obs, *_ = v.step_pose(acts2)
+    T = kinematics.create_fk_fn(v._model, "left")(obs["agent_pos"][:, :6])
+    dz = T[:, 2, 3] - poses["left"][0][2]            # GradIK trades pose error against joint displacement: it gets part way
+    assert (dz > 0.008).all() and (dz < 0.035).all(), dz
+    v.close()
