@@ -108,6 +108,7 @@ struct avsim_batch {
     int32_t *h_reward = nullptr;
     float *d_action = nullptr;
     float *d_rpose = nullptr;   // render: world pose of every geom and camera, [B][ngeom + ncam][12]
+    float4 *d_rrect = nullptr;  // render: screen rectangle of every geom per requested camera, [B][8][ngeom]
     int *d_camids = nullptr;
 };
 
@@ -312,14 +313,16 @@ extern "C" int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, i
     CU(cudaSetDevice(b->model->device));
     size_t n = (size_t)b->st.num_envs;
     if (!b->d_rpose) {
-        if (!dalloc(b, &b->d_rpose, n * (d.ngeom + d.ncam) * 12) || !dalloc(b, &b->d_camids, 8))
+        if (!dalloc(b, &b->d_rpose, n * (d.ngeom + d.ncam) * 12) || !dalloc(b, &b->d_camids, 8) ||
+            !dalloc(b, &b->d_rrect, n * 8 * d.ngeom))
             return fail(AVSIM_ERR_CUDA, "avsim_render: device allocation failed");
     }
     CU(cudaMemcpyAsync(b->d_camids, cam_ids_host, ncam * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-    avsim_render_prep_kernel<<<b->fwd_grid, 32, sizeof(EnvS), b->stream>>>(d, b->st, b->d_rpose, d.ncam, d.cam_body, d.cam_pos, d.cam_quat);
+    avsim_render_prep_kernel<<<b->fwd_grid, 32, sizeof(EnvS), b->stream>>>(d, b->st, b->d_rpose, b->d_rrect, d.ncam, d.cam_body, d.cam_pos,
+                                                                            d.cam_quat, d.cam_fovy, b->d_camids, ncam, H, W);
     CU(cudaGetLastError());
     dim3 grid(((W + AV_RT_W - 1) / AV_RT_W) * ((H + AV_RT_H - 1) / AV_RT_H), ncam, (unsigned)n);
-    avsim_render_kernel<<<grid, AV_RT_W * AV_RT_H, 0, b->stream>>>(d, b->d_rpose, d.geom_rgba, d.geom_visible, d.cam_fovy, b->d_camids, ncam,
+    avsim_render_kernel<<<grid, AV_RT_W * AV_RT_H, 0, b->stream>>>(d, b->d_rpose, b->d_rrect, d.geom_rgba, d.geom_visible, d.cam_fovy, b->d_camids, ncam,
                                                                d.ncam, H, W, dst_dev);
     b->launches += 2;
     CU(cudaGetLastError());

@@ -11,8 +11,9 @@
 //
 // Two kernels:
 //   avsim_render_prep_kernel  warp per environment: forward kinematics from qpos, world pose of every geom and camera
-//                             -> rpose[B][ngeom + ncam_all][12] (pos 3 | rotation 9), L2 resident
-//   avsim_render_kernel       block per (32 x 8 pixel tile, camera, environment): culls geoms against the tile's cone
+//                             -> rpose[B][ngeom + ncam_all][12] (pos 3 | rotation 9), and the screen rectangle of every
+//                             geom's oriented box in every requested camera -> rrect[B][ncam][ngeom]; L2 resident
+//   avsim_render_kernel       block per (32 x 8 pixel tile, camera, environment): culls geoms by screen rectangle
 //                             into shared memory, one primary ray per thread, nearest hit, shade, stage the tile in shared
 //                             memory and write it as 32-bit words (96 contiguous bytes per tile row).  HBM-write bound:
 //                             H*W*3 bytes per image.
@@ -24,8 +25,10 @@
 #define AV_RT_MAXG 48   // candidate geoms per tile
 
 __global__ void __launch_bounds__(32) avsim_render_prep_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
-                                                               float *__restrict__ rpose, int ncam_all, const int *__restrict__ cam_body,
-                                                               const float *__restrict__ cam_pos, const float *__restrict__ cam_quat) {
+                                                               float *__restrict__ rpose, float4 *__restrict__ rrect, int ncam_all,
+                                                               const int *__restrict__ cam_body, const float *__restrict__ cam_pos,
+                                                               const float *__restrict__ cam_quat, const float *__restrict__ cam_fovy,
+                                                               const int *__restrict__ cam_ids, int ncam, int H, int W) {
     EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
     int lane = threadIdx.x;
     for (int env = blockIdx.x; env < B.num_envs; env += gridDim.x) {
@@ -52,6 +55,55 @@ __global__ void __launch_bounds__(32) avsim_render_prep_kernel(const __grid_cons
             M3 R = mul(Rb, q2m(qnormalize(ldq(cam_quat + 4 * c))));
             st3(out + 12 * (m.ngeom + c), p);
             stm3(out + 12 * (m.ngeom + c) + 3, R);
+        }
+        __syncwarp();
+        // screen-space bounding rectangle of every geom's oriented box in every requested camera: the tile cull of the
+        // render kernel is then four compares per geom (bounding spheres let the long frame extrusions and the table
+        // into every tile).  Empty = (1, 1, 0, 0); a box that straddles the camera plane gets the whole image.
+        for (int ci = 0; ci < ncam; ci++) {
+            int cam = cam_ids[ci];
+            const float *cp = out + 12 * (m.ngeom + cam);
+            V3 o = ld3(cp);
+            M3 Rc = ldm3(cp + 3);
+            float th = tanf(0.5f * cam_fovy[cam] * 0.017453292519943295f), aspect = (float)W / (float)H;
+            for (int g = lane; g < m.ngeom; g += 32) {
+                float4 rect = make_float4(1.f, 1.f, 0.f, 0.f);
+                if (m.geom_visible[g]) {
+                    V3 c = ld3(out + 12 * g);
+                    M3 R = ldm3(out + 12 * g + 3);
+                    int ty = m.geom_type[g];
+                    V3 h = ty == AV_GEOM_MESH ? ld3(m.geom_aabb + 3 * g) : ld3(m.geom_size + 3 * g);
+                    if (ty == AV_GEOM_SPHERE) h = v3(h.x, h.x, h.x);
+                    if (ty == AV_GEOM_CYLINDER) h = v3(h.x, h.x, h.y);
+                    // corners in camera space; the part of the box in front of the near plane z = -zn is the convex hull of
+                    // the in-front corners and the points where box edges cross that plane
+                    const float zn = 0.02f, sx = 0.5f * W / (th * aspect), sy = 0.5f * H / th;
+                    float x0 = 1e30f, y0 = 1e30f, x1 = -1e30f, y1 = -1e30f;
+                    V3 pc[8];
+                    int nfront = 0;
+                    for (int k = 0; k < 8; k++) {
+                        V3 pw = c + mul(R, v3((k & 1) ? h.x : -h.x, (k & 2) ? h.y : -h.y, (k & 4) ? h.z : -h.z));
+                        pc[k] = mulT(Rc, pw - o);
+                        if (pc[k].z <= -zn) {
+                            nfront++;
+                            float iz = -1.0f / pc[k].z, x = 0.5f * W + pc[k].x * iz * sx, y = 0.5f * H - pc[k].y * iz * sy;
+                            x0 = fminf(x0, x); x1 = fmaxf(x1, x); y0 = fminf(y0, y); y1 = fmaxf(y1, y);
+                        }
+                    }
+                    if (nfront > 0 && nfront < 8)
+                        for (int k = 0; k < 8; k++)
+                            for (int bit = 1; bit < 8; bit <<= 1) {
+                                int j = k ^ bit;
+                                if (j < k || (pc[k].z <= -zn) == (pc[j].z <= -zn)) continue;
+                                float t = (-zn - pc[k].z) / (pc[j].z - pc[k].z);
+                                float px_ = pc[k].x + t * (pc[j].x - pc[k].x), py_ = pc[k].y + t * (pc[j].y - pc[k].y);
+                                float x = 0.5f * W + px_ / zn * sx, y = 0.5f * H - py_ / zn * sy;
+                                x0 = fminf(x0, x); x1 = fmaxf(x1, x); y0 = fminf(y0, y); y1 = fmaxf(y1, y);
+                            }
+                    if (nfront > 0) rect = make_float4(fmaxf(x0 - 1.f, -1.f), fmaxf(y0 - 1.f, -1.f), fminf(x1 + 1.f, W + 1.f), fminf(y1 + 1.f, H + 1.f));
+                }
+                rrect[((size_t)env * ncam + ci) * m.ngeom + g] = rect;
+            }
         }
         __syncwarp();
     }
@@ -118,7 +170,7 @@ __device__ inline float ray_geom(const RGeom &g, V3 o, V3 d, V3 &nrm) {
 }
 
 __global__ void __launch_bounds__(AV_RT_W *AV_RT_H) avsim_render_kernel(const __grid_constant__ DevModel m, const float *__restrict__ rpose,
-                                                                        const float *__restrict__ geom_rgb, const int *__restrict__ geom_visible,
+                                                                        const float4 *__restrict__ rrect, const float *__restrict__ geom_rgb, const int *__restrict__ geom_visible,
                                                                         const float *__restrict__ cam_fovy, const int *__restrict__ cam_ids, int ncam,
                                                                         int ncam_all, int H, int W, unsigned char *__restrict__ dst) {
     __shared__ RGeom sg[AV_RT_MAXG];
@@ -139,18 +191,13 @@ __global__ void __launch_bounds__(AV_RT_W *AV_RT_H) avsim_render_kernel(const __
     };
     if (tid == 0) s_n = 0;
     __syncthreads();
-    // cull: a geom's bounding sphere against the cone around the tile's centre ray
+    // cull: the geom's screen rectangle (prep kernel) against this tile
     {
-        float cx = tx * AV_RT_W + 0.5f * AV_RT_W, cy = ty * AV_RT_H + 0.5f * AV_RT_H;
-        V3 dc = ray(cx, cy), dk = ray((float)(tx * AV_RT_W), (float)(ty * AV_RT_H));
-        float cosc = dot(dc, dk), sinc = sqrtf(fmaxf(0.f, 1.f - cosc * cosc));     // half angle of the tile cone
+        const float x0 = (float)(tx * AV_RT_W), y0 = (float)(ty * AV_RT_H);
+        const float4 *rr = rrect + ((size_t)env * ncam + ci) * m.ngeom;
         for (int g = tid; g < m.ngeom; g += blockDim.x) {
-            if (!geom_visible[g]) continue;
-            V3 c = ld3(base + 12 * g) - o;
-            float rb = m.geom_rbound[g], along = dot(c, dc);
-            float perp = sqrtf(fmaxf(0.f, dot(c, c) - along * along));
-            // distance from the sphere centre to the cone surface (conservative): perp*cos - along*sin <= rb
-            if (along + rb <= 0.f || perp * cosc - along * sinc > rb) continue;
+            float4 q = rr[g];
+            if (q.x > q.z || q.x >= x0 + AV_RT_W || q.z < x0 || q.y >= y0 + AV_RT_H || q.w < y0) continue;
             int k = atomicAdd(&s_n, 1);
             if (k < AV_RT_MAXG) {
                 RGeom &r = sg[k];
