@@ -22,7 +22,7 @@ MAX_CONTACTS = 64
 SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
-    "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render",
+    "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render", "avsim_set_warmstart",
 ]
 
 
@@ -58,6 +58,7 @@ def load_library():
     L.avsim_create.restype = vp; L.avsim_create.argtypes = [vp, i32, u64, vp]
     L.avsim_destroy.argtypes = [vp]
     L.avsim_set_options.argtypes = [vp, i32, i32, i32]
+    L.avsim_set_warmstart.argtypes = [vp, i32]
     L.avsim_reset.argtypes = [vp, vp, vp]
     L.avsim_step.argtypes = [vp, vp, i32]
     L.avsim_forward.argtypes = [vp]
@@ -163,6 +164,10 @@ class Batch:
 
     def set_options(self, solver_iters=20, noslip_iters=-1, multiccd=-1):
         check(self.lib.avsim_set_options(self.ptr, solver_iters, noslip_iters, multiccd))
+
+    def set_warmstart(self, mode):
+        """1: MuJoCo-style warm start from the previous qacc (default); 2: per-constraint force cache."""
+        check(self.lib.avsim_set_warmstart(self.ptr, int(mode)))
 
     def reset(self, mask=None, free_pos=None):
         t = self.torch

@@ -130,14 +130,15 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     BatchState &s = b->st;
     memset(&s, 0, sizeof s);
     s.num_envs = num_envs; s.seed = seed;
-    s.solver_iters = 20; s.noslip_iters = d.noslip_iterations; s.multiccd = d.multiccd;
+    s.solver_iters = 20; s.noslip_iters = d.noslip_iterations; s.multiccd = d.multiccd; s.warm_mode = 1;
     size_t B = num_envs;
     bool ok = dalloc(b, &s.qpos, B * d.nq) && dalloc(b, &s.qvel, B * d.nv) && dalloc(b, &s.ctrl, B * d.nu) &&
               dalloc(b, &s.warm, B * d.nv) && dalloc(b, &s.agent_pos, B * d.nj_obs) && dalloc(b, &s.reward, B) &&
               dalloc(b, &s.status, B) && dalloc(b, &s.latch, B) && dalloc(b, &s.ncon, B) && dalloc(b, &s.episode, B) &&
               dalloc(b, &s.contacts, B * AV_NCON * 16) && dalloc(b, &s.qacc, B * d.nv) && dalloc(b, &s.xpos, B * 3 * d.nbody) &&
               dalloc(b, &s.qfrc_bias, B * d.nv) && dalloc(b, &s.qacc_smooth, B * d.nv) && dalloc(b, &s.mass_diag, B * d.nv) &&
-              dalloc(b, &s.scratch, B * AV_SCRATCH_FLOATS) && dalloc(b, &s.env_cycles, B) && dalloc(b, &s.order, B) && dalloc(b, &s.queue, 1) && dalloc(b, &b->d_action, B * d.nj_obs);
+              dalloc(b, &s.scratch, B * AV_SCRATCH_FLOATS) && dalloc(b, &s.env_cycles, B) && dalloc(b, &s.fc_key, B * (AV_NCON + AV_NSC)) && dalloc(b, &s.fc_n, B * 2) &&
+              dalloc(b, &s.fc_val, B * (AV_NCON * 6 + AV_NSC)) && dalloc(b, &s.order, B) && dalloc(b, &s.queue, 1) && dalloc(b, &b->d_action, B * d.nj_obs);
     if (!ok) { fail(AVSIM_ERR_CUDA, "avsim_create: device allocation failed"); avsim_destroy(b); return nullptr; }
     if (cudaMallocHost(&b->h_action, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
         cudaMallocHost(&b->h_agent, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
@@ -184,6 +185,12 @@ extern "C" int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_it
     b->st.solver_iters = solver_iters;
     b->st.noslip_iters = noslip_iters >= 0 ? noslip_iters : b->model->dm.noslip_iterations;
     b->st.multiccd = multiccd >= 0 ? multiccd : b->model->dm.multiccd;
+    return AVSIM_OK;
+}
+
+extern "C" int avsim_set_warmstart(avsim_batch *b, int mode) {
+    if (!b || (mode != 1 && mode != 2)) return fail(AVSIM_ERR_ARG, "avsim_set_warmstart: mode must be 1 (qacc map) or 2 (force cache)");
+    b->st.warm_mode = mode;
     return AVSIM_OK;
 }
 

@@ -85,6 +85,10 @@ struct BatchState {
     float *scratch;                                 // [B][AV_SCRATCH_FLOATS]
     int *order;                                     // [B] environments in the order the step kernel hands them out (costliest first)
     int *queue;                                     // [1] head of that work queue
+    // constraint-force cache (warm start mode 2): forces of the previous solve keyed by constraint identity
+    int *fc_key, *fc_n;                             // [B][AV_NCON + AV_NSC], [B][2] (contact keys, scalar keys)
+    float *fc_val;                                  // [B][AV_NCON * 6 + AV_NSC]
+    int warm_mode;                                  // 1: MuJoCo-style map of qacc_warmstart, 2: force cache
     long long *env_cycles;                          // [B] SM cycles the last step kernel spent on each environment
     uint64_t seed;
     int solver_iters, noslip_iters, multiccd;

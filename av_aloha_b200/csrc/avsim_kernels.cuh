@@ -78,7 +78,16 @@ __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS 
     }
 }
 
-__device__ __forceinline__ void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf) {
+__device__ __forceinline__ FCache env_fcache(const BatchState &B, int env) {
+    FCache fc;
+    fc.key = B.fc_key + (size_t)env * (AV_NCON + AV_NSC);
+    fc.val = B.fc_val + (size_t)env * (AV_NCON * 6 + AV_NSC);
+    fc.n = B.fc_n + 2 * (size_t)env;
+    fc.mode = B.warm_mode;
+    return fc;
+}
+
+__device__ __forceinline__ void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf, const FCache &fc) {
     stage_kinematics(m, S, lane);
     pf.mark(PF_KIN, lane);
     stage_inertia(m, S, lane);
@@ -86,11 +95,11 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
     stage_collision(m, S, scratch, lane, B.multiccd != 0, pf);
     stage_smooth(m, S, lane);
     pf.mark(PF_SMOOTH, lane);
-    stage_rows_scalar(m, S, lane);
+    stage_rows_scalar(m, S, lane, fc);
     pf.mark(PF_ROWS_S, lane);
-    stage_rows_contact(m, S, scratch, lane);
+    stage_rows_contact(m, S, scratch, lane, fc);
     pf.mark(PF_ROWS_C, lane);
-    stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters);
+    stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters, B.warm_mode);   // physics.forward(): the force cache is read, not updated
     pf.mark(PF_SOLVE, lane);
 }
 
@@ -127,6 +136,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
         const bool active = base + warp < B.num_envs;
         const int env = active ? B.order[base + warp] : 0;
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
+        const FCache fc = env_fcache(B, env);
         pf.start();
         long long c0 = clock64();
         if (active) {
@@ -143,13 +153,14 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
             if (B.sync == 1) __syncthreads();
             AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
             AV_STAGE_SYNC(stage_collision(m, S, scratch, lane, B.multiccd != 0, pf));
-            AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane); pf.mark(PF_ROWS_S, lane);
-                          stage_rows_contact(m, S, scratch, lane); pf.mark(PF_ROWS_C, lane));
-            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane));
+            AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane, fc); pf.mark(PF_ROWS_S, lane);
+                          stage_rows_contact(m, S, scratch, lane, fc); pf.mark(PF_ROWS_C, lane));
+            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, B.warm_mode));
             for (int it = 0; it < B.solver_iters + B.noslip_iters; it++) {   // sync 3: the sweeps in lockstep too
                 if (active) solve_sweep(m, S, scratch, lane, it >= B.solver_iters);
                 if (B.sync >= 3) __syncthreads();
             }
+            if (active) stage_cache_store(m, S, lane, fc);
             pf.mark(PF_SOLVE, lane);
             if (B.sync == 2) __syncthreads();
             AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const 
         pf.start();
         env_load(m, B, S, env, lane);
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
-        env_forward(m, B, S, scratch, lane, pf);
+        env_forward(m, B, S, scratch, lane, pf, env_fcache(B, env));
         for (int i = lane; i < m.nv; i += 32) {
             B.qacc[(size_t)env * m.nv + i] = S.qacc_smooth[i] + S.acc[i];
             B.qacc_smooth[(size_t)env * m.nv + i] = S.qacc_smooth[i];
@@ -268,6 +279,7 @@ __global__ void avsim_reset_kernel(DevModel m, BatchState B, const uint8_t *__re
         qpos[qa] = p[0]; qpos[qa + 1] = p[1]; qpos[qa + 2] = p[2];
         qpos[qa + 3] = 1.f; qpos[qa + 4] = qpos[qa + 5] = qpos[qa + 6] = 0.f;
     }
+    B.fc_n[2 * env] = B.fc_n[2 * env + 1] = 0;   // a fresh episode has no force history
     B.latch[env] = 0;
     B.reward[env] = 0;
     B.status[env] = 0;

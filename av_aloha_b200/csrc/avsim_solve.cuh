@@ -170,7 +170,13 @@ __device__ __forceinline__ void qcqp5(const float (&A)[15], const float (&b)[5],
 }
 
 // ------------------------------------------------------------------ K5: contact rows, one contact at a time
-__device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *scratch, int lane) {
+__device__ __forceinline__ int contact_key(const EnvS &S, int c) {
+    int pair = S.c_info[c] & 0xffff, ord = 0;
+    for (int k = c - 1; k >= 0 && (S.c_info[k] & 0xffff) == pair; k--) ord++;
+    return (3 << 24) | pair | (ord << 16);
+}
+
+__device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *scratch, int lane, const FCache &fc) {
     int col = lane & 15, half = lane >> 4;
     for (int c = 0; c < S.ncon; c++) {
         int info = S.c_info[c], g1 = info & 0xff, g2 = (info >> 8) & 0xff, dim = (info >> 16) & 0xf;
@@ -288,6 +294,13 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
 #pragma unroll
         for (int k = 0; k < 15; k++) blk[AV_CB_LC + k] = Lc[k];
         float *f = S.c_f + 6 * c;
+        if (fc.mode == 2) {   // warm start from the force this contact carried in the previous solve (0 when it is new)
+            int key = contact_key(S, c), nc = fc.n[0], hit = -1;
+            for (int k = 0; k < nc; k++)
+                if (fc.key[k] == key) { hit = k; break; }
+#pragma unroll
+            for (int k = 0; k < 6; k++) f[k] = hit >= 0 ? fc.val[6 * hit + k] : 0.f;
+        }
         if (f[0] <= 0.f) {
 #pragma unroll
             for (int k = 0; k < 6; k++) f[k] = 0.f;
@@ -441,7 +454,7 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
 
 // warm start: acc <- M^-1 J^T f_warm, kept only if it beats f = 0.  The sweeps themselves are driven by the caller
 // (stage_solve below, or the step kernel with a block barrier per sweep).
-__device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *scratch, int lane) {
+__device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *scratch, int lane, int warm_mode) {
     int col = lane & 15, half = lane >> 4;
     // acc <- M^-1 J^T f_warm  (constraint part of the acceleration); dual cost of the warm start
     for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
@@ -486,14 +499,27 @@ __device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *sc
         }
     }
     __syncwarp();
-    if (cost >= 0.f) {  // the warm start does not beat f = 0
+    // MuJoCo keeps its warm start only if it beats f = 0; the force cache (mode 2) is kept unconditionally
+    if (warm_mode != 2 && cost >= 0.f) {
         for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
         for (int i = lane; i < AV_NSC; i += 32) S.sc_f[i] = 0.f;
         for (int i = lane; i < AV_NCON * 6; i += 32) S.c_f[i] = 0.f;
         __syncwarp();
     }
 }
-__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters) {
-    stage_solve_begin(m, S, scratch, lane);
+// after the last sweep: remember every constraint's force under its identity key for the next solve's warm start
+__device__ inline void stage_cache_store(const DevModel &m, EnvS &S, int lane, const FCache &fc) {
+    for (int c = lane; c < S.ncon; c += 32) {
+        fc.key[c] = contact_key(S, c);
+        bool live = !((S.c_info[c] >> 20) & 1);
+#pragma unroll
+        for (int k = 0; k < 6; k++) fc.val[6 * c + k] = live ? S.c_f[6 * c + k] : 0.f;
+    }
+    for (int r = lane; r < S.nsc; r += 32) { fc.key[AV_NCON + r] = S.sc_key[r]; fc.val[AV_NCON * 6 + r] = S.sc_f[r]; }
+    if (lane == 0) { fc.n[0] = S.ncon; fc.n[1] = S.nsc; }
+    __syncwarp();
+}
+__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters, int warm_mode) {
+    stage_solve_begin(m, S, scratch, lane, warm_mode);
     for (int it = 0; it < iters + noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= iters);
 }

@@ -71,7 +71,7 @@ struct EnvS {
     union {
         float gpos[AV_NG * 3];  // world centre of every geom
         struct {
-            int sc_dof1[AV_NSC], sc_dof2[AV_NSC], sc_tree[AV_NSC];
+            int sc_dof1[AV_NSC], sc_dof2[AV_NSC], sc_tree[AV_NSC], sc_key[AV_NSC];
             float sc_c1[AV_NSC], sc_c2[AV_NSC], sc_b[AV_NSC], sc_R[AV_NSC], sc_f[AV_NSC], sc_lo[AV_NSC], sc_hi[AV_NSC],
                 sc_A[AV_NSC], sc_aref[AV_NSC], sc_MJ[AV_NSC * AV_TD];
         };
@@ -88,6 +88,15 @@ struct EnvS {
     int ncon, nsc, ncand_p, ncand_c, status;
 };
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");
+
+// per-environment view of the constraint-force cache in global memory (BatchState.fc_*)
+struct FCache {
+    int *key, *n;
+    float *val;
+    int mode;
+};
+// identity of a contact: geom pair + ordinal among the (consecutive) contacts of that pair; same as the oracle's key
+__device__ __forceinline__ int contact_key(const EnvS &S, int c);
 
 __device__ __forceinline__ M3 body_mat(const EnvS &S, int b) { return q2m(ldq(S.xquat + 4 * b)); }
 
@@ -496,7 +505,7 @@ __device__ __forceinline__ void kbi(const DevModel &m, const float *solref, cons
 }
 
 // one scalar row (equality / friction loss / joint limit), written by the lane that found it
-__device__ inline void emit_scalar_row(const DevModel &m, EnvS &S, int r, int d1, int d2, float c1, float c2, float pos,
+__device__ inline void emit_scalar_row(const DevModel &m, EnvS &S, const FCache &fc, int key, int r, int d1, int d2, float c1, float c2, float pos,
                                        float lo, float hi, const float *solref, const float *solimp, float invw) {
     if (r >= AV_NSC) { S.status |= 4; return; }
     float K, B, imp;
@@ -518,11 +527,19 @@ __device__ inline void emit_scalar_row(const DevModel &m, EnvS &S, int r, int d1
     S.sc_R[r] = R; S.sc_A[r] = A; S.sc_lo[r] = lo; S.sc_hi[r] = hi;
     // warm start: primal -> dual map, clamped
     float jw = c1 * S.warm[d1] + (d2 >= 0 ? c2 * S.warm[d2] : 0.f);
-    S.sc_f[r] = fminf(fmaxf(-(jw - aref) / R, lo), hi);
+    float f0 = -(jw - aref) / R;
+    if (fc.mode == 2) {   // force of the same constraint in the previous solve (0 when it is new)
+        f0 = 0.f;
+        int ns = fc.n[1];
+        for (int k = 0; k < ns; k++)
+            if (fc.key[AV_NCON + k] == key) { f0 = fc.val[AV_NCON * 6 + k]; break; }
+    }
+    S.sc_key[r] = key;
+    S.sc_f[r] = fminf(fmaxf(f0, lo), hi);
 }
 
 // rows in MuJoCo's order [equality | friction loss | violated joint limits]; row indices via ballots
-__device__ AV_STAGE void stage_rows_scalar(const DevModel &m, EnvS &S, int lane) {
+__device__ AV_STAGE void stage_rows_scalar(const DevModel &m, EnvS &S, int lane, const FCache &fc) {
     const float BIG = 3.0e38f;
     if (lane < m.neq) {
         int e = lane;
@@ -531,7 +548,7 @@ __device__ AV_STAGE void stage_rows_scalar(const DevModel &m, EnvS &S, int lane)
         float poly = c[0] + x * (c[1] + x * (c[2] + x * (c[3] + x * c[4])));
         float dpoly = c[1] + x * (2 * c[2] + x * (3 * c[3] + x * 4 * c[4]));
         float pos = S.qpos[m.eq_qadr1[e]] - m.qpos0[m.eq_qadr1[e]] - poly;
-        emit_scalar_row(m, S, e, m.eq_dof1[e], m.eq_dof2[e], 1.f, -dpoly, pos, -BIG, BIG, m.eq_solref + 2 * e,
+        emit_scalar_row(m, S, fc, (0 << 24) | e, e, m.eq_dof1[e], m.eq_dof2[e], 1.f, -dpoly, pos, -BIG, BIG, m.eq_solref + 2 * e,
                         m.eq_solimp + 5 * e, m.eq_invweight0[e]);
     }
     int nrow = m.neq;
@@ -541,7 +558,7 @@ __device__ AV_STAGE void stage_rows_scalar(const DevModel &m, EnvS &S, int lane)
         unsigned mk = __ballot_sync(AV_FULL, has);
         if (has) {
             float fl = m.dof_frictionloss[i];
-            emit_scalar_row(m, S, nrow + __popc(mk & ((1u << lane) - 1u)), i, -1, 1.f, 0.f, 0.f, -fl, fl,
+            emit_scalar_row(m, S, fc, (1 << 24) | i, nrow + __popc(mk & ((1u << lane) - 1u)), i, -1, 1.f, 0.f, 0.f, -fl, fl,
                             m.dof_solref + 2 * i, m.dof_solimp + 5 * i, m.dof_invweight0[i]);
         }
         nrow += __popc(mk);
@@ -558,7 +575,7 @@ __device__ AV_STAGE void stage_rows_scalar(const DevModel &m, EnvS &S, int lane)
         unsigned mk = __ballot_sync(AV_FULL, has);
         if (has) {
             int d1 = m.jnt_dofadr[j];
-            emit_scalar_row(m, S, nrow + __popc(mk & ((1u << lane) - 1u)), d1, -1, side ? -1.f : 1.f, 0.f, dist, 0.f, BIG,
+            emit_scalar_row(m, S, fc, (2 << 24) | j, nrow + __popc(mk & ((1u << lane) - 1u)), d1, -1, side ? -1.f : 1.f, 0.f, dist, 0.f, BIG,
                             m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, m.dof_invweight0[d1]);
         }
         nrow += __popc(mk);

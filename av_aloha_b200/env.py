@@ -277,7 +277,7 @@ class GuidedVisionVectorEnv:
     metadata = GuidedVisionEnv.metadata
 
     def __init__(self, task: str, num_envs: int, num_arms: int = 3, cameras=(), max_episode_steps: int = 300,
-                 device: int = 0, solver_iterations: int = 20, seed: int = 0, reference_rng: bool = False,
+                 device: int = 0, solver_iterations: int = 8, warmstart: int = 2, seed: int = 0, reference_rng: bool = False,
                  observation_height: int = 480, observation_width: int = 640):
         self.task = TASK_OF.get(task, task)
         self.cameras = list(cameras)
@@ -289,6 +289,7 @@ class GuidedVisionVectorEnv:
         self._model = _model(self.task, num_arms, device)
         self._batch = capi.Batch(self._model, self.num_envs, seed=seed)
         self._batch.set_options(solver_iters=solver_iterations)
+        self._batch.set_warmstart(warmstart)
         self.max_reward = self._model.max_reward
         self._free_joints = model_io.load_names(self.task, num_arms)["free_joint"]
         self._elapsed = np.zeros(self.num_envs, np.int64)

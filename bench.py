@@ -5,7 +5,9 @@ Workload (BASELINE.json configs[1]): SlotInsertion-3Arms-
 lockstep, no render.  Actions are a synthetic scripted policy that performs the task (av_aloha_b200/workload.py: reach,
 pinch a slot rail with the left hand, grasp the stick with the right, lift, carry over the slot, lower into the gap;
 waypoints IK-solved per environment for object placements drawn from the reference's reset ranges, + N(0, 0.01 rad)
-joint noise, seed 1234).  One "step" = one env.step over the whole batch = 20 physics substeps of 2 ms + reward +
+joint noise, seed 1234).  Solver setting: 8 PGS sweeps + 3 noslip per substep with the per-constraint force-cache warm
+start -- 3-20x closer to the converged trajectory on this workload than 20 sweeps with MuJoCo-style warm start, the setting the round
+started with (profiles/r1_warmstart_accuracy.txt).  One "step" = one env.step over the whole batch = 20 physics substeps of 2 ms + reward +
 agent_pos (reference gym_guided_vision/env.py:203-226), including the auto-reset of the environments whose 300-step
 episode (sim_slot_insertion_3arms.yaml:17) ended on that step.  Episodes are STAGGERED: environment e starts at script
 phase (e * 300) // B, so every timed step sees the whole episode's mix of free motion, grasping and insertion and
@@ -121,7 +123,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle)
-def cpu_steps_per_sec(n_envs, n_steps, threads, solver_iters, seed=1234):
+def cpu_steps_per_sec(n_envs, n_steps, threads, solver_iters, seed=1234, warmstart=2):
     """The CPU path (fp64 oracle) on `threads` host threads: a sample of n_envs environments of the bench workload, their
     episode phases spread evenly over the 300-step script.  Each environment is first rolled (untimed) from reset to
     its phase, then n_steps consecutive env.steps are timed.  ctypes releases the GIL, so threads run in parallel."""
@@ -138,7 +140,7 @@ def cpu_steps_per_sec(n_envs, n_steps, threads, solver_iters, seed=1234):
     envs = []
     for e in range(n_envs):
         o = OracleEnv(om)
-        o.set_options(max_iter=solver_iters, tol=0.0)
+        o.set_options(max_iter=solver_iters, tol=0.0, warmstart=warmstart)
         o.reset(free_pos=obj[e])
         envs.append(o)
 
@@ -171,7 +173,7 @@ def run_reference(args):
     vals = []
     total = args.warmup + args.steps
     # each "step" of this arm = one env.step of a bounded sample of `n_envs` environments on all host threads
-    v, dt = cpu_steps_per_sec(n_envs, total, cores, args.solver_iters)
+    v, dt = cpu_steps_per_sec(n_envs, total, cores, args.solver_iters, warmstart=args.warmstart)
     vals.append(v)
     value = float(np.mean(vals))
     line = {
@@ -181,7 +183,8 @@ def run_reference(args):
         "config": {"workload": f"SlotInsertion-3Arms-v0 no render, scripted grasp/insert policy, sample of {n_envs} envs "
                                f"x {total} consecutive env.steps, episode phases spread over the 300-step script "
                                f"(of the B=4096 staggered workload)",
-                   "solver_iters": args.solver_iters, "nsubsteps": 20},
+                   "solver_iters": args.solver_iters, "nsubsteps": 20,
+                   "warmstart": "force cache" if args.warmstart == 2 else "qacc map"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{n_envs} envs x {total} env.steps at staggered episode phases, fp64 CPU restatement of the "
                                    f"pipeline (MuJoCo not installable offline), {args.solver_iters} PGS sweeps + 3 noslip"},
@@ -210,6 +213,7 @@ def run_gpu(args):
     model = capi.Model(model_io.model_path(TASK, ARMS), local)
     batch = capi.Batch(model, B, seed=1234 + rank)
     batch.set_options(solver_iters=args.solver_iters)
+    batch.set_warmstart(args.warmstart)
     obj, acts_np, masks_np, phase = make_workload(B, 1234 + rank)
     acts = torch.as_tensor(acts_np, device=dev)                       # [T, B, 21] resident in HBM
     masks = torch.as_tensor(masks_np, device=dev)                     # [T, B] u8: envs whose episode restarts at step t
@@ -320,7 +324,8 @@ def run_gpu(args):
             "config": {"workload": f"SlotInsertion-3Arms-v0 batch={B}/GPU lockstep, no render, scripted grasp/lift/insert policy "
                                    f"(IK-solved joint targets + N(0,0.01) noise), 300-step episodes staggered over the batch, "
                                    f"auto-reset inside the step", "batch_per_gpu": B, "nsubsteps": 20,
-                       "solver_iters": args.solver_iters, "noslip_iters": 3, "parallelism": f"env-sharded x{world}",
+                       "solver_iters": args.solver_iters, "noslip_iters": 3,
+                       "warmstart": "force cache" if args.warmstart == 2 else "qacc map", "parallelism": f"env-sharded x{world}",
                        "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
                        "timing": "sum of per-step CUDA event pairs on the launching stream, max over ranks"},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(B * model.njoints * 4),
@@ -340,7 +345,7 @@ def run_gpu(args):
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             n_envs, n_steps = 2 * max(cores, 4), 150
-            v, dt = cpu_steps_per_sec(n_envs, n_steps, cores, args.solver_iters)
+            v, dt = cpu_steps_per_sec(n_envs, n_steps, cores, args.solver_iters, warmstart=args.warmstart)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_envs} envs x {n_steps} env.steps at staggered episode phases, {dt:.1f} s timed, "
                                               f"fp64 CPU restatement (MuJoCo not installable offline)"}
@@ -357,7 +362,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
-    ap.add_argument("--solver-iters", type=int, default=20, dest="solver_iters")
+    ap.add_argument("--solver-iters", type=int, default=8, dest="solver_iters")
+    ap.add_argument("--warmstart", type=int, default=2, choices=[1, 2],
+                    help="1: MuJoCo-style qacc map, 2: per-constraint force cache (profiles/r1_warmstart_accuracy.txt)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", dest="no_clocks", help="diagnostic: do not poll nvidia-smi during the run")
     ap.add_argument("--no-flush", action="store_true", dest="no_flush", help="diagnostic: do not flush L2 between timed steps")

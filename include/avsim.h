@@ -65,6 +65,12 @@ void avsim_destroy(avsim_batch *b);
  * multiccd < 0 takes the model's flag (aloha_sim.xml:5). */
 int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_iters, int multiccd);
 
+/* warm start of the constraint solve.  1 (default): MuJoCo's scheme, the previous qacc mapped to forces (what the reference
+ * does through data.qacc_warmstart).  2: every constraint starts from the force it carried in the previous solve, matched
+ * by identity (geom pair + ordinal); same optimum, but Gauss-Seidel then needs far fewer sweeps for the same accuracy
+ * (profiles/r1_warmstart_accuracy.txt). */
+int avsim_set_warmstart(avsim_batch *b, int mode);
+
 /* reset: replaces GuidedVisionEnv.reset + task reset (env.py:228-249, 474-501, 513-543, 604-637, 705-735, 792-818).
  * mask_dev: u8[B] nullable (null = all envs).  free_pos_dev: f32[B][nfree][3] object positions drawn by the host
  * in the reference's np.random order, nullable (null = Philox draw on the device from (seed, env, episode)). */

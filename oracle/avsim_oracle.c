@@ -206,6 +206,7 @@ typedef struct {
     int noslip_iter;    /* -1: take from model */
     int multiccd;       /* -1: take from model */
     int warmstart;
+    int sweep_mode;     /* 0: forward sweeps (what the CUDA kernel does); 1: alternate forward / backward (experiment) */
 } ora_options;
 
 typedef struct ora_data {
@@ -235,6 +236,9 @@ typedef struct ora_data {
     double qacc[NV_MAX], qfrc_constraint[NV_MAX];
     int solver_iters;
     int reward;
+    /* force cache (opt.warmstart == 2): forces of the previous solve keyed by constraint identity */
+    int cache_n, cache_key[NEFC_MAX], cache_frozen;   /* frozen: physics.forward() reads the cache but does not update it */
+    double cache_f[NEFC_MAX][6];
     long *pair_hist;   /* optional [npair] histogram of pairs reaching the narrowphase (diagnostics) */
 } ora_data;
 
@@ -258,6 +262,7 @@ long *ora_pair_hist(ora_data *d) {
     if (!d->pair_hist) d->pair_hist = (long *)calloc((size_t)d->m->npair, sizeof(long));
     return d->pair_hist;
 }
+void ora_set_sweep_mode(ora_data *d, int mode) { d->opt.sweep_mode = mode; }
 void ora_set_options(ora_data *d, int max_iter, double tol, int noslip_iter, int multiccd, int warmstart) {
     d->opt.max_iter = max_iter; d->opt.tol = tol; d->opt.noslip_iter = noslip_iter; d->opt.multiccd = multiccd;
     d->opt.warmstart = warmstart;
@@ -484,7 +489,7 @@ static void stage_smooth(ora_data *d) {
         memcpy(d->cvel[b], v, sizeof v);
     }
     /* RNE with qacc = 0: bias = Coriolis + centrifugal + gravity (mj_rne) */
-    static double cacc[NB_MAX][6], cfrc[NB_MAX][6];
+    static __thread double cacc[NB_MAX][6], cfrc[NB_MAX][6];
     memset(cacc, 0, sizeof cacc);
     memset(cfrc, 0, sizeof cfrc);
     v3scl(cacc[0] + 3, m->gravity, -1.0);
@@ -602,7 +607,7 @@ static void stage_constraint_rows(ora_data *d) {
         }
     }
     /* contacts: elliptic cone rows {normal, tangent1, tangent2, torsion, roll1, roll2}[:dim] */
-    static double jp1[3][NV_MAX], jr1[3][NV_MAX], jp2[3][NV_MAX], jr2[3][NV_MAX];
+    static __thread double jp1[3][NV_MAX], jr1[3][NV_MAX], jp2[3][NV_MAX], jr2[3][NV_MAX];
     for (int c = 0; c < d->ncon; c++) {
         ora_contact *con = &d->con[c];
         con->efc_adr = -1;
@@ -727,7 +732,30 @@ static void stage_solve(ora_data *d) {
     double *f = d->efc_force;
     /* warm start from qacc_warmstart: primal -> dual map f = -(J a - aref)/R, projected; kept only if it beats f = 0 */
     memset(f, 0, n * sizeof(double));
+    /* identity key of every block: scalar rows (type, id); contacts (geom pair, ordinal within the pair) */
+    int key_of[NEFC_MAX];
+    {
+        int prev_pair = -1, ord = 0;
+        for (int r = 0; r < n; r++) {
+            if (d->efc_type[r] != ROW_CONTACT) { key_of[r] = (d->efc_type[r] << 24) | d->efc_id[r]; continue; }
+            const ora_contact *con = &d->con[d->efc_id[r]];
+            int pair = con->geom1 | (con->geom2 << 8);
+            ord = pair == prev_pair ? ord + 1 : 0;
+            prev_pair = pair;
+            key_of[r] = (ROW_CONTACT << 24) | pair | (ord << 16);
+            for (int k = 1; k < con->dim; k++) key_of[r + k] = -1;
+            r += con->dim - 1;
+        }
+    }
     if (d->opt.warmstart) {
+        if (d->opt.warmstart == 2) {
+            for (int r = 0; r < n; r++) {
+                if (key_of[r] < 0) continue;
+                int dim = d->efc_type[r] == ROW_CONTACT ? d->con[d->efc_id[r]].dim : 1;
+                for (int c = 0; c < d->cache_n; c++)
+                    if (d->cache_key[c] == key_of[r]) { for (int k = 0; k < dim; k++) f[r + k] = d->cache_f[c][k]; break; }
+            }
+        } else
         for (int r = 0; r < n; r++) f[r] = -(rowdot(d, r, d->qacc_warmstart) - d->efc_aref[r]) / d->efc_R[r];
         for (int r = 0; r < n; r++) {
             if (d->efc_type[r] == ROW_FLOSS) f[r] = fmin(fmax(f[r], -d->efc_floss[r]), d->efc_floss[r]);
@@ -743,14 +771,24 @@ static void stage_solve(ora_data *d) {
                 r += con->dim - 1;
             }
         }
-        if (dual_cost(d, f) >= 0) memset(f, 0, n * sizeof(double));
+        /* MuJoCo keeps its warm start only if it beats f = 0; the force cache is kept unconditionally (any feasible start
+         * converges, and the comparison is a knife edge between fp32 and fp64 when both costs are close) */
+        if (d->opt.warmstart != 2 && dual_cost(d, f) >= 0) memset(f, 0, n * sizeof(double));
     }
     /* block projected Gauss-Seidel */
     double trM = 0;
     for (int i = 0; i < nv; i++) trM += d->M[i][i];
+    /* block starts (a scalar row is a block of one, a contact a block of `dim` rows): sweeps walk them forwards, or --
+     * experiment, opt.sweep_mode = 1 -- forwards and backwards alternately (symmetric Gauss-Seidel) */
+    int blk_start[NEFC_MAX], nblk = 0;
+    for (int i = 0; i < n; i++) {
+        blk_start[nblk++] = i;
+        if (d->efc_type[i] == ROW_CONTACT) i += d->con[d->efc_id[i]].dim - 1;
+    }
     for (int it = 0; it < d->opt.max_iter; it++) {
         double improvement = 0; /* decrease of the dual cost over this sweep (exact, block by block) */
-        for (int i = 0; i < n; i++) {
+        for (int kk = 0; kk < nblk; kk++) {
+            int i = blk_start[(d->opt.sweep_mode == 1 && (it & 1)) ? nblk - 1 - kk : kk];
             int type = d->efc_type[i];
             if (type != ROW_CONTACT) {
                 double res = d->efc_b[i] + d->efc_R[i] * f[i];
@@ -807,7 +845,6 @@ static void stage_solve(ora_data *d) {
                 for (int l = 0; l < dim; l++) s += 0.5 * AR[k][l] * (f[i + l] - old[l]);
                 improvement -= (f[i + k] - old[k]) * s;
             }
-            i += dim - 1;
         }
         d->solver_iters = it + 1;
         if (improvement / trM < d->opt.tol) break;
@@ -844,6 +881,13 @@ static void stage_solve(ora_data *d) {
             }
         }
     }
+    if (!d->cache_frozen) d->cache_n = 0;
+    for (int r = 0; r < n && !d->cache_frozen; r++) {
+        if (key_of[r] < 0) continue;
+        int dim = d->efc_type[r] == ROW_CONTACT ? d->con[d->efc_id[r]].dim : 1, c = d->cache_n++;
+        d->cache_key[c] = key_of[r];
+        for (int k = 0; k < 6; k++) d->cache_f[c][k] = k < dim ? f[r + k] : 0.0;
+    }
     for (int r = 0; r < n; r++) {
         const double *x = d->MinvJT + (size_t)r * NV_MAX;
         for (int i = 0; i < nv; i++) {
@@ -858,7 +902,7 @@ static void stage_integrate(ora_data *d) {
     const ora_model *m = d->m;
     int nv = m->nv;
     double h = m->timestep;
-    static double Mh[NV_MAX][NV_MAX], Lh[NV_MAX][NV_MAX];
+    static __thread double Mh[NV_MAX][NV_MAX], Lh[NV_MAX][NV_MAX];
     double acc[NV_MAX];
     memcpy(Mh, d->M, sizeof Mh);
     for (int i = 0; i < nv; i++) {
@@ -960,17 +1004,21 @@ static int stage_reward(ora_data *d) {
 }
 
 /* ------------------------------------------------------------------ public drivers */
-int ora_forward(ora_data *d) {
+static int forward_pass(ora_data *d, int frozen) {
     stage_kinematics(d);
     if (stage_inertia(d)) return -1;
     stage_collision(d);
     stage_smooth(d);
     stage_constraint_rows(d);
+    d->cache_frozen = frozen;
     stage_solve(d);
+    d->cache_frozen = 0;
     return 0;
 }
+/* physics.forward(): like mj_forward it leaves the warm-start state (qacc_warmstart / force cache) untouched */
+int ora_forward(ora_data *d) { return forward_pass(d, 1); }
 int ora_substep(ora_data *d) {
-    if (ora_forward(d)) return -1;
+    if (forward_pass(d, 0)) return -1;
     stage_integrate(d);
     return 0;
 }
@@ -995,6 +1043,7 @@ int ora_env_step(ora_data *d, const double *action, int nsub) {
 }
 /* reference env.py:228-249 + task reset: home pose, open fingers, ctrl = home, object poses, qvel = 0 */
 void ora_reset(ora_data *d, const double *arm_pose /*21*/, const double *free_pos /*nfree*3 or NULL*/) {
+    d->cache_n = 0;   /* a fresh episode has no force history */
     const ora_model *m = d->m;
     memcpy(d->qpos, m->qpos0, m->nq * sizeof(double));
     memset(d->qvel, 0, sizeof(d->qvel));

@@ -54,7 +54,8 @@ struct EmuBatch {
     std::vector<float> f[16];
     std::vector<int> iv[8];
     std::vector<long long> cyc;
-    std::vector<int> order, queue;
+    std::vector<int> order, queue, fckey, fcn;
+    std::vector<float> fcval;
 };
 
 extern "C" {
@@ -74,11 +75,14 @@ EmuBatch *emu_create(const char *path, int num_envs) {
     s.xpos = F(7, B * 3 * d.nbody); s.qfrc_bias = F(8, B * d.nv); s.qacc_smooth = F(9, B * d.nv);
     s.mass_diag = F(10, B * d.nv); s.scratch = F(11, B * AV_SCRATCH_FLOATS);
     b->cyc.assign(B, 0); s.env_cycles = b->cyc.data();
+    b->fckey.assign(B * (AV_NCON + AV_NSC), 0); b->fcn.assign(B * 2, 0); b->fcval.assign(B * (AV_NCON * 6 + AV_NSC), 0.f);
+    s.fc_key = b->fckey.data(); s.fc_n = b->fcn.data(); s.fc_val = b->fcval.data(); s.warm_mode = 1;
     b->order.resize(B); b->queue.assign(1, 0); s.order = b->order.data(); s.queue = b->queue.data();
     s.reward = I(0, B); s.status = I(1, B); s.latch = I(2, B); s.ncon = I(3, B); s.episode = I(4, B);
     return b;
 }
 void emu_destroy(EmuBatch *b) { delete b; }
+void emu_set_warmstart(EmuBatch *b, int mode) { b->st.warm_mode = mode; }
 void emu_set_options(EmuBatch *b, int iters, int noslip, int multiccd) {
     b->st.solver_iters = iters;
     b->st.noslip_iters = noslip >= 0 ? noslip : b->pk.dm.noslip_iterations;

@@ -32,6 +32,7 @@ def lib():
         _lib.emu_create.argtypes = [C.c_char_p, C.c_int]
         _lib.emu_destroy.argtypes = [C.c_void_p]
         _lib.emu_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.emu_set_warmstart.argtypes = [C.c_void_p, C.c_int]
         _lib.emu_dim.argtypes = [C.c_void_p, C.c_int]
         _lib.emu_f.restype = C.POINTER(C.c_float)
         _lib.emu_f.argtypes = [C.c_void_p, C.c_int]
@@ -69,6 +70,9 @@ class EmuBatch:
 
     def set_options(self, iters=50, noslip=-1, multiccd=-1):
         lib().emu_set_options(self.ptr, iters, noslip, multiccd)
+
+    def set_warmstart(self, mode):
+        lib().emu_set_warmstart(self.ptr, mode)
 
     def forward(self):
         lib().emu_forward(self.ptr)

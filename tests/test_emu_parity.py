@@ -91,3 +91,24 @@ def test_mixed_primitive_and_convex_contacts_keep_oracle_order(ctx):
 def _geom_types(path):
     from av_aloha_b200 import model_io
     return model_io.load_avm(path)["geom_type"]
+
+
+def test_force_cache_warm_start_matches_oracle(ctx):
+    """warm start mode 2 (each constraint starts from the force it carried in the previous solve, matched by identity):
+    kernel source and oracle agree at a low, unconverged sweep count over two env.steps with mixed contacts"""
+    EmuBatch, om, OracleEnv, path = ctx
+    fp = np.array([[[0.0, 0.12, -0.002], [0.06, -0.011, 0.133]]])
+    eb = EmuBatch(path, 1)
+    eb.set_options(8)
+    eb.set_warmstart(2)
+    eb.reset(fp)
+    o = OracleEnv(om)
+    o.set_options(max_iter=8, tol=0.0, warmstart=2)
+    o.reset(free_pos=fp[0])
+    act = HOME.copy()
+    act[6] = act[13] = 0.3
+    for _ in range(2):
+        eb.step(act[None].astype(np.float32), 20)
+        r = o.step(act)
+    assert eb.ncon[0] == o.ncon and eb.reward[0] == r and eb.status[0] == 0
+    assert np.abs(eb.qpos[0] - o.qpos).max() <= 2e-4

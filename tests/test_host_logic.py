@@ -94,3 +94,30 @@ def test_model_tables_match_reference_constants():
     names = model_io.load_names("slot_insertion", 2)
     b = names["body"].index("middle_base_link")
     assert np.allclose(m2["body_pos"][b], [0, -2.4, -0.4])
+
+
+def test_oracle_is_thread_safe(slot_model_path):
+    """bench.py's CPU legs step oracle environments from a thread pool (ctypes releases the GIL): concurrent stepping must
+    give bit-identical results to serial stepping (the oracle once kept scratch arrays in function-level statics)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import HOME, OracleEnv, OracleModel
+
+    om = OracleModel(slot_model_path)
+    act = HOME.copy()
+    act[6] = act[13] = 1.0
+
+    def run(e):
+        o = OracleEnv(om)
+        o.set_options(max_iter=10, tol=0.0)
+        o.reset(free_pos=np.array([[0.01 * e, 0.12, 0.0], [0.02, -0.05 + 0.005 * e, 0.0]]))
+        a = act.copy()
+        a[0] += 0.05 * e
+        for _ in range(3):
+            o.step(a)
+        return o.qpos.copy()
+
+    serial = [run(e) for e in range(6)]
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        threaded = list(ex.map(run, range(6)))
+    for a, b in zip(serial, threaded):
+        assert np.array_equal(a, b)

@@ -25,6 +25,7 @@ def setup(B, iters, seed=1234):
     model = capi.Model(model_io.model_path("slot_insertion", 3), 0)
     batch = capi.Batch(model, B, seed=seed)
     batch.set_options(solver_iters=iters)
+    batch.set_warmstart(int(os.environ.get("WARM", "2")))
     obj, acts_np, masks_np, phase = bench.make_workload(B, seed)
     acts = torch.as_tensor(acts_np, device="cuda")
     masks = torch.as_tensor(masks_np, device="cuda")
