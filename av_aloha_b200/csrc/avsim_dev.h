@@ -21,7 +21,7 @@
 #define AV_NCON 64      // max contacts per environment (== AVSIM_MAX_CONTACTS)
 #define AV_NSC 20       // max scalar constraint rows (equality + friction loss + joint limits)
 #define AV_NCAND 64     // broadphase survivors per class
-#define AV_MAX_WARPS 14  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
+#define AV_MAX_WARPS 15  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
 #define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
 #ifndef AV_BULK_PREFETCH
 #define AV_BULK_PREFETCH 0 // 1: TMA bulk prefetch of contact blocks in the solver sweep (measured slower, see avsim_solve.cuh)
@@ -98,4 +98,7 @@ struct BatchState {
 // per-contact block in global scratch (avsim_solve.cuh): AR 21 | Lc 15 | b 6 | R 4 | mu 3 | 1/mu 3 | J[6][16] |
 // geometry (pos 3, frame 9, dist 1, friction 3) written by the narrowphase, read once by the row assembly
 #define AV_CBLK (52 + 6 * AV_JW + 16)
-#define AV_SCRATCH_FLOATS (AV_NCON * AV_CBLK)
+#define AV_NKEEP 32      // convex pairs per environment that survive the box filter
+#define AV_CTMP 24       // floats of one pooled narrowphase result: n | normal 3 | 5 x dist | 5 x pos
+#define AV_SCR_TMP (AV_NCON * AV_CBLK)
+#define AV_SCRATCH_FLOATS (AV_SCR_TMP + AV_NKEEP * AV_CTMP)

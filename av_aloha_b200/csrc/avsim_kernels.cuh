@@ -114,6 +114,35 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
 // Environments differ ~5x in cost; avsim_order_kernel sorts the queue by the cycles each environment took in the
 // previous step (costliest first), which (a) fills the tail of the launch with cheap environments and (b) puts
 // environments of similar cost into the same block, so the lockstep barriers wait for little.
+// Collision of a lockstep block: phase A per environment, then the convex pairs of ALL the block's environments are pooled
+// and every warp (also the ones without an environment) pulls (environment, pair) items, then phase C per environment.
+__device__ __forceinline__ void block_collision(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, int warp, int W,
+                                                bool active, Prof &pf) {
+    AV_SHARED int s_next, s_off[AV_MAX_WARPS + 1];
+    AV_SHARED float *s_scr[AV_MAX_WARPS];
+    if (active) stage_collision_a(m, S, scratch, lane, pf);
+    if (lane == 0) { s_off[warp + 1] = active ? S.nkeep : 0; s_scr[warp] = scratch; }
+    if (warp == 0 && lane == 0) { s_next = 0; s_off[0] = 0; }
+    __syncthreads();
+    if (warp == 0 && lane == 0)
+        for (int w = 0; w < W; w++) s_off[w + 1] += s_off[w];
+    __syncthreads();
+    const int total = s_off[W];
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&s_next, 1);
+        item = __shfl_sync(AV_FULL, item, 0);
+        if (item >= total) break;
+        int w = 0;
+        while (item >= s_off[w + 1]) w++;
+        const EnvS &Se = *(reinterpret_cast<const EnvS *>(av_smem_raw) + w);
+        collide_item(m, Se, s_scr[w], item - s_off[w], lane, B.multiccd != 0);
+    }
+    __syncthreads();
+    if (active) stage_collision_c(m, S, scratch, lane, pf);
+    if (B.sync >= 2) __syncthreads();
+}
+
 #define AV_STAGE_SYNC(call)              \
     do {                                 \
         if (active) { call; }            \
@@ -152,7 +181,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
         for (int s = 0; s < nsub; s++) {
             if (B.sync == 1) __syncthreads();
             AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
-            AV_STAGE_SYNC(stage_collision(m, S, scratch, lane, B.multiccd != 0, pf));
+            block_collision(m, B, S, scratch, lane, warp, W, active, pf);
             AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane, fc); pf.mark(PF_ROWS_S, lane);
                           stage_rows_contact(m, S, scratch, lane, fc); pf.mark(PF_ROWS_C, lane));
             AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, B.warm_mode));
@@ -166,7 +195,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
             AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
         }
         AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane));
-        AV_STAGE_SYNC(stage_collision(m, S, scratch, lane, B.multiccd != 0, pf));
+        block_collision(m, B, S, scratch, lane, warp, W, active, pf);
         if (active) {
             env_store(m, B, S, env, lane);
             env_outputs(m, B, S, scratch, env, lane, true);

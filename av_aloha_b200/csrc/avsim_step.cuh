@@ -57,7 +57,7 @@ struct EnvS {
     float M[AV_MBLK], Minv[AV_MBLK];
     float qfrc_smooth[AV_NVP], qacc_smooth[AV_NVP], acc[AV_NVP], qfrc_bias[AV_NVP];
     union {
-        struct { float gaabb[AV_NG * 3]; int cand_p[AV_NCAND], cand_c[AV_NCAND]; };
+        struct { float gaabb[AV_NG * 3]; int cand_p[AV_NCAND], cand_c[AV_NCAND], keep_c[AV_NKEEP]; };
         struct { float cvel[AV_NB * 6], cdofdot[AV_NV * 6]; };
     };
     union {
@@ -85,7 +85,7 @@ struct EnvS {
     unsigned long long mbar[2];
     unsigned cuse[2];
 #endif
-    int ncon, nsc, ncand_p, ncand_c, status;
+    int ncon, nsc, ncand_p, ncand_c, nkeep, status;
 };
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");
 
@@ -340,44 +340,37 @@ __device__ inline void narrow_primitive(const DevModel &m, EnvS &S, float *scrat
     if (lane == 0) S.ncand_p = 0;
     __syncwarp();
 }
-// convex candidates (mesh hulls, cylinders): oriented-box rejection per lane, then warp-cooperative MPR one pair at a
-// time; drains S.cand_c
-__device__ inline void narrow_convex(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd) {
+// convex candidates (mesh hulls, cylinders): oriented-box rejection, one candidate per lane; survivors are appended to
+// S.keep_c in candidate order; drains S.cand_c
+__device__ inline void filter_convex(const DevModel &m, EnvS &S, int lane) {
     for (int base = 0; base < S.ncand_c; base += 32) {
-        int k = base + lane, keep = 0;
+        int k = base + lane, keep = 0, pk = 0;
         if (k < S.ncand_c) {
-            int pk = S.cand_c[k], g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
+            pk = S.cand_c[k];
+            int g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
             Shape A = load_shape(m, S, g1), B = load_shape(m, S, g2);
             keep = !obb_separated(ld3(m.geom_aabb + 3 * g1), A, ld3(m.geom_aabb + 3 * g2), B);
         }
         unsigned mk = __ballot_sync(AV_FULL, keep);
-        while (mk) {
-            int src = __ffs(mk) - 1;
-            mk &= mk - 1;
-            int pk = S.cand_c[base + src], g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
-            Shape A = load_shape(m, S, g1), B = load_shape(m, S, g2);
-            PrimOut o;
-            bool mc = multiccd && A.type != AV_GEOM_SPHERE && B.type != AV_GEOM_SPHERE;
-            collide_convex(A, B, mc, lane, o);
-            int n0 = S.ncon;
-            __syncwarp();
-            if (lane < o.n) {
-                if (n0 + lane < AV_NCON) add_contact(m, S, scratch, n0 + lane, g1, g2, o.dist[lane], o.pos[lane], o.nrm);
-                else S.status |= 2;
-            }
-            if (lane == 0) S.ncon = min(AV_NCON, n0 + o.n);
-            __syncwarp();
+        int n0 = S.nkeep;
+        __syncwarp();
+        if (keep) {
+            int s = n0 + __popc(mk & ((1u << lane) - 1u));
+            if (s < AV_NKEEP) S.keep_c[s] = pk; else S.status |= 2;
         }
+        if (lane == 0) S.nkeep = min(AV_NKEEP, n0 + __popc(mk));
+        __syncwarp();
     }
     if (lane == 0) S.ncand_c = 0;
     __syncwarp();
 }
 
-// The pair table lists all primitive pairs before all convex pairs (model compiler), so draining the primitive list
-// before the convex one -- whenever a list reaches a warp's worth of candidates, and at the end -- yields contacts in
-// pair-table order: the same order the oracle's single loop produces.  The lists can therefore never overflow.
-__device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd, Prof &pf) {
-    if (lane == 0) { S.ncon = 0; S.ncand_p = 0; S.ncand_c = 0; }
+// Collision, phase A (own environment): broadphase over the pair table, primitive narrowphase, box filter of the convex
+// candidates.  The pair table lists all primitive pairs before all convex pairs (model compiler) and the primitive list
+// is drained before anything convex is emitted, so contacts come out in pair-table order -- the order of the oracle's
+// single loop.  The candidate lists are drained whenever they reach a warp's worth, so they cannot overflow.
+__device__ AV_STAGE void stage_collision_a(const DevModel &m, EnvS &S, float *scratch, int lane, Prof &pf) {
+    if (lane == 0) { S.ncon = 0; S.ncand_p = 0; S.ncand_c = 0; S.nkeep = 0; }
     __syncwarp();
     // broadphase: bounding spheres + world AABBs, pair list strided over lanes, warp-aggregated append
     for (int base = 0; base < m.npair; base += 32) {
@@ -403,16 +396,51 @@ __device__ AV_STAGE void stage_collision(const DevModel &m, EnvS &S, float *scra
         if (lane == 0) { S.ncand_p = np + __popc(mp); S.ncand_c = nc + __popc(mc); }
         __syncwarp();
         if (S.ncand_p >= 32) narrow_primitive(m, S, scratch, lane);
-        if (S.ncand_c >= 32) {
-            narrow_primitive(m, S, scratch, lane);
-            narrow_convex(m, S, scratch, lane, multiccd);
-        }
+        if (S.ncand_c >= 32) filter_convex(m, S, lane);
     }
     pf.mark(PF_BROAD, lane);
     narrow_primitive(m, S, scratch, lane);
+    filter_convex(m, S, lane);
     pf.mark(PF_PRIM, lane);
-    narrow_convex(m, S, scratch, lane, multiccd);
+}
+
+// Collision, phase B: one kept convex pair (index k) of environment S -- which may belong to ANOTHER warp of the block:
+// the lockstep step kernel pools the convex pairs of all its environments and lets every warp pull items, because the
+// number of hull pairs per environment varies from 0 to 15 and the stage barrier would otherwise wait for the unluckiest.
+// Warp-cooperative MPR (+ multiccd); the result goes to the environment's scratch (n | normal | 5 x dist | 5 x pos).
+__device__ AV_STAGE void collide_item(const DevModel &m, const EnvS &S, float *scratch, int k, int lane, bool multiccd) {
+    int pk = S.keep_c[k], g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
+    Shape A = load_shape(m, S, g1), B = load_shape(m, S, g2);
+    PrimOut o;
+    bool mc = multiccd && A.type != AV_GEOM_SPHERE && B.type != AV_GEOM_SPHERE;
+    collide_convex(A, B, mc, lane, o);
+    float *tmp = scratch + AV_SCR_TMP + k * AV_CTMP;
+    if (lane == 0) { tmp[0] = (float)o.n; tmp[1] = o.nrm.x; tmp[2] = o.nrm.y; tmp[3] = o.nrm.z; }
+    if (lane < o.n) { tmp[4 + lane] = o.dist[lane]; st3(tmp + 9 + 3 * lane, o.pos[lane]); }
+    __syncwarp();
+}
+
+// Collision, phase C (own environment): contacts from the pooled results, in candidate order
+__device__ AV_STAGE void stage_collision_c(const DevModel &m, EnvS &S, float *scratch, int lane, Prof &pf) {
+    for (int k = 0; k < S.nkeep; k++) {
+        const float *tmp = scratch + AV_SCR_TMP + k * AV_CTMP;
+        int n = (int)tmp[0], pk = S.keep_c[k], g1 = pk & 0xff, g2 = (pk >> 8) & 0xff, n0 = S.ncon;
+        __syncwarp();
+        if (lane < n) {
+            if (n0 + lane < AV_NCON) add_contact(m, S, scratch, n0 + lane, g1, g2, tmp[4 + lane], ld3(tmp + 9 + 3 * lane), ld3(tmp + 1));
+            else S.status |= 2;
+        }
+        if (lane == 0) S.ncon = min(AV_NCON, n0 + n);
+        __syncwarp();
+    }
     pf.mark(PF_CONVEX, lane);
+}
+
+// the three phases back to back for one warp on its own (forward kernel, host emulation of single-warp blocks)
+__device__ inline void stage_collision(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd, Prof &pf) {
+    stage_collision_a(m, S, scratch, lane, pf);
+    for (int k = 0; k < S.nkeep; k++) collide_item(m, S, scratch, k, lane, multiccd);
+    stage_collision_c(m, S, scratch, lane, pf);
 }
 
 // ------------------------------------------------------------------ K3b: velocity, bias, actuation, smooth acceleration
