@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("AVSIM_LIB") or os.path.join(_HERE, "csrc", "libavsim.
 
 # avsim_field
 QPOS, QVEL, CTRL, WARMSTART, AGENT_POS, REWARD, SUCCESS, NCON, CONTACTS, STATUS, LATCH, QACC, XPOS, QFRC_BIAS, \
-    QACC_SMOOTH, MASS_DIAG, ENV_CYCLES = range(17)
+    QACC_SMOOTH, MASS_DIAG, ENV_CYCLES, FC_KEY, FC_N, FC_VAL = range(20)
 MAX_CONTACTS = 64
 
 SYMBOLS = [
@@ -149,6 +149,7 @@ class Batch:
             STATUS: (None, torch.int32), LATCH: (None, torch.int32), QACC: (m.nv, torch.float32),
             XPOS: ((m.nbody, 3), torch.float32), QFRC_BIAS: (m.nv, torch.float32), QACC_SMOOTH: (m.nv, torch.float32),
             MASS_DIAG: (m.nv, torch.float32), ENV_CYCLES: (None, torch.int64),
+            FC_KEY: (MAX_CONTACTS + 20, torch.int32), FC_N: (2, torch.int32), FC_VAL: (MAX_CONTACTS * 6 + 20, torch.float32),
         }
 
     def close(self):

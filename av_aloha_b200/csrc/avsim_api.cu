@@ -17,7 +17,7 @@
 
 #define AV_SORT_MAX 8192
 #ifndef AV_DEFAULT_WARPS
-#define AV_DEFAULT_WARPS 6
+#define AV_DEFAULT_WARPS 13
 #endif
 
 static thread_local char g_err[512] = "";
@@ -252,6 +252,9 @@ static int field_ptr(avsim_batch *b, int field, void **p, size_t *bytes) {
     case AVSIM_QACC_SMOOTH: *p = s.qacc_smooth; *bytes = B * d.nv * 4; break;
     case AVSIM_MASS_DIAG: *p = s.mass_diag; *bytes = B * d.nv * 4; break;
     case AVSIM_ENV_CYCLES: *p = s.env_cycles; *bytes = B * 8; break;
+    case AVSIM_FC_KEY: *p = s.fc_key; *bytes = B * (AV_NCON + AV_NSC) * 4; break;
+    case AVSIM_FC_N: *p = s.fc_n; *bytes = B * 2 * 4; break;
+    case AVSIM_FC_VAL: *p = s.fc_val; *bytes = B * (AV_NCON * 6 + AV_NSC) * 4; break;
     default: return fail(AVSIM_ERR_ARG, "unknown field");
     }
     return AVSIM_OK;
@@ -282,7 +285,8 @@ extern "C" int avsim_get(avsim_batch *b, int field, void *dst_dev) {
 
 extern "C" int avsim_set(avsim_batch *b, int field, const void *src_dev) {
     if (!b || !src_dev) return fail(AVSIM_ERR_ARG, "avsim_set: null argument");
-    if (field != AVSIM_QPOS && field != AVSIM_QVEL && field != AVSIM_CTRL && field != AVSIM_WARMSTART && field != AVSIM_LATCH)
+    if (field != AVSIM_QPOS && field != AVSIM_QVEL && field != AVSIM_CTRL && field != AVSIM_WARMSTART && field != AVSIM_LATCH &&
+        field != AVSIM_FC_KEY && field != AVSIM_FC_N && field != AVSIM_FC_VAL)
         return fail(AVSIM_ERR_ARG, "avsim_set: field is read-only");
     CU(cudaSetDevice(b->model->device));
     void *p;

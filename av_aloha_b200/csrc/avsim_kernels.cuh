@@ -117,11 +117,14 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
 // Collision of a lockstep block: phase A per environment, then the convex pairs of ALL the block's environments are pooled
 // and every warp (also the ones without an environment) pulls (environment, pair) items, then phase C per environment.
 __device__ __forceinline__ void block_collision(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, int warp, int W,
-                                                bool active, Prof &pf) {
+                                                bool active, Prof &pf, long long &own) {
     AV_SHARED int s_next, s_off[AV_MAX_WARPS + 1];
     AV_SHARED float *s_scr[AV_MAX_WARPS];
+    AV_SHARED unsigned long long s_cost[AV_MAX_WARPS];   // cycles spent (by any warp) on each environment's pooled items
+    long long t0 = clock64();
     if (active) stage_collision_a(m, S, scratch, lane, pf);
-    if (lane == 0) { s_off[warp + 1] = active ? S.nkeep : 0; s_scr[warp] = scratch; }
+    if (active) own += clock64() - t0;
+    if (lane == 0) { s_off[warp + 1] = active ? S.nkeep : 0; s_scr[warp] = scratch; s_cost[warp] = 0ull; }
     if (warp == 0 && lane == 0) { s_next = 0; s_off[0] = 0; }
     __syncthreads();
     if (warp == 0 && lane == 0)
@@ -136,17 +139,29 @@ __device__ __forceinline__ void block_collision(const DevModel &m, const BatchSt
         int w = 0;
         while (item >= s_off[w + 1]) w++;
         const EnvS &Se = *(reinterpret_cast<const EnvS *>(av_smem_raw) + w);
+        long long ti = clock64();
         collide_item(m, Se, s_scr[w], item - s_off[w], lane, B.multiccd != 0);
+        if (lane == 0) atomicAdd(&s_cost[w], (unsigned long long)(clock64() - ti));
     }
     __syncthreads();
+    t0 = clock64();
     if (active) stage_collision_c(m, S, scratch, lane, pf);
+    if (active) own += (clock64() - t0) + (long long)s_cost[warp];
     if (B.sync >= 2) __syncthreads();
 }
 
-#define AV_STAGE_SYNC(call)              \
-    do {                                 \
-        if (active) { call; }            \
-        if (B.sync >= 2) __syncthreads(); \
+// `own` accumulates the cycles this warp spends on ITS environment, excluding the waits at the lockstep barriers: the
+// queue is sorted by it.  (Sorting by wall cycles per environment degenerates within a few dozen steps: in lockstep all
+// environments of a block finish together, so every one of them inherits the cost of the slowest and the order stops
+// reflecting the environments themselves -- measured as a drift from 47 to 58 ms/step.)
+#define AV_STAGE_SYNC(call)                       \
+    do {                                          \
+        if (active) {                             \
+            long long t0_ = clock64();            \
+            call;                                 \
+            own += clock64() - t0_;               \
+        }                                         \
+        if (B.sync >= 2) __syncthreads();         \
     } while (0)
 
 __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
@@ -167,7 +182,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
         const FCache fc = env_fcache(B, env);
         pf.start();
-        long long c0 = clock64();
+        long long own = 0;
         if (active) {
             env_load(m, B, S, env, lane);
             pf.mark(PF_LOAD, lane);
@@ -181,12 +196,16 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
         for (int s = 0; s < nsub; s++) {
             if (B.sync == 1) __syncthreads();
             AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane));
-            block_collision(m, B, S, scratch, lane, warp, W, active, pf);
+            block_collision(m, B, S, scratch, lane, warp, W, active, pf, own);
             AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane, fc); pf.mark(PF_ROWS_S, lane);
                           stage_rows_contact(m, S, scratch, lane, fc); pf.mark(PF_ROWS_C, lane));
             AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, B.warm_mode));
             for (int it = 0; it < B.solver_iters + B.noslip_iters; it++) {   // sync 3: the sweeps in lockstep too
-                if (active) solve_sweep(m, S, scratch, lane, it >= B.solver_iters);
+                if (active) {
+                    long long t0 = clock64();
+                    solve_sweep(m, S, scratch, lane, it >= B.solver_iters);
+                    own += clock64() - t0;
+                }
                 if (B.sync >= 3) __syncthreads();
             }
             if (active) stage_cache_store(m, S, lane, fc);
@@ -195,12 +214,12 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
             AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
         }
         AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane));
-        block_collision(m, B, S, scratch, lane, warp, W, active, pf);
+        block_collision(m, B, S, scratch, lane, warp, W, active, pf, own);
         if (active) {
             env_store(m, B, S, env, lane);
             env_outputs(m, B, S, scratch, env, lane, true);
             pf.mark(PF_OUT, lane);
-            if (lane == 0) B.env_cycles[env] = clock64() - c0;
+            if (lane == 0) B.env_cycles[env] = own;
             __syncwarp();
         }
     }

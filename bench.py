@@ -219,7 +219,7 @@ def run_gpu(args):
     masks = torch.as_tensor(masks_np, device=dev)                     # [T, B] u8: envs whose episode restarts at step t
     mask_any = masks_np.any(axis=1)
     fp_dev = torch.as_tensor(obj.astype(np.float32), device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def barrier():
         if world > 1:

@@ -46,7 +46,10 @@ enum avsim_field {
     AVSIM_QFRC_BIAS = 13,  /* f32 [nv]                                                                          */
     AVSIM_QACC_SMOOTH = 14,/* f32 [nv]                                                                          */
     AVSIM_MASS_DIAG = 15,  /* f32 [nv]      diagonal of the joint-space inertia                                */
-    AVSIM_ENV_CYCLES = 16  /* i64 [1]       SM cycles the last avsim_step spent on this environment (load-balance diagnostics) */
+    AVSIM_ENV_CYCLES = 16, /* i64 [1]       SM cycles the last avsim_step spent on this environment (load-balance diagnostics) */
+    AVSIM_FC_KEY = 17,     /* i32 [84]      force cache: identity keys of the constraints of the last solve (64 contacts | 20 scalar rows) */
+    AVSIM_FC_N = 18,       /* i32 [2]       force cache: number of contact keys, number of scalar-row keys                      */
+    AVSIM_FC_VAL = 19      /* f32 [404]     force cache: 64 x 6 contact forces | 20 scalar-row forces                           */
 };
 #define AVSIM_MAX_CONTACTS 64
 

@@ -95,6 +95,7 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline long long clock64() { return 0; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }   // fibers never preempt between collectives
 using std::isfinite;
 using std::max;

@@ -14,7 +14,9 @@ import torch
 import bench
 from av_aloha_b200 import capi, model_io
 
-FIELDS = {"qpos": capi.QPOS, "qvel": capi.QVEL, "ctrl": capi.CTRL, "warm": capi.WARMSTART, "latch": capi.LATCH}
+FIELDS = {"qpos": capi.QPOS, "qvel": capi.QVEL, "ctrl": capi.CTRL, "warm": capi.WARMSTART, "latch": capi.LATCH,
+          "fc_key": capi.FC_KEY, "fc_n": capi.FC_N, "fc_val": capi.FC_VAL}   # incl. the solver's force cache: without it the
+# first solve after a restore starts from zero forces and the grasped objects slip (a lighter, unrepresentative state)
 
 
 def path(B):
@@ -47,7 +49,8 @@ def restore(B, iters, seed=1234):
         z = np.load(p)
         batch.reset(free_pos=fp)
         for k, f in FIELDS.items():
-            batch.set(f, z[k])
+            if k in z.files:
+                batch.set(f, z[k])
         t0 = int(z["t"])
     else:
         batch.reset(free_pos=fp)
