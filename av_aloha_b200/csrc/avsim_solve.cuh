@@ -391,43 +391,29 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
         if (lane == 0) S.sc_f[r] = x;
         __syncwarp();
     }
-    const int n = S.ncon;
-#if AV_BULK_PREFETCH
-    // contact blocks: the block of contact c + 1 is fetched by the TMA engine (bulk async copy, L2 -> shared) while
-    // contact c is being updated; buffer b's k-th fill completes phase k of its mbarrier.  Measured on B200 this is
-    // SLOWER than reading the blocks straight from L1/L2 (89 vs 81 ms/step: the per-contact cross-proxy fence and the
-    // mbarrier wait cost more than the hidden latency), so it is compiled out by default (-DAV_BULK_PREFETCH=1).
-    const unsigned bytes = AV_CB_GEO * sizeof(float);
-    unsigned use0 = S.cuse[0], use1 = S.cuse[1];
-    if (n > 0 && lane == 0) {
-        fence_proxy_async();
-        bulk_g2s(S.cbuf[0], scratch, bytes, &S.mbar[0]);
-    }
-#endif
-    for (int c = 0; c < n; c++) {
-#if AV_BULK_PREFETCH
-        const int b = c & 1;
-        if (c + 1 < n && lane == 0) {
-            fence_proxy_async();
-            bulk_g2s(S.cbuf[b ^ 1], scratch + (c + 1) * AV_CBLK, bytes, &S.mbar[b ^ 1]);
-        }
-        const unsigned use = b ? use1 : use0;
-        const bool arrived = mbar_wait(&S.mbar[b], use & 1u);
-        if (b) use1++; else use0++;
-        const float *blk = arrived ? S.cbuf[b] : scratch + c * AV_CBLK;
-        if (!arrived && lane == 0) S.status |= 8;
-#else
+    // contacts, two at a time: the schedule (solve_schedule) pairs contacts that touch disjoint kinematic trees; such
+    // updates commute, so each half-warp (16 lanes = the 16 columns of a contact Jacobian) runs its own contact's
+    // update concurrently -- the block update itself is uniform per contact and used to be replicated on all 32 lanes
+    for (int sl = 0; sl < S.nslot; sl++) {
+        const int pr = S.c_slot[sl], ca = pr & 0xff, cb_ = (pr >> 8) & 0xff;
+        const bool valid = !half || cb_ != 0xff;
+        const int c = (half && cb_ != 0xff) ? cb_ : ca;        // an idle second half mirrors the first (results discarded)
+        const int info = S.c_info[c], dim = (info >> 16) & 0xf;
         const float *blk = scratch + c * AV_CBLK;
-#endif
-        int info = S.c_info[c], dim = (info >> 16) & 0xf;
-        if ((info >> 20) & 1) { __syncwarp(); continue; }
-        int tr = S.c_tree[c], dof = tr_dof(tr, col);
+        const int tr = S.c_tree[c], dof = tr_dof(tr, col);
         const float *J = blk + AV_CB_J;
-        float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
+        float jc[6], res[6], old[6], f[6], df[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) jc[k] = J[k * AV_JW + col];
+        const float x = dof >= 0 ? S.acc[dof] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) res[k] = jc[k] * x;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 6; k++) res[k] += __shfl_xor_sync(AV_FULL, res[k], o);
         CBlk cb;
         cblk_load(blk, cb);
-        float res[6], old[6], f[6], df[6];
-        block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
 #pragma unroll
         for (int k = 0; k < 6; k++) old[k] = S.c_f[6 * c + k];
         float lam = S.c_lam[c];
@@ -435,25 +421,54 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
 #pragma unroll
         for (int k = 0; k < 6; k++) df[k] = f[k] - old[k];
         __syncwarp();
-        block_apply(S, j0, j1, j2, df, tr, lane);
-        if (lane < 6) {
+        // acc += Minv_tree (J^T df): this lane's column of J^T df, then the 8x8 block inverse of the column's tree
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) t += jc[k] * df[k];
+        const float *Mi = S.Minv + tr_tree(tr, col) * (AV_TD * AV_TD) + (col & 7) * AV_TD;
+        float da = 0.f;
+#pragma unroll
+        for (int k = 0; k < AV_TD; k++) da += Mi[k] * __shfl_sync(AV_FULL, t, (col & 8) + k, 16);
+        if (valid && dof >= 0) S.acc[dof] += da;
+        if (valid && col < 6) {
             float fv = 0.f;
 #pragma unroll
             for (int k = 0; k < 6; k++)
-                if (k == lane) fv = f[k];
-            S.c_f[6 * c + lane] = fv;
+                if (k == col) fv = f[k];
+            S.c_f[6 * c + col] = fv;
         }
-        if (lane == 6) S.c_lam[c] = lam;
+        if (valid && col == 6) S.c_lam[c] = lam;
         __syncwarp();
     }
-#if AV_BULK_PREFETCH
-    if (lane == 0) { S.cuse[0] = use0; S.cuse[1] = use1; }
-    __syncwarp();
-#endif
 }
 
-// warm start: acc <- M^-1 J^T f_warm, kept only if it beats f = 0.  The sweeps themselves are driven by the caller
-// (stage_solve below, or the step kernel with a block barrier per sweep).
+// Half-warp schedule of the sweep: every not-yet-scheduled contact a is paired with the next later contact b whose
+// kinematic trees are disjoint from a's (b = 0xff when there is none).  Same greedy rule, same order as the oracle.
+__device__ inline void solve_schedule(EnvS &S, int lane) {
+    auto tmask = [&](int c) {
+        if (c >= S.ncon || ((S.c_info[c] >> 20) & 1)) return -1;          // no rows: never scheduled
+        int tr = S.c_tree[c];
+        return (((tr >> 6) & 15) ? 1 << ((tr >> 20) & 7) : 0) | (((tr >> 16) & 15) ? 1 << ((tr >> 23) & 7) : 0);
+    };
+    const int m0 = tmask(lane), m1 = tmask(lane + 32);
+    unsigned u0 = __ballot_sync(AV_FULL, m0 < 0), u1 = __ballot_sync(AV_FULL, m1 < 0);   // "used" bit sets
+    int ns = 0;
+    for (int a = 0; a < S.ncon; a++) {
+        if ((a < 32 ? u0 >> a : u1 >> (a - 32)) & 1u) continue;
+        if (a < 32) u0 |= 1u << a; else u1 |= 1u << (a - 32);
+        const int ma = __shfl_sync(AV_FULL, a < 32 ? m0 : m1, a & 31);
+        unsigned later0 = a < 31 ? ~((2u << a) - 1u) : 0u, later1 = a < 32 ? 0xffffffffu : (a < 63 ? ~((2u << (a - 32)) - 1u) : 0u);
+        unsigned b0 = __ballot_sync(AV_FULL, m0 >= 0 && !(m0 & ma)) & ~u0 & later0;
+        unsigned b1 = __ballot_sync(AV_FULL, m1 >= 0 && !(m1 & ma)) & ~u1 & later1;
+        int b = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : 0xff);
+        if (b != 0xff) { if (b < 32) u0 |= 1u << b; else u1 |= 1u << (b - 32); }
+        if (lane == 0) S.c_slot[ns] = a | (b << 8);
+        ns++;
+    }
+    if (lane == 0) S.nslot = ns;
+    __syncwarp();
+}
+
 __device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *scratch, int lane, int warm_mode) {
     int col = lane & 15, half = lane >> 4;
     // acc <- M^-1 J^T f_warm  (constraint part of the acceleration); dual cost of the warm start
@@ -506,6 +521,7 @@ __device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *sc
         for (int i = lane; i < AV_NCON * 6; i += 32) S.c_f[i] = 0.f;
         __syncwarp();
     }
+    solve_schedule(S, lane);
 }
 // after the last sweep: remember every constraint's force under its identity key for the next solve's warm start
 __device__ inline void stage_cache_store(const DevModel &m, EnvS &S, int lane, const FCache &fc) {

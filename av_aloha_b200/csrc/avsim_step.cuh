@@ -66,6 +66,7 @@ struct EnvS {
             __align__(16) float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
             float c_f[AV_NCON * 6], c_lam[AV_NCON];
             int c_tree[AV_NCON];  // packed dof ranges / tree ids of the two kinematic trees (tr_pack)
+            unsigned short c_slot[AV_NCON];  // solver schedule: contact a | contact b << 8 (0xff: none) per half-warp slot
         };
     };
     union {
@@ -85,7 +86,7 @@ struct EnvS {
     unsigned long long mbar[2];
     unsigned cuse[2];
 #endif
-    int ncon, nsc, ncand_p, ncand_c, nkeep, status;
+    int ncon, nsc, ncand_p, ncand_c, nkeep, nslot, status;
 };
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");
 

@@ -50,7 +50,7 @@ typedef struct ora_model {
     int task_id, max_reward, num_arms, noslip_iterations, multiccd;
     double timestep, impratio;
     const double *gravity;
-    const int *body_parent, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_weld;
+    const int *body_parent, *body_jntadr, *body_jntnum, *body_dofadr, *body_dofnum, *body_weld, *body_tree;
     const double *body_pos, *body_quat, *body_mass, *body_ipos, *body_inertia, *body_invweight0;
     const int *jnt_type, *jnt_body, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
     const double *jnt_axis, *jnt_pos, *jnt_range, *jnt_solref, *jnt_solimp;
@@ -109,7 +109,7 @@ ora_model *ora_model_load(const char *path) {
     m->num_arms = avm_i(m, "num_arms")[0]; m->noslip_iterations = avm_i(m, "noslip_iterations")[0];
     m->multiccd = avm_i(m, "multiccd")[0];
     m->timestep = avm_f(m, "timestep")[0]; m->impratio = avm_f(m, "impratio")[0];
-    F(gravity); I(body_parent); I(body_jntadr); I(body_jntnum); I(body_dofadr); I(body_dofnum); I(body_weld);
+    F(gravity); I(body_parent); I(body_jntadr); I(body_jntnum); I(body_dofadr); I(body_dofnum); I(body_weld); I(body_tree);
     F(body_pos); F(body_quat); F(body_mass); F(body_ipos); F(body_inertia); F(body_invweight0);
     I(jnt_type); I(jnt_body); I(jnt_qposadr); I(jnt_dofadr); I(jnt_limited);
     F(jnt_axis); F(jnt_pos); F(jnt_range); F(jnt_solref); F(jnt_solimp);
@@ -778,12 +778,27 @@ static void stage_solve(ora_data *d) {
     /* block projected Gauss-Seidel */
     double trM = 0;
     for (int i = 0; i < nv; i++) trM += d->M[i][i];
-    /* block starts (a scalar row is a block of one, a contact a block of `dim` rows): sweeps walk them forwards, or --
-     * experiment, opt.sweep_mode = 1 -- forwards and backwards alternately (symmetric Gauss-Seidel) */
+    /* Sweep order.  Scalar rows first, in row order.  Contacts in the order of the CUDA solver's half-warp schedule: it
+     * updates two contacts at once when they touch disjoint kinematic trees (such updates commute, so doing them one
+     * after the other here is the same computation); the schedule pairs each not-yet-scheduled contact with the next
+     * later one whose trees are disjoint from its own, greedily, and walks the pairs (a then b) in creation order. */
     int blk_start[NEFC_MAX], nblk = 0;
-    for (int i = 0; i < n; i++) {
-        blk_start[nblk++] = i;
-        if (d->efc_type[i] == ROW_CONTACT) i += d->con[d->efc_id[i]].dim - 1;
+    {
+        int cstart[NCON_MAX], cmask[NCON_MAX], used[NCON_MAX], nc = 0;
+        for (int i = 0; i < n; i++) {
+            if (d->efc_type[i] != ROW_CONTACT) { blk_start[nblk++] = i; continue; }
+            const ora_contact *con = &d->con[d->efc_id[i]];
+            int t1 = m->body_tree[m->geom_body[con->geom1]], t2 = m->body_tree[m->geom_body[con->geom2]];
+            cstart[nc] = i; cmask[nc] = (t1 >= 0 ? 1 << t1 : 0) | (t2 >= 0 ? 1 << t2 : 0); used[nc] = 0; nc++;
+            i += con->dim - 1;
+        }
+        for (int a = 0; a < nc; a++) {
+            if (used[a]) continue;
+            used[a] = 1;
+            blk_start[nblk++] = cstart[a];
+            for (int b = a + 1; b < nc; b++)
+                if (!used[b] && !(cmask[a] & cmask[b])) { used[b] = 1; blk_start[nblk++] = cstart[b]; break; }
+        }
     }
     for (int it = 0; it < d->opt.max_iter; it++) {
         double improvement = 0; /* decrease of the dual cost over this sweep (exact, block by block) */
@@ -852,7 +867,8 @@ static void stage_solve(ora_data *d) {
     /* noslip post-pass: friction-loss rows and contact friction rows on the unregularised A, normals fixed */
     int nos = d->opt.noslip_iter >= 0 ? d->opt.noslip_iter : m->noslip_iterations;
     for (int it = 0; it < nos; it++) {
-        for (int i = 0; i < n; i++) {
+        for (int kk = 0; kk < nblk; kk++) {
+            int i = blk_start[kk];
             int type = d->efc_type[i];
             if (type == ROW_FLOSS) {
                 double res = d->efc_b[i];
@@ -877,7 +893,6 @@ static void stage_solve(ora_data *d) {
                     qcqp(dim - 1, Ac, bc, con->friction, f[i], y);
                     for (int k = 1; k < dim; k++) f[i + k] = y[k - 1];
                 }
-                i += dim - 1;
             }
         }
     }
