@@ -398,6 +398,26 @@ __device__ inline void collide_convex(const Shape &A, const Shape &B, bool multi
     }
 }
 
+// One MPR run of a convex pair, the unit of work the lockstep kernel pools across a block's environments: q = -1 the
+// unperturbed shapes; q = 0..3 (multiccd) the shapes rotated by +-1e-3 rad about the tangent axes of the unperturbed
+// normal nrm0 through the unperturbed contact point pos0.  Same arithmetic as collide_convex above, run by run.
+__device__ inline bool collide_convex_run(const Shape &A, const Shape &B, int q, V3 pos0, V3 nrm0, int lane, float &dist, V3 &pos, V3 &nrm) {
+    Shape A2 = A, B2 = B;
+    if (q >= 0) {
+        V3 t1, t2;
+        make_frame(nrm0, t1, t2);
+        V3 ax = q < 2 ? t1 : t2;
+        float ang = (q & 1) ? -1e-3f : 1e-3f;
+        M3 Rp = rot_axis_angle(ax, ang), Rm = rot_axis_angle(ax, -ang);
+        A2.mat = mul(Rp, A.mat); A2.pos = pos0 + mul(Rp, A.pos - pos0);
+        B2.mat = mul(Rm, B.mat); B2.pos = pos0 + mul(Rm, B.pos - pos0);
+    }
+    float dp;
+    bool hit = mpr_penetration(A2, B2, lane, dp, nrm, pos) && norm(nrm) >= 0.5f;
+    dist = -dp;
+    return hit;
+}
+
 // conservative oriented-box test on the 6 face axes of the two local bounding boxes
 __device__ inline bool obb_separated(V3 hA, const Shape &A, V3 hB, const Shape &B) {
     V3 d = B.pos - A.pos;

@@ -114,18 +114,13 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
 // Environments differ ~5x in cost; avsim_order_kernel sorts the queue by the cycles each environment took in the
 // previous step (costliest first), which (a) fills the tail of the launch with cheap environments and (b) puts
 // environments of similar cost into the same block, so the lockstep barriers wait for little.
-// Collision of a lockstep block: phase A per environment, then the convex pairs of ALL the block's environments are pooled
-// and every warp (also the ones without an environment) pulls (environment, pair) items, then phase C per environment.
-__device__ __forceinline__ void block_collision(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, int warp, int W,
-                                                bool active, Prof &pf, long long &own) {
-    AV_SHARED int s_next, s_off[AV_MAX_WARPS + 1];
-    AV_SHARED float *s_scr[AV_MAX_WARPS];
-    AV_SHARED unsigned long long s_cost[AV_MAX_WARPS];   // cycles spent (by any warp) on each environment's pooled items
-    long long t0 = clock64();
-    if (active) stage_collision_a(m, S, scratch, lane, pf);
-    if (active) own += clock64() - t0;
-    if (lane == 0) { s_off[warp + 1] = active ? S.nkeep : 0; s_scr[warp] = scratch; s_cost[warp] = 0ull; }
-    if (warp == 0 && lane == 0) { s_next = 0; s_off[0] = 0; }
+// Collision of a lockstep block: phase A per environment, then the MPR runs of ALL the block's environments are pooled and
+// every warp (also the ones without an environment) pulls items -- first the unperturbed runs, then the perturbed
+// (multiccd) runs of the pairs that touch -- then phase C per environment.
+__device__ __forceinline__ void pool_round(const DevModel &m, EnvS &S, int lane, int warp, int W, int my_items, int per_pair,
+                                           int *s_next, int *s_off, float *const *s_scr, unsigned long long *s_cost) {
+    if (lane == 0) s_off[warp + 1] = my_items;
+    if (warp == 0 && lane == 0) { *s_next = 0; s_off[0] = 0; }
     __syncthreads();
     if (warp == 0 && lane == 0)
         for (int w = 0; w < W; w++) s_off[w + 1] += s_off[w];
@@ -133,19 +128,36 @@ __device__ __forceinline__ void block_collision(const DevModel &m, const BatchSt
     const int total = s_off[W];
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(&s_next, 1);
+        if (lane == 0) item = atomicAdd(s_next, 1);
         item = __shfl_sync(AV_FULL, item, 0);
         if (item >= total) break;
         int w = 0;
         while (item >= s_off[w + 1]) w++;
         const EnvS &Se = *(reinterpret_cast<const EnvS *>(av_smem_raw) + w);
+        int local = item - s_off[w];
         long long ti = clock64();
-        collide_item(m, Se, s_scr[w], item - s_off[w], lane, B.multiccd != 0);
+        if (per_pair == 1) collide_item(m, Se, s_scr[w], local, 0, lane);
+        else collide_item(m, Se, s_scr[w], Se.cand_c[local >> 2], 1 + (local & 3), lane);
         if (lane == 0) atomicAdd(&s_cost[w], (unsigned long long)(clock64() - ti));
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void block_collision(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, int warp, int W,
+                                                bool active, Prof &pf, long long &own) {
+    AV_SHARED int s_next, s_off[AV_MAX_WARPS + 1];
+    AV_SHARED float *s_scr[AV_MAX_WARPS];
+    AV_SHARED unsigned long long s_cost[AV_MAX_WARPS];   // cycles spent (by any warp) on each environment's pooled items
+    const bool multiccd = B.multiccd != 0;
+    long long t0 = clock64();
+    if (active) stage_collision_a(m, S, scratch, lane, pf);
+    if (active) own += clock64() - t0;
+    if (lane == 0) { s_scr[warp] = scratch; s_cost[warp] = 0ull; }
+    pool_round(m, S, lane, warp, W, active ? S.nkeep : 0, 1, &s_next, s_off, s_scr, s_cost);
+    if (active) collide_select(m, S, scratch, lane, multiccd);
+    pool_round(m, S, lane, warp, W, active ? 4 * S.ncand_c : 0, 4, &s_next, s_off, s_scr, s_cost);
     t0 = clock64();
-    if (active) stage_collision_c(m, S, scratch, lane, pf);
+    if (active) stage_collision_c(m, S, scratch, lane, multiccd, pf);
     if (active) own += (clock64() - t0) + (long long)s_cost[warp];
     if (B.sync >= 2) __syncthreads();
 }

@@ -405,43 +405,91 @@ __device__ AV_STAGE void stage_collision_a(const DevModel &m, EnvS &S, float *sc
     pf.mark(PF_PRIM, lane);
 }
 
-// Collision, phase B: one kept convex pair (index k) of environment S -- which may belong to ANOTHER warp of the block:
-// the lockstep step kernel pools the convex pairs of all its environments and lets every warp pull items, because the
-// number of hull pairs per environment varies from 0 to 15 and the stage barrier would otherwise wait for the unluckiest.
-// Warp-cooperative MPR (+ multiccd); the result goes to the environment's scratch (n | normal | 5 x dist | 5 x pos).
-__device__ AV_STAGE void collide_item(const DevModel &m, const EnvS &S, float *scratch, int k, int lane, bool multiccd) {
+// Collision, phase B: pooled MPR runs.  An item is one run of one kept convex pair of environment S -- which may belong to
+// ANOTHER warp of the block: the lockstep step kernel pools the runs of all its environments and lets every warp pull
+// items, because the number of hull pairs per environment varies from 0 to 15 and the stage barrier would otherwise wait
+// for the unluckiest.  Two rounds: the unperturbed runs (run = 0), then -- for the pairs that touch and take multiccd --
+// the four perturbed runs (run = 1..4), which need the unperturbed contact point and normal.
+// Result slots in the environment's scratch, per pair: hit | normal 3 | 5 x dist (1e30 = miss) | 5 x pos.
+__device__ AV_STAGE void collide_item(const DevModel &m, const EnvS &S, float *scratch, int k, int run, int lane) {
     int pk = S.keep_c[k], g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
     Shape A = load_shape(m, S, g1), B = load_shape(m, S, g2);
-    PrimOut o;
-    bool mc = multiccd && A.type != AV_GEOM_SPHERE && B.type != AV_GEOM_SPHERE;
-    collide_convex(A, B, mc, lane, o);
     float *tmp = scratch + AV_SCR_TMP + k * AV_CTMP;
-    if (lane == 0) { tmp[0] = (float)o.n; tmp[1] = o.nrm.x; tmp[2] = o.nrm.y; tmp[3] = o.nrm.z; }
-    if (lane < o.n) { tmp[4 + lane] = o.dist[lane]; st3(tmp + 9 + 3 * lane, o.pos[lane]); }
+    V3 pos0 = v3(0, 0, 0), nrm0 = v3(0, 0, 1), pos, nrm;
+    if (run > 0) { pos0 = ld3(tmp + 9); nrm0 = ld3(tmp + 1); }
+    float dist;
+    bool hit = collide_convex_run(A, B, run - 1, pos0, nrm0, lane, dist, pos, nrm);
+    if (lane == 0) {
+        if (run == 0) { tmp[0] = hit ? 1.f : 0.f; st3(tmp + 1, nrm); }
+        tmp[4 + run] = hit ? dist : 1e30f;
+        st3(tmp + 9 + 3 * run, pos);
+    }
     __syncwarp();
 }
+// after the unperturbed round (own environment): the pairs that go on to the perturbed round -> S.cand_c[0..ncand_c)
+__device__ inline void collide_select(const DevModel &m, EnvS &S, const float *scratch, int lane, bool multiccd) {
+    for (int base = 0; base < S.nkeep; base += 32) {
+        int k = base + lane, go = 0;
+        if (k < S.nkeep && multiccd) {
+            int pk = S.keep_c[k];
+            go = scratch[AV_SCR_TMP + k * AV_CTMP] > 0.5f && m.geom_type[pk & 0xff] != AV_GEOM_SPHERE &&
+                 m.geom_type[(pk >> 8) & 0xff] != AV_GEOM_SPHERE;
+        }
+        unsigned mk = __ballot_sync(AV_FULL, go);
+        int n0 = S.ncand_c;
+        __syncwarp();
+        if (go) S.cand_c[n0 + __popc(mk & ((1u << lane) - 1u))] = k;
+        if (lane == 0) S.ncand_c = n0 + __popc(mk);
+        __syncwarp();
+    }
+}
 
-// Collision, phase C (own environment): contacts from the pooled results, in candidate order
-__device__ AV_STAGE void stage_collision_c(const DevModel &m, EnvS &S, float *scratch, int lane, Prof &pf) {
+// Collision, phase C (own environment): contacts from the pooled results, in candidate order; perturbed points that
+// coincide with an earlier point of the pair (< 0.1 mm) are dropped, like collide_convex does
+__device__ AV_STAGE void stage_collision_c(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd, Prof &pf) {
     for (int k = 0; k < S.nkeep; k++) {
         const float *tmp = scratch + AV_SCR_TMP + k * AV_CTMP;
-        int n = (int)tmp[0], pk = S.keep_c[k], g1 = pk & 0xff, g2 = (pk >> 8) & 0xff, n0 = S.ncon;
-        __syncwarp();
-        if (lane < n) {
-            if (n0 + lane < AV_NCON) add_contact(m, S, scratch, n0 + lane, g1, g2, tmp[4 + lane], ld3(tmp + 9 + 3 * lane), ld3(tmp + 1));
-            else S.status |= 2;
+        if (!(tmp[0] > 0.5f)) continue;
+        int pk = S.keep_c[k], g1 = pk & 0xff, g2 = (pk >> 8) & 0xff;
+        bool mc = multiccd && m.geom_type[g1] != AV_GEOM_SPHERE && m.geom_type[g2] != AV_GEOM_SPHERE;
+        V3 acc_pos[5];
+        float acc_dist[5];
+        int n = 1;
+        acc_pos[0] = ld3(tmp + 9); acc_dist[0] = tmp[4];
+#pragma unroll
+        for (int r = 1; r <= 4; r++) {
+            if (!mc || !(tmp[4 + r] < 1e29f)) continue;
+            V3 ps = ld3(tmp + 9 + 3 * r);
+            bool dup = false;
+#pragma unroll
+            for (int c = 0; c < 4; c++) dup = dup || (c < n && norm(ps - acc_pos[c]) < 1e-4f);
+            if (dup) continue;
+#pragma unroll
+            for (int c = 1; c < 5; c++)
+                if (c == n) { acc_pos[c] = ps; acc_dist[c] = tmp[4 + r]; }
+            n++;
         }
+        int n0 = S.ncon;
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 5; c++)      // one lane writes each contact; unrolled so the small arrays stay in registers
+            if (c < n && lane == c) {
+                if (n0 + c < AV_NCON) add_contact(m, S, scratch, n0 + c, g1, g2, acc_dist[c], acc_pos[c], ld3(tmp + 1));
+                else S.status |= 2;
+            }
         if (lane == 0) S.ncon = min(AV_NCON, n0 + n);
         __syncwarp();
     }
     pf.mark(PF_CONVEX, lane);
 }
 
-// the three phases back to back for one warp on its own (forward kernel, host emulation of single-warp blocks)
+// the phases back to back for one warp on its own (forward kernel, host emulation of single-warp blocks)
 __device__ inline void stage_collision(const DevModel &m, EnvS &S, float *scratch, int lane, bool multiccd, Prof &pf) {
     stage_collision_a(m, S, scratch, lane, pf);
-    for (int k = 0; k < S.nkeep; k++) collide_item(m, S, scratch, k, lane, multiccd);
-    stage_collision_c(m, S, scratch, lane, pf);
+    for (int k = 0; k < S.nkeep; k++) collide_item(m, S, scratch, k, 0, lane);
+    collide_select(m, S, scratch, lane, multiccd);
+    for (int i = 0; i < 4 * S.ncand_c; i++) collide_item(m, S, scratch, S.cand_c[i >> 2], 1 + (i & 3), lane);
+    stage_collision_c(m, S, scratch, lane, multiccd, pf);
 }
 
 // ------------------------------------------------------------------ K3b: velocity, bias, actuation, smooth acceleration
