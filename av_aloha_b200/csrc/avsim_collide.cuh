@@ -12,7 +12,7 @@
 
 #define AV_MPR_TOL 1e-6f
 #define AV_MPR_ITERS 50
-#define AV_SUP_UNROLL 8
+#define AV_SUP_UNROLL 11   // 11 x 32 = 352 vertices per chunk: the finger hulls (345 / 347 vertices) scan in one chunk
 
 struct Shape {
     int type, nvert;
@@ -196,14 +196,14 @@ __device__ inline V3 support_world(const Shape &S, V3 dir, int lane) {
     if (S.type == AV_GEOM_MESH) {
         float bd = -3.0e38f;
         int bi = 0x7fffffff;
-        // 8 independent 512-byte row loads in flight per lane before the first use: the scan is bound by L2 latency
+        // up to AV_SUP_UNROLL independent 512-byte row loads in flight per lane before the first use: the scan is bound by L2 latency
         // (ncu: one third of all stall samples sat on the dependent load->FMA of the rolled loop), not by bandwidth
         for (int base = lane; base < S.nvert; base += 32 * AV_SUP_UNROLL) {
             float4 pv[AV_SUP_UNROLL];
 #pragma unroll
             for (int u = 0; u < AV_SUP_UNROLL; u++) {
                 int i = base + 32 * u;
-                pv[u] = ldg4(S.vert + (i < S.nvert ? i : lane));
+                pv[u] = ldg4(S.vert + (i < S.nvert ? i : lane));     // unconditional: a predicated load breaks the batching
             }
 #pragma unroll
             for (int u = 0; u < AV_SUP_UNROLL; u++) {
