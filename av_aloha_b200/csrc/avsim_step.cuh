@@ -569,7 +569,10 @@ __device__ __forceinline__ float impedance(const float *solimp, float x_abs) {
     if (x <= 0.f) return d0;
     float y;
     if (power == 1.f) y = x;
-    else if (x <= mid) y = powf(x / mid, power) * mid;
+    else if (power == 2.f) {   // the default solimp (every constraint of the AV-ALOHA models): no powf
+        float a = x <= mid ? x / mid : (1.f - x) / (1.f - mid);
+        y = x <= mid ? a * a * mid : 1.f - a * a * (1.f - mid);
+    } else if (x <= mid) y = powf(x / mid, power) * mid;
     else y = 1.f - powf((1.f - x) / (1.f - mid), power) * (1.f - mid);
     return d0 + y * (dw - d0);
 }
