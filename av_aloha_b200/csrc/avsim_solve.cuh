@@ -228,7 +228,11 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
         float vv[6], aa[6], ww[6];
         block_rows(j0, j1, j2, xv, half, vv);
         block_rows(j0, j1, j2, xa, half, aa);
-        block_rows(j0, j1, j2, xw, half, ww);
+        if (fc.mode != 2) block_rows(j0, j1, j2, xw, half, ww);   // J qacc_warmstart: only the MuJoCo-style warm start needs it
+        else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) ww[k] = 0.f;
+        }
         __syncwarp();
         // impedance, regularisation, reference acceleration (uniform)
         float K, B, imp, solref[2], solimp[5];
@@ -491,29 +495,31 @@ __device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *sc
         __syncwarp();
     }
     float cost = 0.f;
-    for (int r = 0; r < S.nsc; r++) {
-        float f = S.sc_f[r];
-        float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
-        cost += f * (0.5f * (ja + S.sc_R[r] * f) + S.sc_b[r]);
-    }
-    for (int c = 0; c < S.ncon; c++) {
-        if ((S.c_info[c] >> 20) & 1) continue;
-        const float *blk = scratch + c * AV_CBLK;
-        int tr = S.c_tree[c], dof = tr_dof(tr, col);
-        const float *J = blk + AV_CB_J;
-        float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
-        float res[6];
-        block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
-        // R (rows 0 | 1,2 | 3 | 4,5) and b straight from the block: the full CBlk is not needed here
-        float Rn = blk[AV_CB_PAR], Rf = blk[AV_CB_PAR + 1], Rt = blk[AV_CB_PAR + 2], Rr = blk[AV_CB_PAR + 3];
-        float Rk[6] = {Rn, Rf, Rf, Rt, Rr, Rr};
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            float f = S.c_f[6 * c + k];   // dead rows: f = 0
-            cost += f * (0.5f * (res[k] + Rk[k] * f) + blk[AV_CB_B + k]);
+    if (warm_mode != 2) {   // dual cost of the warm start (decides whether MuJoCo-style warm start is kept)
+        for (int r = 0; r < S.nsc; r++) {
+            float f = S.sc_f[r];
+            float ja = S.sc_c1[r] * S.acc[S.sc_dof1[r]] + (S.sc_dof2[r] >= 0 ? S.sc_c2[r] * S.acc[S.sc_dof2[r]] : 0.f);
+            cost += f * (0.5f * (ja + S.sc_R[r] * f) + S.sc_b[r]);
         }
+        for (int c = 0; c < S.ncon; c++) {
+            if ((S.c_info[c] >> 20) & 1) continue;
+            const float *blk = scratch + c * AV_CBLK;
+            int tr = S.c_tree[c], dof = tr_dof(tr, col);
+            const float *J = blk + AV_CB_J;
+            float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
+            float res[6];
+            block_rows(j0, j1, j2, dof >= 0 ? S.acc[dof] : 0.f, half, res);
+            // R (rows 0 | 1,2 | 3 | 4,5) and b straight from the block: the full CBlk is not needed here
+            float Rn = blk[AV_CB_PAR], Rf = blk[AV_CB_PAR + 1], Rt = blk[AV_CB_PAR + 2], Rr = blk[AV_CB_PAR + 3];
+            float Rk[6] = {Rn, Rf, Rf, Rt, Rr, Rr};
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                float f = S.c_f[6 * c + k];   // dead rows: f = 0
+                cost += f * (0.5f * (res[k] + Rk[k] * f) + blk[AV_CB_B + k]);
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
     // MuJoCo keeps its warm start only if it beats f = 0; the force cache (mode 2) is kept unconditionally
     if (warm_mode != 2 && cost >= 0.f) {
         for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
