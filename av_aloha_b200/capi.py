@@ -23,6 +23,7 @@ SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
     "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render", "avsim_set_warmstart",
+    "avsim_pixels_to_float",
 ]
 
 
@@ -66,6 +67,7 @@ def load_library():
     L.avsim_set.argtypes = [vp, i32, vp]
     L.avsim_step_host.argtypes = [vp, vp, i32, vp, vp]
     L.avsim_render.argtypes = [vp, C.POINTER(C.c_int), i32, i32, i32, vp]
+    L.avsim_pixels_to_float.argtypes = [vp, C.c_int64, i32, i32, vp, i32, vp]
     L.avsim_launch_count.restype = C.c_int64; L.avsim_launch_count.argtypes = [vp]
     L.avsim_diffik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(DiffIKParams), vp, vp]
     L.avsim_gradik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(GradIKParams), vp, vp]
@@ -83,6 +85,27 @@ class AvsimError(RuntimeError):
 def check(rc):
     if rc != 0:
         raise AvsimError(f"avsim error {rc}: {load_library().avsim_last_error().decode()}")
+
+
+def pixels_to_float(img, out=None):
+    """uint8 CUDA tensor [..., H, W, 3] -> float32 CUDA tensor [..., 3, H, W] in [0, 1] (avsim_pixels_to_float: the image half
+    of lerobot's preprocess_observation, utils.py:37-50, without leaving the device).  Runs on torch's current stream."""
+    import torch
+
+    if not (torch.is_tensor(img) and img.is_cuda and img.dtype == torch.uint8 and img.is_contiguous()):
+        raise ValueError("pixels_to_float: expected a contiguous uint8 CUDA tensor")
+    if img.dim() < 3 or img.shape[-1] != 3:
+        raise ValueError(f"pixels_to_float: expected channel-last images [..., H, W, 3], got {tuple(img.shape)}")
+    lead, (H, W) = tuple(img.shape[:-3]), img.shape[-3:-1]
+    if out is None:
+        out = torch.empty(lead + (3, H, W), dtype=torch.float32, device=img.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == lead + (3, H, W)):
+        raise ValueError("pixels_to_float: bad output tensor")
+    n = int(np.prod(lead)) if lead else 1
+    stream = torch.cuda.current_stream(img.device).cuda_stream
+    check(load_library().avsim_pixels_to_float(C.c_void_p(img.data_ptr()), C.c_int64(n), int(H), int(W), C.c_void_p(out.data_ptr()),
+                                               img.device.index or 0, C.c_void_p(stream)))
+    return out
 
 
 class Model:

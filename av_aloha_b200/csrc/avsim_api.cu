@@ -13,6 +13,7 @@
 #include "avsim_ik.cuh"
 #include "avsim_kernels.cuh"
 #include "avsim_model_pack.h"
+#include "avsim_obs.cuh"
 #include "avsim_render.cuh"
 
 #define AV_SORT_MAX 8192
@@ -336,6 +337,27 @@ extern "C" int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, i
     avsim_render_kernel<<<grid, AV_RT_W * AV_RT_H, 0, b->stream>>>(d, b->d_rpose, b->d_rrect, d.geom_rgba, d.geom_visible, d.cam_fovy, b->d_camids, ncam,
                                                                d.ncam, H, W, dst_dev);
     b->launches += 2;
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}
+
+// device-resident preprocess_observation (reference lerobot/lerobot/common/envs/utils.py:37-50): u8 [n][H][W][3] -> f32 [n][3][H][W] / 255
+extern "C" int avsim_pixels_to_float(const uint8_t *src_dev, int64_t n_images, int H, int W, float *dst_dev, int device, void *stream) {
+    if (!src_dev || !dst_dev || n_images < 0 || H < 1 || W < 1) return fail(AVSIM_ERR_ARG, "avsim_pixels_to_float: bad arguments");
+    if (n_images == 0) return AVSIM_OK;
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const long long hw = (long long)H * W, cap = (long long)sms * 8;        // 8 resident 256-thread blocks per SM
+    if (hw % 4 == 0 && ((uintptr_t)src_dev % 4) == 0 && ((uintptr_t)dst_dev % 16) == 0) {
+        long long nquads = n_images * (hw / 4), per = (long long)AV_OBS_THREADS * AV_OBS_UNROLL;
+        long long grid = (nquads + per - 1) / per;
+        avsim_pixels_to_float_kernel<<<(unsigned)(grid < cap ? grid : cap), AV_OBS_THREADS, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint32_t *>(src_dev), dst_dev, nquads, (int)(hw / 4));
+    } else {
+        long long nvals = n_images * 3 * hw, grid = (nvals + AV_OBS_THREADS - 1) / AV_OBS_THREADS;
+        avsim_pixels_to_float_any_kernel<<<(unsigned)(grid < cap ? grid : cap), AV_OBS_THREADS, 0, (cudaStream_t)stream>>>(src_dev, dst_dev, nvals, (int)hw);
+    }
     CU(cudaGetLastError());
     return AVSIM_OK;
 }

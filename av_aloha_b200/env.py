@@ -398,6 +398,45 @@ class GuidedVisionVectorEnv:
         obs["ctrl"] = self._batch.get(capi.CTRL).cpu().numpy().astype(np.float64)
         return obs, self._reward.astype(np.float64), np.zeros(self.num_envs, bool), np.zeros(self.num_envs, bool), {}
 
+    # -- device-resident variants: nothing below copies to the host.  The unchanged lerobot loop pays, per
+    # step, a D2H of every frame plus a CPU uint8 -> fp32 cast (eval.py:150, utils.py:37-50); a policy that lives on the same
+    # GPU can read the frames where avsim_render wrote them (av_aloha_b200/observation.py turns them into its input planes).
+    def observation_device(self, render=True):
+        """{"pixels": uint8 CUDA [B, ncam, H, W, 3] (None when no cameras or render=False), "agent_pos": f32 CUDA [B, nj]};
+        camera k of the pixel tensor is self.cameras[k]."""
+        px = None
+        if self.cameras and render:
+            self._px_dev = self._batch.render(self._cam_ids, self.observation_height, self.observation_width,
+                                              out=getattr(self, "_px_dev", None))
+            px = self._px_dev
+        return {"pixels": px, "agent_pos": self._batch.get(capi.AGENT_POS)}
+
+    def reset_device(self, render=True):
+        self._reset_rows(np.ones(self.num_envs, bool))
+        return self.observation_device(render), {}
+
+    def step_device(self, actions, render=True):
+        """`step` with CUDA tensors in and out: actions f32 [B, nj] on the batch's device.  Returns (observation_device(),
+        reward i32 CUDA [B], terminated bool CUDA [B], truncated bool CUDA [B], info); on a step where episodes end (TimeLimit,
+        then auto-reset as in `step`) info["final_success"] holds the per-env is_success of the finished episodes as a bool
+        CUDA tensor (False elsewhere) and info["_final_info"] the mask -- the content of gymnasium's info["final_info"]."""
+        import torch
+
+        dev = self._batch.dev
+        a = torch.as_tensor(actions, dtype=torch.float32, device=dev).reshape(self.num_envs, self.num_joints).contiguous()
+        self._batch.step(a, SIM_PHYSICS_ENV_STEP_RATIO)
+        self._elapsed += 1
+        reward = self._batch.get(capi.REWARD)
+        truncated = self._elapsed >= self._max_episode_steps           # host-side step counters: no device sync
+        info = {}
+        if truncated.any():
+            tr = torch.as_tensor(truncated, device=dev)
+            info = {"final_success": self._batch.get(capi.SUCCESS).bool() & tr, "_final_info": tr}
+            self._reset_rows(truncated)
+        else:
+            tr = torch.zeros(self.num_envs, dtype=torch.bool, device=dev)
+        return self.observation_device(render), reward, torch.zeros_like(tr), tr, info
+
     def success_and_max_reward(self):
         """Per-env (reward == max_reward, reward) of the last step as CUDA tensors: the payload of the one collective of the
         path (rank-sharded rollouts all_gather these at episode end)."""

@@ -131,3 +131,59 @@ def create_fk_fn(model, arm):
         return out[0] if single else out
 
     return forward_kinematics
+
+
+# ---- create_safety_fn / safety (reference data_collection_scripts/kinematics.py:54-135).  The checks are host predicates
+# over the FK kernel's pose; rows are checked in the reference's order and the first failing check names the message.
+SAFETY_MESSAGES = ("", "Joint tracking safety margin exceeded", "Joint limit safety margin exceeded",
+                   "End effector position outside bounds", "End effector action position outside bounds",
+                   "End effector pose tracking safety margin exceeded")
+
+
+def _angular_error(desired, current):
+    """transform_utils.py:183-194: half the sum of the column cross products, batched over the leading axis"""
+    return 0.5 * sum(np.cross(current[..., :3, k], desired[..., :3, k]) for k in range(3))
+
+
+def create_safety_fn(model, arm, xyz_bounds, joint_limit_safety_margin=0.01, joint_tracking_safety_margin=1.0,
+                     eef_pos_tracking_safety_margin=0.2, eef_rot_tracking_safety_margin=3.0):
+    """``safety_fn(qpos, ctrl, Taction=None) -> (ok, message)`` for one arm, or -- with a leading batch axis on qpos / ctrl
+    (/ Taction) -- ``(ok bool[n], code int[n])`` with ``SAFETY_MESSAGES[code]`` the reference's message."""
+    a = _arm(arm)
+    return _make_safety_fn(create_fk_fn(model, a), model.ik_range(a), xyz_bounds, joint_limit_safety_margin,
+                           joint_tracking_safety_margin, eef_pos_tracking_safety_margin, eef_rot_tracking_safety_margin)
+
+
+def _make_safety_fn(fk_fn, joint_range, xyz_bounds, joint_limit_safety_margin, joint_tracking_safety_margin,
+                    eef_pos_tracking_safety_margin, eef_rot_tracking_safety_margin):
+    """the predicates around an FK function (the CUDA kernel in the product; the CPU tests inject the emulated kernel)"""
+    xyz_bounds = np.array(xyz_bounds, np.float64)
+    joint_limits = np.array(joint_range, np.float64).copy()
+    assert np.all(joint_limit_safety_margin < (joint_limits[:, 1] - joint_limits[:, 0]) / 2)
+    joint_limits[:, 0] += joint_limit_safety_margin
+    joint_limits[:, 1] -= joint_limit_safety_margin
+
+    def safety_fn(qpos, ctrl, Taction=None):
+        q, c = np.asarray(qpos, np.float64), np.asarray(ctrl, np.float64)
+        single = q.ndim == 1
+        q, c = np.atleast_2d(q), np.atleast_2d(c)
+        T = np.asarray(fk_fn(q), np.float64).reshape(-1, 4, 4)
+        code = np.zeros(len(q), np.int64)
+
+        def flag(bad, k):                                    # the first failing check wins, as in the reference's early returns
+            code[(code == 0) & bad] = k
+
+        flag(np.any(np.abs(q - c) > joint_tracking_safety_margin, axis=1), 1)
+        flag(np.any(q < joint_limits[:, 0], axis=1) | np.any(q > joint_limits[:, 1], axis=1), 2)
+        flag(np.any(T[:, :3, 3] < xyz_bounds[:, 0], axis=1) | np.any(T[:, :3, 3] > xyz_bounds[:, 1], axis=1), 3)
+        if Taction is not None:
+            Ta = np.asarray(Taction, np.float64).reshape(-1, 4, 4)
+            flag(np.any(Ta[:, :3, 3] < xyz_bounds[:, 0], axis=1) | np.any(Ta[:, :3, 3] > xyz_bounds[:, 1], axis=1), 4)
+            pos_err = np.linalg.norm(Ta[:, :3, 3] - T[:, :3, 3], axis=1)
+            rot_err = np.linalg.norm(_angular_error(Ta, T), axis=1)
+            flag(~((pos_err < eef_pos_tracking_safety_margin) & (rot_err < eef_rot_tracking_safety_margin)), 5)
+        if single:
+            return bool(code[0] == 0), SAFETY_MESSAGES[int(code[0])]
+        return code == 0, code
+
+    return safety_fn

@@ -94,6 +94,12 @@ int avsim_set(avsim_batch *b, int field, const void *src_dev);
  * Ray-cast of the physics geoms (mesh geoms as oriented bounding boxes of their hulls); W must be a multiple of 4. */
 int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev);
 
+/* device-resident observation path: replaces the image half of lerobot's preprocess_observation (reference
+ * lerobot/lerobot/common/envs/utils.py:37-50: channel-last u8 -> channel-first f32 in [0,1], fp32 division by 255,
+ * bit-exact).  src_dev: u8 [n_images][H][W][3] (what avsim_render wrote, any leading [B][ncam] flattened),
+ * dst_dev: f32 [n_images][3][H][W].  Stand-alone: needs no batch; runs on `stream` of `device`. */
+int avsim_pixels_to_float(const uint8_t *src_dev, int64_t n_images, int H, int W, float *dst_dev, int device, void *stream);
+
 /* host-buffer convenience path used by the gym-facing wrapper (e2e metric): copies happen inside the call. */
 int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host);
 

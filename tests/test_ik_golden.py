@@ -161,3 +161,41 @@ def test_gpu_gradik(gold, gpu_model, arm):
     ctl, ctl8 = kinematics.GradIK(gpu_model, arm, **kw), kinematics.GradIK(gpu_model, arm, **dict(kw, max_iterations=8))
     from av_aloha_b200 import model_io
     _check_gradik(ctl.run(*args), ctl8.run(*args), gold, arm, model_io.load_avm(gpu_model.avm_path))
+
+
+# ------------------------------------------------------------------ create_safety_fn (reference kinematics.py:54-135)
+SAFETY_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "safety_golden.npz")
+
+
+def _check_safety(fn, sg, arm):
+    """golden = (ok, message) of the reference's own safety_fn on the same inputs (tools/gen_safety_golden.py); the codes
+    index the reference's messages in the order of its early returns"""
+    from av_aloha_b200.kinematics import SAFETY_MESSAGES
+    q, ctrl, T, has_T, code = (sg[f"{k}_{arm}"] for k in ("q", "ctrl", "T", "hasT", "code"))
+    assert set(np.unique(code)) == set(range(6))                       # every return path of the reference is exercised
+    ok_b, code_b = fn(q[has_T], ctrl[has_T], T[has_T])                  # batched, with a target pose
+    assert np.array_equal(code_b, code[has_T]) and np.array_equal(ok_b, code[has_T] == 0)
+    ok_n, code_n = fn(q[~has_T], ctrl[~has_T])                          # batched, Taction=None
+    assert np.array_equal(code_n, code[~has_T])
+    for i in (0, 1, 2, 3, 8, 9):                                        # single calls return the reference's (bool, message)
+        ok, msg = fn(q[i], ctrl[i], T[i] if has_T[i] else None)
+        assert (ok, msg) == (code[i] == 0, SAFETY_MESSAGES[code[i]])
+
+
+@pytest.mark.parametrize("arm", [0, 1, 2])
+def test_emu_safety_fn_matches_reference(emu_batch, arm, slot_model_path):
+    from av_aloha_b200 import kinematics, model_io
+    emu, eb = emu_batch
+    sg, avm = np.load(SAFETY_GOLD), model_io.load_avm(slot_model_path)
+    n = int(avm["ik_ndof"][arm])
+    fk = lambda q: emu.emu_fk(eb, arm, np.atleast_2d(q))   # noqa: E731
+    fn = kinematics._make_safety_fn(fk, avm["ik_range"][arm, :n], sg[f"bounds_{arm}"], 0.01, 1.0, 0.2, 3.0)
+    _check_safety(fn, sg, arm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arm", [0, 1, 2])
+def test_gpu_safety_fn_matches_reference(gpu_model, arm):
+    from av_aloha_b200 import kinematics
+    sg = np.load(SAFETY_GOLD)
+    _check_safety(kinematics.create_safety_fn(gpu_model, arm, sg[f"bounds_{arm}"]), sg, arm)
