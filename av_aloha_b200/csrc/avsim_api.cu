@@ -343,8 +343,9 @@ extern "C" int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, i
 
 // device-resident preprocess_observation (reference lerobot/lerobot/common/envs/utils.py:37-50): u8 [n][H][W][3] -> f32 [n][3][H][W] / 255
 extern "C" int avsim_pixels_to_float(const uint8_t *src_dev, int64_t n_images, int H, int W, float *dst_dev, int device, void *stream) {
-    if (!src_dev || !dst_dev || n_images < 0 || H < 1 || W < 1) return fail(AVSIM_ERR_ARG, "avsim_pixels_to_float: bad arguments");
-    if (n_images == 0) return AVSIM_OK;
+    if (n_images < 0 || H < 1 || W < 1) return fail(AVSIM_ERR_ARG, "avsim_pixels_to_float: bad arguments");
+    if (n_images == 0) return AVSIM_OK;                       // an empty batch has no buffers to look at
+    if (!src_dev || !dst_dev) return fail(AVSIM_ERR_ARG, "avsim_pixels_to_float: null buffer");
     CU(cudaSetDevice(device));
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));

@@ -12,6 +12,9 @@
 
 #define AV_MPR_TOL 1e-6f
 #define AV_MPR_ITERS 50
+#ifndef AV_SUP_REDUX
+#define AV_SUP_REDUX 1   // REDUX argmax + register-carried winner in the hull support scan (0: shuffle butterfly + reload)
+#endif
 #define AV_SUP_UNROLL 11   // 11 x 32 = 352 vertices per chunk: the finger hulls (345 / 347 vertices) scan in one chunk
 
 struct Shape {
@@ -196,6 +199,9 @@ __device__ inline V3 support_world(const Shape &S, V3 dir, int lane) {
     if (S.type == AV_GEOM_MESH) {
         float bd = -3.0e38f;
         int bi = 0x7fffffff;
+#if AV_SUP_REDUX
+        float bx = 0.f, by = 0.f, bz = 0.f;     // the lane's best vertex travels with its score: no dependent reload of the winner
+#endif
         // up to AV_SUP_UNROLL independent 512-byte row loads in flight per lane before the first use: the scan is bound by L2 latency
         // (ncu: one third of all stall samples sat on the dependent load->FMA of the rolled loop), not by bandwidth
         for (int base = lane; base < S.nvert; base += 32 * AV_SUP_UNROLL) {
@@ -209,12 +215,25 @@ __device__ inline V3 support_world(const Shape &S, V3 dir, int lane) {
             for (int u = 0; u < AV_SUP_UNROLL; u++) {
                 int i = base + 32 * u;
                 float dt = pv[u].x * dl.x + pv[u].y * dl.y + pv[u].z * dl.z;
+#if AV_SUP_REDUX
+                if (i < S.nvert && dt > bd) { bd = dt; bi = i; bx = pv[u].x; by = pv[u].y; bz = pv[u].z; }
+#else
                 if (i < S.nvert && dt > bd) { bd = dt; bi = i; }
+#endif
             }
         }
+#if AV_SUP_REDUX
+        // argmax by two REDUX ops on an order-preserving key (ties -> smallest index, as warp_argmax), then the owner lane
+        // (vertex i lives in lane i & 31) broadcasts the coordinates it already holds
+        bd += 0.0f;                                                  // -0.0 -> +0.0: the key order must match float compare
+        warp_argmax_redux(bd, bi);
+        const int owner = bi & 31;
+        pl = v3(__shfl_sync(AV_FULL, bx, owner), __shfl_sync(AV_FULL, by, owner), __shfl_sync(AV_FULL, bz, owner));
+#else
         warp_argmax(bd, bi);
         float4 p = ldg4(S.vert + bi);
         pl = v3(p.x, p.y, p.z);
+#endif
     } else if (S.type == AV_GEOM_BOX) {
         pl = v3(dl.x >= 0 ? S.size.x : -S.size.x, dl.y >= 0 ? S.size.y : -S.size.y, dl.z >= 0 ? S.size.z : -S.size.z);
     } else if (S.type == AV_GEOM_SPHERE) {

@@ -172,6 +172,16 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 // argmax with lowest-index tie break; returns the winning (value, index) in every lane
+// Same result (largest value, smallest index among ties) with two REDUX instructions instead of ten dependent shuffles: the
+// float is mapped to an order-preserving unsigned key (v must not be -0.0: callers add +0.0f).  Indices must be >= 0.
+__device__ __forceinline__ void warp_argmax_redux(float &v, int &i) {
+    unsigned u = __float_as_uint(v);
+    u ^= (unsigned)((int)u >> 31) | 0x80000000u;
+    unsigned m = __reduce_max_sync(AV_FULL, u);
+    i = (int)__reduce_min_sync(AV_FULL, u == m ? (unsigned)i : 0xffffffffu);
+    m ^= (m & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+    v = __uint_as_float(m);
+}
 __device__ __forceinline__ void warp_argmax(float &v, int &i) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -69,6 +69,8 @@ static threadIdx_t threadIdx;
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
+static inline unsigned __float_as_uint(float f) { return f2u(f); }
+static inline float __uint_as_float(unsigned u) { return u2f(u); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::exchange(0); }
 static inline void __syncthreads() { emu::exchange(0); }   // one warp per emulated block
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::exchange((uint32_t)v)[src & 31]; }
@@ -88,6 +90,18 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     const uint32_t *x = emu::exchange(pred ? 1u : 0u);
     unsigned r = 0;
     for (int i = 0; i < 32; i++) r |= (x[i] ? 1u : 0u) << i;
+    return r;
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    const uint32_t *x = emu::exchange(v);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r = x[i] > r ? x[i] : r;
+    return r;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    const uint32_t *x = emu::exchange(v);
+    unsigned r = 0xffffffffu;
+    for (int i = 0; i < 32; i++) r = x[i] < r ? x[i] : r;
     return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }

@@ -150,3 +150,50 @@ def test_teleop_pose_action_step_tracks_targets():
     dz = T[:, 2, 3] - poses["left"][0][2]            # GradIK trades pose error against joint displacement: it gets part way
     assert (dz > 0.008).all() and (dz < 0.035).all(), dz
     v.close()
+
+
+def test_config1_insert_peg_two_arms_plumbing():
+    """BASELINE.json configs[0] / SURVEY.md 8d config 1: InsertPeg-2Arms-v0 single env, np.random.seed(1000) (the yaml seed,
+    zed_wrist_act.yaml:3), 400 steps (sim_insert_peg_2arms.yaml:17) of the hold action: obs keys / shapes / dtypes, reward 0,
+    the arm settles and stays put; once with the registry's default 4 cameras and once with cameras=[].  (SURVEY.md guessed a
+    drift bound of 5e-3 rad; the position actuators have no gravity compensation, so the arms sag to their PD equilibrium --
+    0.0265 rad at wrist_angle, kp = 37 -- within the first second and then hold it.  The bound here is the oracle's own
+    trajectory: same sag to 1e-4, steady to 1e-5 over the last 100 steps.)"""
+    from av_aloha_b200 import env, model_io
+    from oracle.oracle import OracleEnv, OracleModel
+
+    spec = next(s for s in env.ENVS if s["id"] == "gym_guided_vision/InsertPeg-2Arms-v0")
+    cams = spec["kwargs"]["cameras"]
+    assert len(cams) == 4 and spec["kwargs"]["num_arms"] == 2
+    a = _hold(14)
+    e = env.make("gym_guided_vision/InsertPeg-2Arms-v0")                   # default cameras, 480 x 640
+    np.random.seed(1000)
+    obs, info = e.reset(seed=1000)
+    assert set(obs) == {"pixels", "agent_pos"} and set(obs["pixels"]) == set(cams)
+    for _ in range(3):
+        obs, reward, terminated, truncated, info = e.step(a)
+    for c in cams:
+        assert obs["pixels"][c].shape == (480, 640, 3) and obs["pixels"][c].dtype == np.uint8 and obs["pixels"][c].max() > 0
+    assert obs["agent_pos"].shape == (14,) and obs["agent_pos"].dtype == np.float64
+    assert (reward, terminated, truncated, info) == (0, False, False, {"is_success": False})
+    e.close()
+    e = env.make("gym_guided_vision/InsertPeg-2Arms-v0", cameras=[])
+    np.random.seed(1000)
+    obs0, _ = e.reset(seed=1000)
+    assert obs0["pixels"] == {}
+    np.random.seed(1000)
+    o = OracleEnv(OracleModel(model_io.model_path("insert_peg", 2)))
+    o.set_options(max_iter=50, tol=0.0, warmstart=1)
+    o.reset(free_pos=env.reference_reset_draws("insert_peg", model_io.load_names("insert_peg", 2)["free_joint"]))
+    a21 = np.concatenate([a, HOME[14:]]).astype(np.float64)
+    worst, at300 = 0.0, None
+    for k in range(400):
+        obs, reward, terminated, truncated, info = e.step(a)
+        assert o.step(a21) == reward == 0 and not terminated and not truncated
+        worst = max(worst, float(np.abs(obs["agent_pos"] - obs0["agent_pos"]).max()))
+        if k == 299:
+            at300 = obs["agent_pos"].copy()
+    assert np.abs(obs["agent_pos"] - o.agent_pos()[:14]).max() <= 1e-4          # 400 steps = 8000 substeps next to the oracle
+    assert np.abs(obs["agent_pos"] - at300).max() <= 1e-5                        # settled: holds the pose
+    assert worst < 5e-2, worst                                                   # PD sag, not drift
+    e.close()
