@@ -17,6 +17,10 @@
 #include "avsim_render.cuh"
 
 #define AV_SORT_MAX 8192
+#ifndef AV_DEFAULT_HEAVY_TASKS
+#define AV_DEFAULT_HEAVY_TASKS 0
+#define AV_DEFAULT_HEAVY_WARPS 0
+#endif
 #ifndef AV_DEFAULT_WARPS
 #define AV_DEFAULT_WARPS 13
 #endif
@@ -165,7 +169,15 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_render_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SORT_MAX * (int)sizeof(unsigned long long)));
-    b->grid = std::min((num_envs + b->warps - 1) / b->warps, per_sm * sms);
+    // heavy tasks (BatchState::heavy_tasks): only when the batch is at least two rounds of resident slots, so that the slots the
+    // helper warps give up are a small share of the launch.  Diagnostic override: AVSIM_HEAVY="tasks:warps".
+    const char *eh = getenv("AVSIM_HEAVY");
+    int ht = AV_DEFAULT_HEAVY_TASKS, hw = AV_DEFAULT_HEAVY_WARPS;
+    if (eh && sscanf(eh, "%d:%d", &ht, &hw) != 2) { ht = 0; hw = 0; }
+    if (ht < 0 || hw < 1 || hw >= b->warps || num_envs < 2 * per_sm * sms * b->warps || (long long)ht * hw > num_envs / 4) ht = 0;
+    s.heavy_tasks = ht; s.heavy_warps = ht ? hw : 0;
+    int tasks = ht + (num_envs - ht * s.heavy_warps + b->warps - 1) / b->warps;
+    b->grid = std::min(tasks, per_sm * sms);
     b->fwd_grid = std::min(num_envs, 8 * sms);
     if (avsim_reset(b, nullptr, nullptr) != 0) { avsim_destroy(b); return nullptr; }
     return b;

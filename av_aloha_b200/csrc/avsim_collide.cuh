@@ -13,7 +13,8 @@
 #define AV_MPR_TOL 1e-6f
 #define AV_MPR_ITERS 50
 #ifndef AV_SUP_REDUX
-#define AV_SUP_REDUX 1   // REDUX argmax + register-carried winner in the hull support scan (0: shuffle butterfly + reload)
+#define AV_SUP_REDUX 0   // 1: REDUX argmax + register-carried winner in the hull support scan instead of the shuffle butterfly + reload.
+                         // Same results (emulator parity green); measured SLOWER on B200: 40.3 vs 39.95 ms/step (profiles/r1_summary.md)
 #endif
 #define AV_SUP_UNROLL 11   // 11 x 32 = 352 vertices per chunk: the finger hulls (345 / 347 vertices) scan in one chunk
 

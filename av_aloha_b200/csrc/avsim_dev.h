@@ -92,6 +92,10 @@ struct BatchState {
     long long *env_cycles;                          // [B] SM cycles the last step kernel spent on each environment
     uint64_t seed;
     int solver_iters, noslip_iters, multiccd;
+    // The first `heavy_tasks` entries of the work queue hand out only `heavy_warps` environments per block (the costliest ones:
+    // the queue is sorted); the block's remaining warps carry no environment and only pull pooled narrowphase items, which
+    // shortens the launch's critical path (the block with the costliest environments).  0 = every task takes a full block.
+    int heavy_tasks, heavy_warps;
     int sync;   // lockstep granularity of a block's warps: 2 = barrier after every stage, 1 = once per substep, 0 = none
 };
 

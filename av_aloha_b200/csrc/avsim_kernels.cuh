@@ -184,12 +184,15 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
     Prof pf;
     env_pipe_init(S, lane);
     for (;;) {
-        if (warp == 0 && lane == 0) s_base = atomicAdd(B.queue, W);
+        if (warp == 0 && lane == 0) s_base = atomicAdd(B.queue, 1);
         __syncthreads();
-        const int base = s_base;
+        const int task = s_base;
         __syncthreads();
+        // task -> slice of the sorted order: the first heavy_tasks tasks take heavy_warps environments each, the rest W
+        const int nenv = task < B.heavy_tasks ? B.heavy_warps : W;
+        const int base = task < B.heavy_tasks ? task * B.heavy_warps : B.heavy_tasks * B.heavy_warps + (task - B.heavy_tasks) * W;
         if (base >= B.num_envs) break;
-        const bool active = base + warp < B.num_envs;
+        const bool active = warp < nenv && base + warp < B.num_envs;
         const int env = active ? B.order[base + warp] : 0;
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
         const FCache fc = env_fcache(B, env);

@@ -203,13 +203,13 @@ def test_audit_rewards_equals_episode_by_episode_replay():
     """f3: all episodes at once == the reference's loop (set_qpos(all_qpos[0]); step_action; get_reward), one env at a time"""
     import torch
     from av_aloha_b200 import capi, model_io, replay, workload
-    E, T = 6, 150
+    E, T = 5, 260                                            # the scripted grasp reaches reward >= 2 between steps 180 and 250
     obj = workload.sample_object_positions(E, 11)
     acts = workload.slot_insertion_script(300, obj, 11)[:T].transpose(1, 0, 2).copy()       # [E, T, 21]
     model = capi.Model(model_io.model_path("slot_insertion", 3), 0)
     first = np.empty((E, model.nq), np.float32)
     seq = np.zeros((E, T), np.int32)
-    lengths = np.array([T, T, 100, T, 1, 0])
+    lengths = np.array([T, 100, T, 1, 0])
     for e in range(E):
         b = capi.Batch(model, 1, seed=0)
         b.set_options(solver_iters=8)
@@ -228,8 +228,8 @@ def test_audit_rewards_equals_episode_by_episode_replay():
         n = int(lengths[e])
         assert np.array_equal(out["rewards"][e, :n], seq[e, :n]), e
         assert int(out["episode_max"][e]) == (int(seq[e, :n].max()) if n else 0)
-    assert out["episode_max"].max() >= 1                       # the scripted policy at least touches / grasps
+    assert out["episode_max"].max() >= 2                       # the scripted policy grasps the stick in episode 0 (step 198)
     assert out["not_max_reward_episodes"] == [int(i) for i in np.nonzero(~out["max_reward_reached"])[0]]
-    assert 5 in out["not_max_reward_episodes"]                 # the empty episode can not have reached it
+    assert 4 in out["not_max_reward_episodes"]                 # the empty episode can not have reached it
     with pytest.raises(ValueError):
         replay.audit_rewards("slot_insertion", first[:, :5], acts)
