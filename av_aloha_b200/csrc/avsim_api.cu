@@ -24,6 +24,9 @@
 #ifndef AV_DEFAULT_WARPS
 #define AV_DEFAULT_WARPS 13
 #endif
+#ifndef AV_DEFAULT_ENVW
+#define AV_DEFAULT_ENVW 13
+#endif
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
@@ -106,7 +109,7 @@ struct avsim_batch {
     const avsim_model *model;
     BatchState st;
     cudaStream_t stream;
-    int grid, fwd_grid, warps;
+    int grid, fwd_grid, warps, envw;
     int64_t launches = 0;
     std::vector<void *> allocs;
     float *h_action = nullptr, *h_agent = nullptr;   // pinned staging for the host-buffer path
@@ -161,11 +164,17 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     CUP(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, m->device));
     CUP(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
     int esz = (int)sizeof(EnvS);
+    // block = `warps` warps, of which the first `envw` own an environment slice in shared memory (AVSIM_WARPS / AVSIM_ENVW)
+    const char *ee = getenv("AVSIM_ENVW");
     b->warps = ew ? atoi(ew) : AV_DEFAULT_WARPS;
-    b->warps = std::max(1, std::min(b->warps, std::min(AV_MAX_WARPS, (smem_blk - 64) / esz)));
-    int per_sm = eb ? atoi(eb) : std::max(1, smem_sm / (b->warps * esz + 1024));
-    per_sm = std::max(1, std::min(per_sm, smem_sm / (b->warps * esz + 1024)));
-    CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->warps * esz));
+    b->warps = std::max(1, std::min(b->warps, AV_MAX_WARPS));
+    b->envw = ee ? atoi(ee) : std::min(b->warps, AV_DEFAULT_ENVW);
+    b->envw = std::max(1, std::min(b->envw, std::min(b->warps, std::min(AV_MAX_ENVW, (smem_blk - 64) / esz))));
+    s.env_warps = b->envw;
+    int per_sm = eb ? atoi(eb) : std::max(1, smem_sm / (b->envw * esz + 1024));
+    per_sm = std::max(1, std::min(per_sm, smem_sm / (b->envw * esz + 1024)));
+    per_sm = std::max(1, std::min(per_sm, 64 / b->warps));                    // 64 resident warps per SM
+    CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_render_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SORT_MAX * (int)sizeof(unsigned long long)));
@@ -174,9 +183,9 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     const char *eh = getenv("AVSIM_HEAVY");
     int ht = AV_DEFAULT_HEAVY_TASKS, hw = AV_DEFAULT_HEAVY_WARPS;
     if (eh && sscanf(eh, "%d:%d", &ht, &hw) != 2) { ht = 0; hw = 0; }
-    if (ht < 0 || hw < 1 || hw >= b->warps || num_envs < 2 * per_sm * sms * b->warps || (long long)ht * hw > num_envs / 4) ht = 0;
+    if (ht < 0 || hw < 1 || hw >= b->envw || num_envs < 2 * per_sm * sms * b->envw || (long long)ht * hw > num_envs / 4) ht = 0;
     s.heavy_tasks = ht; s.heavy_warps = ht ? hw : 0;
-    int tasks = ht + (num_envs - ht * s.heavy_warps + b->warps - 1) / b->warps;
+    int tasks = ht + (num_envs - ht * s.heavy_warps + b->envw - 1) / b->envw;
     b->grid = std::min(tasks, per_sm * sms);
     b->fwd_grid = std::min(num_envs, 8 * sms);
     if (avsim_reset(b, nullptr, nullptr) != 0) { avsim_destroy(b); return nullptr; }
@@ -232,7 +241,7 @@ extern "C" int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps
     while (n2 < n) n2 <<= 1;
     if (n2 <= AV_SORT_MAX) avsim_order_kernel<<<1, 1024, n2 * sizeof(unsigned long long), b->stream>>>(b->st, n2);
     else avsim_identity_order_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->st);
-    avsim_step_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->warps, b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
+    avsim_step_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->envw, b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
     b->launches += 2;
     CU(cudaGetLastError());
     return AVSIM_OK;

@@ -21,7 +21,8 @@
 #define AV_NCON 64      // max contacts per environment (== AVSIM_MAX_CONTACTS)
 #define AV_NSC 20       // max scalar constraint rows (equality + friction loss + joint limits)
 #define AV_NCAND 64     // broadphase survivors per class
-#define AV_MAX_WARPS 15  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
+#define AV_MAX_ENVW 15   // environments (shared-memory slices) per block
+#define AV_MAX_WARPS 16  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
 #define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
 #ifndef AV_BULK_PREFETCH
 #define AV_BULK_PREFETCH 0 // 1: TMA bulk prefetch of contact blocks in the solver sweep (measured slower, see avsim_solve.cuh)
@@ -96,6 +97,9 @@ struct BatchState {
     // the queue is sorted); the block's remaining warps carry no environment and only pull pooled narrowphase items, which
     // shortens the launch's critical path (the block with the costliest environments).  0 = every task takes a full block.
     int heavy_tasks, heavy_warps;
+    // warps of a block that own an environment slice (<= blockDim.y); the block's other warps are helpers without shared-memory
+    // state that only pull pooled narrowphase items (registers allow 16 warps per SM, shared memory 13-15 environment slices)
+    int env_warps;
     int sync;   // lockstep granularity of a block's warps: 2 = barrier after every stage, 1 = once per substep, 0 = none
 };
 

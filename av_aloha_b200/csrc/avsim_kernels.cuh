@@ -178,19 +178,19 @@ __device__ __forceinline__ void block_collision(const DevModel &m, const BatchSt
 
 __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
                                                                           const float *__restrict__ action, int nsub) {
-    const int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y;
-    EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + warp);
+    const int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y, EW = B.env_warps;
+    EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + (warp < EW ? warp : 0));   // helper warps (warp >= EW) never touch S
     AV_SHARED int s_base;
     Prof pf;
-    env_pipe_init(S, lane);
+    if (warp < EW) env_pipe_init(S, lane);
     for (;;) {
         if (warp == 0 && lane == 0) s_base = atomicAdd(B.queue, 1);
         __syncthreads();
         const int task = s_base;
         __syncthreads();
         // task -> slice of the sorted order: the first heavy_tasks tasks take heavy_warps environments each, the rest W
-        const int nenv = task < B.heavy_tasks ? B.heavy_warps : W;
-        const int base = task < B.heavy_tasks ? task * B.heavy_warps : B.heavy_tasks * B.heavy_warps + (task - B.heavy_tasks) * W;
+        const int nenv = task < B.heavy_tasks ? B.heavy_warps : EW;
+        const int base = task < B.heavy_tasks ? task * B.heavy_warps : B.heavy_tasks * B.heavy_warps + (task - B.heavy_tasks) * EW;
         if (base >= B.num_envs) break;
         const bool active = warp < nenv && base + warp < B.num_envs;
         const int env = active ? B.order[base + warp] : 0;
