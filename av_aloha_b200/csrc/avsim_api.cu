@@ -171,6 +171,8 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     b->envw = ee ? atoi(ee) : std::min(b->warps, AV_DEFAULT_ENVW);
     b->envw = std::max(1, std::min(b->envw, std::min(b->warps, std::min(AV_MAX_ENVW, (smem_blk - 64) / esz))));
     s.env_warps = b->envw;
+    const char *ek = getenv("AVSIM_KEY");
+    s.key_pooled = ek ? atoi(ek) : 1;
     int per_sm = eb ? atoi(eb) : std::max(1, smem_sm / (b->envw * esz + 1024));
     per_sm = std::max(1, std::min(per_sm, smem_sm / (b->envw * esz + 1024)));
     per_sm = std::max(1, std::min(per_sm, 64 / b->warps));                    // 64 resident warps per SM

@@ -100,6 +100,7 @@ struct BatchState {
     // warps of a block that own an environment slice (<= blockDim.y); the block's other warps are helpers without shared-memory
     // state that only pull pooled narrowphase items (registers allow 16 warps per SM, shared memory 13-15 environment slices)
     int env_warps;
+    int key_pooled;   // 1: the queue's sort key (env_cycles) includes the environment's pooled narrowphase items, 0: only its own stages
     int sync;   // lockstep granularity of a block's warps: 2 = barrier after every stage, 1 = once per substep, 0 = none
 };
 

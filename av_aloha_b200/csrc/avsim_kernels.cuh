@@ -158,7 +158,7 @@ __device__ __forceinline__ void block_collision(const DevModel &m, const BatchSt
     pool_round(m, S, lane, warp, W, active ? 4 * S.ncand_c : 0, 4, &s_next, s_off, s_scr, s_cost);
     t0 = clock64();
     if (active) stage_collision_c(m, S, scratch, lane, multiccd, pf);
-    if (active) own += (clock64() - t0) + (long long)s_cost[warp];
+    if (active) own += (clock64() - t0) + (B.key_pooled ? (long long)s_cost[warp] : 0ll);
     if (B.sync >= 2) __syncthreads();
 }
 

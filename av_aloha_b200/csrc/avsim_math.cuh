@@ -120,10 +120,55 @@ __device__ __forceinline__ S6 inert_mul(const float *I, S6 v) {
     return f;
 }
 
-// read-only model data (hull vertices): non-coherent path
+// read-only model data (hull vertices): non-coherent path.  AV_HULL_HINT=1 adds the L1 evict_last priority: the hulls are
+// shared by all environments of an SM, the per-environment contact blocks that stream through the same L1 are not.
+#ifndef AV_HULL_HINT
+#define AV_HULL_HINT 0
+#endif
 __device__ __forceinline__ float4 ldg4(const float4 *p) {
 #ifdef __CUDA_ARCH__
+#if AV_HULL_HINT
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
     return __ldg(p);
+#endif
+#else
+    return *p;
+#endif
+}
+// loads of the solver's contact blocks inside the sweeps (per-environment scratch, re-read every sweep).  AV_CBLK_LD:
+// 0 default (allocate in L1), 1 ld.cg (L2 only), 2 L1::no_allocate, 3 L1::evict_first
+#ifndef AV_CBLK_LD
+#define AV_CBLK_LD 0
+#endif
+__device__ __forceinline__ float4 ldblk4(const float4 *p) {
+#if defined(__CUDA_ARCH__) && AV_CBLK_LD == 1
+    return __ldcg(p);
+#elif defined(__CUDA_ARCH__) && AV_CBLK_LD == 2
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#elif defined(__CUDA_ARCH__) && AV_CBLK_LD == 3
+    float4 v;
+    asm volatile("ld.global.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ float ldblk1(const float *p) {
+#if defined(__CUDA_ARCH__) && AV_CBLK_LD == 1
+    return __ldcg(p);
+#elif defined(__CUDA_ARCH__) && AV_CBLK_LD == 2
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#elif defined(__CUDA_ARCH__) && AV_CBLK_LD == 3
+    float v;
+    asm volatile("ld.global.L1::evict_first.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 #else
     return *p;
 #endif

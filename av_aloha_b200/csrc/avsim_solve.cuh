@@ -78,7 +78,7 @@ __device__ __forceinline__ void cblk_load(const float *blk, CBlk &c) {
     float v[52];
 #pragma unroll
     for (int i = 0; i < 13; i++) {
-        float4 q = p[i];
+        float4 q = ldblk4(p + i);
         v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
     }
 #pragma unroll
@@ -408,7 +408,7 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
         const float *J = blk + AV_CB_J;
         float jc[6], res[6], old[6], f[6], df[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) jc[k] = J[k * AV_JW + col];
+        for (int k = 0; k < 6; k++) jc[k] = ldblk1(J + k * AV_JW + col);
         const float x = dof >= 0 ? S.acc[dof] : 0.f;
 #pragma unroll
         for (int k = 0; k < 6; k++) res[k] = jc[k] * x;

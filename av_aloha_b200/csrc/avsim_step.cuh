@@ -41,7 +41,8 @@ struct Prof {
 // slice size sets how many environments fit on an SM, and the kernel is latency-bound: more resident warps = more
 // throughput).  Stage order: kinematics -> inertia -> collision -> smooth -> rows_scalar -> rows_contact -> solve ->
 // integrate.  Lifetimes:
-//   crb   : composite inertias (inertia) | cacc,cfrc (smooth) | Cholesky factor L (end of inertia; integrate)
+//   crb   : composite inertias (inertia) | cacc,cfrc (smooth) | Cholesky factor L (end of inertia; integrate) |
+//           J staging of the contact being assembled + M^-1 J^T of the scalar rows (rows_scalar..solve)
 //   u1    : broadphase candidates + world AABBs (kinematics..collision) | cvel, cdofdot (smooth)
 //   u2    : cinert, xipos (kinematics..smooth) | contact forces, multipliers, tree descriptors, J staging (rows_contact..solve)
 //   u3    : geom centres (kinematics..collision) | scalar constraint rows (rows_scalar..solve)
@@ -53,6 +54,10 @@ struct EnvS {
     union {
         float crb[AV_NB * 12];
         float L[AV_MBLK];
+        struct {                                      // rows_scalar .. solve: the region is free between smooth and integrate
+            __align__(16) float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
+            float sc_MJ[AV_NSC * AV_TD];
+        };
     };
     float M[AV_MBLK], Minv[AV_MBLK];
     float qfrc_smooth[AV_NVP], qacc_smooth[AV_NVP], acc[AV_NVP], qfrc_bias[AV_NVP];
@@ -63,7 +68,6 @@ struct EnvS {
     union {
         struct { float cinert[AV_NB * 10], xipos[AV_NB * 3]; };
         struct {
-            __align__(16) float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
             float c_f[AV_NCON * 6], c_lam[AV_NCON];
             int c_tree[AV_NCON];  // packed dof ranges / tree ids of the two kinematic trees (tr_pack)
             unsigned short c_slot[AV_NCON];  // solver schedule: contact a | contact b << 8 (0xff: none) per half-warp slot
@@ -74,7 +78,7 @@ struct EnvS {
         struct {
             int sc_dof1[AV_NSC], sc_dof2[AV_NSC], sc_tree[AV_NSC], sc_key[AV_NSC];
             float sc_c1[AV_NSC], sc_c2[AV_NSC], sc_b[AV_NSC], sc_R[AV_NSC], sc_f[AV_NSC], sc_lo[AV_NSC], sc_hi[AV_NSC],
-                sc_A[AV_NSC], sc_aref[AV_NSC], sc_MJ[AV_NSC * AV_TD];
+                sc_A[AV_NSC], sc_aref[AV_NSC];
         };
     };
     // contacts (collision .. outputs); position / frame / distance / friction live in the contact's global scratch block
@@ -89,6 +93,8 @@ struct EnvS {
     int ncon, nsc, ncand_p, ncand_c, nkeep, nslot, status;
 };
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");
+static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[2 * 6 * AV_JW + AV_NSC * AV_TD]), "row staging must fit inside crb");
+static_assert(sizeof(EnvS) % 16 == 0, "slices must keep 16-byte alignment");
 
 // per-environment view of the constraint-force cache in global memory (BatchState.fc_*)
 struct FCache {

@@ -78,7 +78,7 @@ EmuBatch *emu_create(const char *path, int num_envs) {
     b->fckey.assign(B * (AV_NCON + AV_NSC), 0); b->fcn.assign(B * 2, 0); b->fcval.assign(B * (AV_NCON * 6 + AV_NSC), 0.f);
     s.fc_key = b->fckey.data(); s.fc_n = b->fcn.data(); s.fc_val = b->fcval.data(); s.warm_mode = 1;
     b->order.resize(B); b->queue.assign(1, 0); s.order = b->order.data(); s.queue = b->queue.data();
-    s.env_warps = 1;   // the emulated block is one warp = one environment
+    s.env_warps = 1; s.key_pooled = 1;   // the emulated block is one warp = one environment
     s.reward = I(0, B); s.status = I(1, B); s.latch = I(2, B); s.ncon = I(3, B); s.episode = I(4, B);
     return b;
 }
