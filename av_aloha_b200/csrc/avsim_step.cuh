@@ -43,8 +43,9 @@ struct Prof {
 // integrate.  Lifetimes:
 //   crb   : composite inertias (inertia) | cacc,cfrc (smooth) | Cholesky factor L (end of inertia; integrate) |
 //           J staging of the contact being assembled + M^-1 J^T of the scalar rows (rows_scalar..solve)
-//   u1    : broadphase candidates + world AABBs (kinematics..collision) | cvel, cdofdot (smooth)
-//   u2    : cinert, xipos (kinematics..smooth) | contact forces, multipliers, tree descriptors, J staging (rows_contact..solve)
+//   u1    : broadphase candidates + world AABBs (kinematics..collision) | cvel, cdofdot (smooth) | contact forces, multipliers
+//           (rows_contact..solve)
+//   u2    : cinert, xipos (kinematics..smooth) | tree descriptors, solver schedule (rows_contact..solve)
 //   u3    : geom centres (kinematics..collision) | scalar constraint rows (rows_scalar..solve)
 struct EnvS {
     float qpos[AV_NQ], qvel[AV_NVP], ctrl[24], warm[AV_NVP];
@@ -64,11 +65,11 @@ struct EnvS {
     union {
         struct { float gaabb[AV_NG * 3]; int cand_p[AV_NCAND], cand_c[AV_NCAND], keep_c[AV_NKEEP]; };
         struct { float cvel[AV_NB * 6], cdofdot[AV_NV * 6]; };
+        struct { float c_f[AV_NCON * 6], c_lam[AV_NCON]; };   // contact forces and cone multipliers (rows_contact..solve, cache store)
     };
     union {
         struct { float cinert[AV_NB * 10], xipos[AV_NB * 3]; };
         struct {
-            float c_f[AV_NCON * 6], c_lam[AV_NCON];
             int c_tree[AV_NCON];  // packed dof ranges / tree ids of the two kinematic trees (tr_pack)
             unsigned short c_slot[AV_NCON];  // solver schedule: contact a | contact b << 8 (0xff: none) per half-warp slot
         };
