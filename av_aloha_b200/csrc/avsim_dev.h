@@ -18,6 +18,8 @@
 #define AV_NTREE 6
 #define AV_TD 8         // max dofs per kinematic tree
 #define AV_MBLK (AV_NTREE * AV_TD * AV_TD)
+#define AV_MTRI (AV_TD * (AV_TD + 1) / 2)   // packed lower triangle of one tree's mass block (M is symmetric; only M^-1 and L are kept full)
+#define AV_MPK (AV_NTREE * AV_MTRI)
 #define AV_NCON 64      // max contacts per environment (== AVSIM_MAX_CONTACTS)
 #define AV_NSC 20       // max scalar constraint rows (equality + friction loss + joint limits)
 #define AV_NCAND 64     // broadphase survivors per class

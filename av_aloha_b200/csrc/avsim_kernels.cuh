@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const 
             B.qacc_smooth[(size_t)env * m.nv + i] = S.qacc_smooth[i];
             B.qfrc_bias[(size_t)env * m.nv + i] = S.qfrc_bias[i];
             int t = m.dof_tree[i], dl = i - m.tree_dofadr[t];
-            B.mass_diag[(size_t)env * m.nv + i] = S.M[t * AV_TD * AV_TD + dl * AV_TD + dl];
+            B.mass_diag[(size_t)env * m.nv + i] = S.M[t * AV_MTRI + av_mtri(dl, dl)];
         }
         for (int i = lane; i < 3 * m.nbody; i += 32) B.xpos[(size_t)env * 3 * m.nbody + i] = S.xpos[i];
         env_outputs(m, B, S, scratch, env, lane, false);

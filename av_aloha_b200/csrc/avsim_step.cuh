@@ -60,7 +60,7 @@ struct EnvS {
             float sc_MJ[AV_NSC * AV_TD];
         };
     };
-    float M[AV_MBLK], Minv[AV_MBLK];
+    float M[AV_MPK], Minv[AV_MBLK];   // M: packed lower triangles (av_mtri), read by the two factorisations and one mat-vec per substep
     float qfrc_smooth[AV_NVP], qacc_smooth[AV_NVP], acc[AV_NVP], qfrc_bias[AV_NVP];
     union {
         struct { float gaabb[AV_NG * 3]; int cand_p[AV_NCAND], cand_c[AV_NCAND], keep_c[AV_NKEEP]; };
@@ -210,12 +210,13 @@ __device__ AV_STAGE void stage_kinematics(const DevModel &m, EnvS &S, int lane) 
 }
 
 // ------------------------------------------------------------------ K3a: CRB, factorisation, block inverse
-// Cholesky of the nt x nt block at A (stride AV_TD) into Lb (lower); returns false on a non-positive pivot
+__device__ __forceinline__ int av_mtri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }   // packed symmetric index
+// Cholesky of the nt x nt block at A (packed lower triangle) into Lb (lower, stride AV_TD); returns false on a non-positive pivot
 __device__ inline bool chol_block(const float *A, float *Lb, int nt, const float *diag_add, float h) {
     bool ok = true;
     for (int i = 0; i < nt; i++)
         for (int j = 0; j <= i; j++) {
-            float s = A[i * AV_TD + j];
+            float s = A[i * (i + 1) / 2 + j];
             if (i == j && diag_add) s += h * diag_add[i];
             for (int k = 0; k < j; k++) s -= Lb[i * AV_TD + k] * Lb[j * AV_TD + k];
             if (i == j) {
@@ -240,7 +241,7 @@ __device__ inline void chol_block_solve(const float *Lb, int nt, float *x) {
 }
 
 __device__ AV_STAGE void stage_inertia(const DevModel &m, EnvS &S, int lane) {
-    for (int i = lane; i < AV_MBLK; i += 32) S.M[i] = 0.f;
+    for (int i = lane; i < AV_MPK; i += 32) S.M[i] = 0.f;
     if (lane < m.ntree) {  // composite inertias, leaves to root
         int b0 = m.tree_bodyadr[lane], nb = m.tree_bodynum[lane];
         for (int b = b0; b < b0 + nb; b++)
@@ -254,18 +255,17 @@ __device__ AV_STAGE void stage_inertia(const DevModel &m, EnvS &S, int lane) {
     for (int i = lane; i < m.nv; i += 32) {  // lane = dof: one row of M up the ancestor chain
         int t = m.dof_tree[i], d0 = m.tree_dofadr[t];
         S6 f = inert_mul(S.crb + 12 * m.dof_body[i], ld6(S.cdof + 6 * i));
-        float *Mb = S.M + t * AV_TD * AV_TD;
-        for (int j = i; j >= 0; j = m.dof_parent[j]) {
+        float *Mb = S.M + t * AV_MTRI;
+        for (int j = i; j >= 0; j = m.dof_parent[j]) {           // ancestors have smaller indices: (i, j) is in the lower triangle
             float v = dot6(ld6(S.cdof + 6 * j), f);
             if (j == i) v += m.dof_armature[i];
-            Mb[(i - d0) * AV_TD + (j - d0)] = v;
-            Mb[(j - d0) * AV_TD + (i - d0)] = v;
+            Mb[av_mtri(i - d0, j - d0)] = v;
         }
     }
     __syncwarp();
     if (lane < m.ntree) {
         int nt = m.tree_dofnum[lane];
-        if (!chol_block(S.M + lane * AV_TD * AV_TD, S.L + lane * AV_TD * AV_TD, nt, nullptr, 0.f)) S.status |= 1;
+        if (!chol_block(S.M + lane * AV_MTRI, S.L + lane * AV_TD * AV_TD, nt, nullptr, 0.f)) S.status |= 1;
     }
     __syncwarp();
     for (int w = lane; w < m.nv; w += 32) {  // lane = (tree, column) of the block inverse
@@ -684,9 +684,9 @@ __device__ AV_STAGE void stage_integrate(const DevModel &m, EnvS &S, int lane) {
         int d = pass ? i2 : i;
         if (d < m.nv) {
             int t = m.dof_tree[d], d0 = m.tree_dofadr[t], nt = m.tree_dofnum[t];
-            const float *row = S.M + t * AV_TD * AV_TD + (d - d0) * AV_TD;
+            const float *Mb = S.M + t * AV_MTRI;
             float s = S.qfrc_smooth[d];
-            for (int k = 0; k < nt; k++) s += row[k] * S.acc[d0 + k];
+            for (int k = 0; k < nt; k++) s += Mb[av_mtri(d - d0, k)] * S.acc[d0 + k];
             if (pass) tot2 = s; else tot = s;
         }
     }
@@ -697,7 +697,7 @@ __device__ AV_STAGE void stage_integrate(const DevModel &m, EnvS &S, int lane) {
     if (lane < m.ntree) {
         int nt = m.tree_dofnum[lane], d0 = m.tree_dofadr[lane];
         float *Lb = S.L + lane * AV_TD * AV_TD;
-        chol_block(S.M + lane * AV_TD * AV_TD, Lb, nt, m.dof_damping + d0, h);
+        chol_block(S.M + lane * AV_MTRI, Lb, nt, m.dof_damping + d0, h);
         float x[AV_TD];
         for (int k = 0; k < nt; k++) x[k] = S.qfrc_bias[d0 + k];
         chol_block_solve(Lb, nt, x);
