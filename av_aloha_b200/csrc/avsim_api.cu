@@ -25,7 +25,7 @@
 #define AV_DEFAULT_WARPS 16   // 16 warps x 128 registers fill the register file of an SM
 #endif
 #ifndef AV_DEFAULT_ENVW
-#define AV_DEFAULT_ENVW 13
+#define AV_DEFAULT_ENVW 11   // 11 slices of 11.8 KB keep the shared-memory carve-out at 132 KB (~124 KB of L1); measured best (profiles/r1_sweeps.txt)
 #endif
 
 static thread_local char g_err[512] = "";

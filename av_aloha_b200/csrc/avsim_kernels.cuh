@@ -114,11 +114,12 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
 // Environments differ ~5x in cost; avsim_order_kernel sorts the queue by the cycles each environment took in the
 // previous step (costliest first), which (a) fills the tail of the launch with cheap environments and (b) puts
 // environments of similar cost into the same block, so the lockstep barriers wait for little.
-// Block shape (measured, profiles/r1_summary.md): blockDim.y = 16 warps, of which the first B.env_warps = 13 own an
-// environment slice; the other 3 are HELPER warps without shared-memory state that only pull pooled narrowphase items
-// (16 warps x 128 registers fill the SM's register file, and 13 slices of 12.5 KB keep the shared-memory carve-out at
-// 164 KB, which leaves ~92 KB of L1 for the hull vertices and contact blocks -- the slice count is chosen by the L1 it
-// leaves, not by the shared memory it fills: 14 slices push the carve-out to 196 KB and cost 4 %).
+// Block shape (measured, profiles/r1_summary.md): blockDim.y = 16 warps, of which the first B.env_warps = 11 own an
+// environment slice; the other 5 are HELPER warps without shared-memory state that only pull pooled narrowphase items
+// (16 warps x 128 registers fill the SM's register file).  The slice count is chosen by the L1 it leaves, not by the
+// shared memory it fills: shared memory and L1 split one 256 KB array in steps (... 132, 164, 196, 228 KB); 11 slices of
+// 11.8 KB stay inside the 132 KB step (~124 KB of L1 for hull vertices and contact blocks), 12-13 slices need the 164 KB
+// step and run 6 % slower although more environments are resident, 14 need 196 KB and lose another 4 %.
 // Collision of a lockstep block: phase A per environment, then the MPR runs of ALL the block's environments are pooled and
 // every warp (also the ones without an environment) pulls items -- first the unperturbed runs, then the perturbed
 // (multiccd) runs of the pairs that touch -- then phase C per environment.
