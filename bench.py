@@ -43,7 +43,7 @@ EPISODE_LEN = 300
 ALGO_BYTES_PER_ENV_STEP = 1032   # fp32 state read + written per env.step
 HOME = np.array([0, -0.082, 1.06, 0, -0.953, 0, 0.02239] * 2 + [0, -0.8, 0.8, 0, 0.5, 0, 0], np.float64)
 METRIC = "env-steps/sec SlotInsertion-3Arms batch=4096"
-NCU_DRAM_BYTES_PER_LAUNCH = 736.6e6   # dram read 63.6 MB + write 672.9 MB per launch at B=4096 (profiles/r1_step_kernel_ncu.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 590.7e6   # dram read 39.8 MB + write 550.9 MB per launch at B=4096 (profiles/r1_step_kernel_ncu.txt)
 
 
 def make_workload(B, seed):
