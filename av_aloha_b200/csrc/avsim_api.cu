@@ -28,6 +28,11 @@
 #define AV_DEFAULT_ENVW 11   // 11 slices of 11.8 KB keep the shared-memory carve-out at 132 KB (~124 KB of L1); measured best (profiles/r1_sweeps.txt)
 #endif
 
+// The default slice count is chosen for the shared-memory / L1 split it leaves: growing EnvS past
+// this bound silently moves the kernel to the next carve-out step (132 -> 164 KB) and costs ~6 % -- fail the build instead.
+static_assert(AV_DEFAULT_ENVW * sizeof(EnvS) + 1024 /* static + per-block reserve */ + 1024 <= 132 * 1024,
+              "EnvS grew: AV_DEFAULT_ENVW slices no longer fit the 132 KB shared-memory carve-out");
+
 static thread_local char g_err[512] = "";
 static int fail(int code, const char *fmt, const char *a = "", const char *b = "") {
     snprintf(g_err, sizeof g_err, fmt, a, b);

@@ -8,12 +8,12 @@ from av_aloha_b200 import capi
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-variants = [tuple(int(x) for x in v.split(":")) for v in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["14:1", "7:2", "4:3", "2:7", "1:14"])]
+variants = [tuple(int(x) for x in v.split(":")) for v in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["16:1:2:11", "16:1:2:13", "13:1:2:13"])]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for v in variants:
     nw, nb = v[0], v[1]
     sync = v[2] if len(v) > 2 else 2
-    envw = v[3] if len(v) > 3 else min(nw, 13)      # warps that own an environment slice; the rest only help the pooled narrowphase
+    envw = v[3] if len(v) > 3 else min(nw, 11)      # warps that own an environment slice; the rest only help the pooled narrowphase
     os.environ["AVSIM_WARPS"], os.environ["AVSIM_BLOCKS"], os.environ["AVSIM_SYNC"] = str(nw), str(nb), str(sync)
     os.environ["AVSIM_ENVW"] = str(envw)
     model, batch, acts, masks, mask_any, fp, t0 = steady.restore(B, iters)
