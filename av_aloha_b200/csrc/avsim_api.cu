@@ -30,7 +30,7 @@
 
 // The default slice count is chosen for the shared-memory / L1 split it leaves: growing EnvS past
 // this bound silently moves the kernel to the next carve-out step (132 -> 164 KB) and costs ~6 % -- fail the build instead.
-static_assert(AV_DEFAULT_ENVW * sizeof(EnvS) + 1024 /* static + per-block reserve */ + 1024 <= 132 * 1024,
+static_assert(AV_DEFAULT_ENVW * sizeof(EnvS) + 512 /* static shared memory */ + 1024 /* per-block reserve */ <= 132 * 1024,
               "EnvS grew: AV_DEFAULT_ENVW slices no longer fit the 132 KB shared-memory carve-out");
 
 static thread_local char g_err[512] = "";
