@@ -444,3 +444,11 @@ extern "C" int avsim_fk(const avsim_model *m, int arm, const float *q, int n, fl
     CU(cudaGetLastError());
     return AVSIM_OK;
 }
+extern "C" int avsim_jac(const avsim_model *m, int arm, const float *q, int n, float *J_out, void *stream) {
+    if (!m || !q || !J_out || arm < 0 || arm > 2 || n < 0) return fail(AVSIM_ERR_ARG, "avsim_jac: bad arguments");
+    CU(cudaSetDevice(m->device));
+    if (n == 0) return AVSIM_OK;
+    avsim_jac_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(m->dm, arm, q, n, J_out);
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}

@@ -142,6 +142,20 @@ __global__ void avsim_fk_kernel(DevModel m, int arm, const float *__restrict__ q
     o[12] = o[13] = o[14] = 0.f; o[15] = 1.f;
 }
 
+// jacobian(theta) of create_jac_fn (kinematics.py:28-52): space Jacobian, rows [v; w]; out f32 [n][6][ndof]
+__global__ void avsim_jac_kernel(DevModel m, int arm, const float *__restrict__ q, int n, float *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ArmTab A;
+    load_arm(m, arm, A);
+    double th[7], J[6][7];
+    for (int k = 0; k < A.n; k++) th[k] = q[(size_t)i * A.n + k];
+    ik_jac(A, th, J);
+    float *o = out + (size_t)i * 6 * A.n;
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c < A.n; c++) o[r * A.n + c] = (float)J[r][c];
+}
+
 // DiffIK.run (diff_ik.py:51-90)
 __global__ void avsim_diffik_kernel(DevModel m, int arm, const float *__restrict__ q_in, const float *__restrict__ pos,
                                     const float *__restrict__ quat_wxyz, int n, DiffIKParams P, float *__restrict__ q_out) {

@@ -133,6 +133,29 @@ def create_fk_fn(model, arm):
     return forward_kinematics
 
 
+def create_jac_fn(model, arm):
+    """``jacobian(theta) -> 6 x n`` (or [N, 6, n]) space Jacobian of the end-effector site, rows [v; w] (reference
+    kinematics.py:28-52; what DiffIK iterates on)."""
+    a = _arm(arm)
+    ndof = (6, 6, 7)[a]
+
+    def jacobian(theta):
+        import torch
+
+        dev = torch.device("cuda", model.device)
+        as_np = not hasattr(theta, "is_cuda")
+        th = torch.as_tensor(np.asarray(theta, np.float32) if as_np else theta, dtype=torch.float32, device=dev)
+        single = th.dim() == 1
+        th = th.reshape(-1, ndof).contiguous()
+        out = torch.empty((len(th), 6, ndof), dtype=torch.float32, device=dev)
+        capi.check(model.lib.avsim_jac(model.ptr, a, C.c_void_p(th.data_ptr()), len(th), C.c_void_p(out.data_ptr()), None))
+        if as_np:
+            out = out.cpu().numpy().astype(np.float64)
+        return out[0] if single else out
+
+    return jacobian
+
+
 # ---- create_safety_fn / safety (reference data_collection_scripts/kinematics.py:54-135).  The checks are host predicates
 # over the FK kernel's pose; rows are checked in the reference's order and the first failing check names the message.
 SAFETY_MESSAGES = ("", "Joint tracking safety margin exceeded", "Joint limit safety margin exceeded",

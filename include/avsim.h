@@ -130,6 +130,8 @@ int avsim_gradik(const avsim_model *m, int arm, const float *q_dev, const float 
                  int n, const avsim_gradik_params *p, float *q_out_dev, void *stream);
 /* product-of-exponentials forward kinematics of an arm's end-effector site (kinematics.py:7-26): out f32[n][16] */
 int avsim_fk(const avsim_model *m, int arm, const float *q_dev, int n, float *T_out_dev, void *stream);
+/* space Jacobian of the same site, rows re-ordered to [v; w] (kinematics.py:28-52): out f32[n][6][ndof] (ndof = 6, 6, 7) */
+int avsim_jac(const avsim_model *m, int arm, const float *q_dev, int n, float *J_out_dev, void *stream);
 
 const char *avsim_last_error(void);
 

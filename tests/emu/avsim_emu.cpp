@@ -125,6 +125,10 @@ void emu_fk(EmuBatch *b, int arm, const float *q, int n, float *T_out) {
     int nb = (n + 31) / 32;
     for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_fk_kernel(b->pk.dm, arm, q, n, T_out); });
 }
+void emu_jac(EmuBatch *b, int arm, const float *q, int n, float *J_out) {
+    int nb = (n + 31) / 32;
+    for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_jac_kernel(b->pk.dm, arm, q, n, J_out); });
+}
 void emu_diffik(EmuBatch *b, int arm, const float *q, const float *pos, const float *quat, int n, const DiffIKParams *p, float *out) {
     int nb = (n + 31) / 32;
     for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_diffik_kernel(b->pk.dm, arm, q, pos, quat, n, *p, out); });

@@ -95,6 +95,7 @@ def _ik_setup():
     L = lib()
     fp = C.POINTER(C.c_float)
     L.emu_fk.argtypes = [C.c_void_p, C.c_int, fp, C.c_int, fp]
+    L.emu_jac.argtypes = [C.c_void_p, C.c_int, fp, C.c_int, fp]
     L.emu_diffik.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_int, C.POINTER(DiffIKParams), fp]
     L.emu_gradik.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_int, C.POINTER(GradIKParams), fp]
     return L
@@ -110,6 +111,14 @@ def emu_fk(eb, arm, q):
     out = np.zeros((len(q), 16), np.float32)
     L.emu_fk(eb.ptr, arm, _fp(q), len(q), _fp(out))
     return out.reshape(-1, 4, 4)
+
+
+def emu_jac(eb, arm, q):
+    L = _ik_setup()
+    q = np.ascontiguousarray(q, np.float32)
+    out = np.zeros((len(q), 6, q.shape[1]), np.float32)
+    L.emu_jac(eb.ptr, arm, _fp(q), len(q), _fp(out))
+    return out
 
 
 def emu_diffik(eb, arm, q, pos, quat, params):

@@ -102,6 +102,14 @@ def test_emu_fk_matches_reference(gold, emu_batch, arm):
 
 
 @pytest.mark.parametrize("arm", [0, 1, 2])
+def test_emu_jacobian_matches_reference(gold, emu_batch, arm):
+    """create_jac_fn (kinematics.py:28-52): golden = the reference's own jacobian() on the FK test poses"""
+    emu, eb = emu_batch
+    J = emu.emu_jac(eb, arm, gold[f"fk_q_{arm}"])
+    assert J.shape == gold[f"jac_J_{arm}"].shape and np.abs(J - gold[f"jac_J_{arm}"]).max() <= TOL_FK
+
+
+@pytest.mark.parametrize("arm", [0, 1, 2])
 @pytest.mark.parametrize("tag", ["sim", "real"])
 def test_emu_diffik_matches_reference(gold, emu_batch, arm, tag):
     emu, eb = emu_batch
@@ -134,6 +142,17 @@ def test_gpu_fk(gold, gpu_model, arm):
     from av_aloha_b200 import kinematics
     T = kinematics.create_fk_fn(gpu_model, arm)(gold[f"fk_q_{arm}"])
     assert np.abs(T - gold[f"fk_T_{arm}"]).max() <= TOL_FK
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arm", [0, 1, 2])
+def test_gpu_jacobian(gold, gpu_model, arm):
+    from av_aloha_b200 import kinematics
+    jac = kinematics.create_jac_fn(gpu_model, arm)
+    J = jac(gold[f"fk_q_{arm}"])
+    assert J.shape == gold[f"jac_J_{arm}"].shape and np.abs(J - gold[f"jac_J_{arm}"]).max() <= TOL_FK
+    one = jac(gold[f"fk_q_{arm}"][0])                                    # single pose, like the reference's jacobian(theta)
+    assert one.shape == gold[f"jac_J_{arm}"][0].shape and np.abs(one - gold[f"jac_J_{arm}"][0]).max() <= TOL_FK
 
 
 @pytest.mark.gpu
