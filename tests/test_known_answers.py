@@ -91,3 +91,69 @@ def test_gpu_free_fall_and_spin_closed_form(slot_model_path):
     assert np.abs(qpos[:, qadr + 3:qadr + 7] - quat).max() <= 1e-5
     assert np.abs(qv[:, dof + 3:dof + 6] - [0, 0, W_SPIN]).max() <= 1e-5
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Static equilibrium (Newton's first law through the whole contact pipeline): the stick (0.3536 kg, 4 box-box contacts
+# with the table) and the slot (100 kg) at rest on the table.  Once settled, the constraint solve must return contact
+# forces whose resultant cancels gravity: qfrc_constraint_z = m g, qacc = 0 -- independent of solref / solimp / cone
+# details, which only set the penetration at which that happens.
+REST = np.array([[0.0, 0.12, 0.0], [0.02, -0.05, 0.0]])
+
+
+def _settled_oracle(path):
+    from oracle.oracle import OracleEnv, OracleModel
+    o = OracleEnv(OracleModel(path))
+    o.set_options(max_iter=200, tol=1e-12, warmstart=1)
+    o.reset(free_pos=REST)
+    act = HOME.copy(); act[6] = act[13] = 1.0
+    for _ in range(25):                                       # 1 s: the soft contacts (solref 0.02 s) have long settled
+        o.step(act)
+    o.forward()
+    return o
+
+
+def test_oracle_resting_bodies_carry_their_weight(slot_model_path):
+    o = _settled_oracle(slot_model_path)
+    g = 9.81
+    for dof in (o.model.nv - 6, o.model.nv - 12):             # stick, slot (free joints: the last twelve dofs)
+        m = o.M[dof + 2, dof + 2]
+        assert abs(o.qfrc_constraint[dof + 2] / (m * g) - 1.0) <= 1e-9
+        assert np.abs(o.qacc[dof:dof + 6]).max() <= 1e-9 and np.abs(o.qvel[dof:dof + 6]).max() <= 1e-9
+    assert o.M[o.model.nv - 6 + 2, o.model.nv - 6 + 2] == pytest.approx(0.3536, rel=1e-6)       # task_slot_insertion.xml stick mass
+    assert o.ncon >= 8
+
+
+def test_kernel_source_resting_bodies_carry_their_weight(slot_model_path):
+    """the CUDA forward pass (emulated, fp32) at the settled state: gravity is cancelled to 1e-4 of g"""
+    from tests.emu.emu import EmuBatch
+    o = _settled_oracle(slot_model_path)
+    eb = EmuBatch(slot_model_path, 1)
+    eb.set_options(50)
+    eb.reset(REST[None])
+    eb.qpos[0, :], eb.qvel[0, :], eb.ctrl[0, :] = o.qpos.astype(np.float32), 0.0, o.ctrl.astype(np.float32)
+    eb.forward()
+    assert eb.ncon[0] == o.ncon and eb.status[0] == 0
+    for dof in (eb.nv - 6, eb.nv - 12):
+        assert abs(eb.qacc_smooth[0, dof + 2] + 9.81) <= 1e-4            # free body: smooth acceleration = gravity
+        assert abs(eb.qacc[0, dof + 2]) <= 1e-3                          # ... cancelled by the contact forces
+
+
+@pytest.mark.gpu
+def test_gpu_resting_bodies_carry_their_weight(slot_model_path):
+    from av_aloha_b200 import capi
+    o = _settled_oracle(slot_model_path)
+    model = capi.Model(slot_model_path, 0)
+    b = capi.Batch(model, 2, seed=0)
+    b.set_options(solver_iters=50)
+    b.reset(free_pos=np.tile(REST[None], (2, 1, 1)))
+    b.set(capi.QPOS, np.tile(o.qpos.astype(np.float32), (2, 1)))
+    b.set(capi.QVEL, np.zeros((2, model.nv), np.float32))
+    b.set(capi.CTRL, np.tile(o.ctrl.astype(np.float32), (2, 1)))
+    b.forward()
+    qacc, smooth = b.get(capi.QACC).cpu().numpy(), b.get(capi.QACC_SMOOTH).cpu().numpy()
+    assert (b.get(capi.NCON).cpu().numpy() == o.ncon).all() and int(b.get(capi.STATUS).max().item()) == 0
+    for dof in (model.nv - 6, model.nv - 12):
+        assert np.abs(smooth[:, dof + 2] + 9.81).max() <= 1e-4
+        assert np.abs(qacc[:, dof + 2]).max() <= 1e-3
+    b.close()
