@@ -157,3 +157,48 @@ def test_gpu_resting_bodies_carry_their_weight(slot_model_path):
         assert np.abs(smooth[:, dof + 2] + 9.81).max() <= 1e-4
         assert np.abs(qacc[:, dof + 2]).max() <= 1e-3
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Rigid-body inertia of the task objects from the MJCF numbers alone (reference assets/task_slot_insertion.xml:5-16):
+# box of half sizes (a, b, c) and mass m: I_com = m/3 diag(b^2 + c^2, a^2 + c^2, a^2 + b^2), shifted to the body origin by the
+# parallel-axis term m (|r|^2 1 - r r^T); a free joint's mass block is [[m 1, -m [r]x], [m [r]x, I_origin]].  Default
+# density 1000 kg/m^3 for geoms without a mass attribute.  Pins the model compiler (mesh-free part) and the CRB stage.
+def _box(m, half, r):
+    a, b, c = half
+    I = m / 3.0 * np.diag([b * b + c * c, a * a + c * c, a * a + b * b])
+    r = np.asarray(r, float)
+    return I + m * (r @ r * np.eye(3) - np.outer(r, r)), m * r
+
+
+def _free_block(parts):
+    M = np.zeros((6, 6))
+    for m, half, r in parts:
+        I, mr = _box(m, half, r)
+        M[:3, :3] += m * np.eye(3)
+        M[3:, 3:] += I
+        K = np.array([[0, -mr[2], mr[1]], [mr[2], 0, -mr[0]], [-mr[1], mr[0], 0]])      # m [r]x
+        M[:3, 3:] -= K
+        M[3:, :3] += K
+    return M
+
+
+STICK = [(1000.0 * 8 * 0.17 * 0.013 * 0.02, (0.17, 0.013, 0.02), (0, 0, 0.02))]
+SLOT = [(50.0, (0.1, 0.015, 0.02), (0, 0.032, 0.02)), (50.0, (0.1, 0.015, 0.02), (0, -0.032, 0.02))]
+
+
+def test_free_body_mass_blocks_match_the_mjcf_numbers(slot_model_path):
+    from oracle.oracle import OracleEnv, OracleModel
+    from tests.emu.emu import EmuBatch
+    o = OracleEnv(OracleModel(slot_model_path))
+    o.reset(free_pos=REST)                                    # identity orientation: body frame = world frame
+    o.forward()
+    nv = o.model.nv
+    eb = EmuBatch(slot_model_path, 1)
+    eb.reset(REST[None])
+    eb.forward()
+    for dof, parts in ((nv - 6, STICK), (nv - 12, SLOT)):
+        want = _free_block(parts)
+        got = o.M[dof:dof + 6, dof:dof + 6]
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+        assert np.abs(eb.mass_diag[0, dof:dof + 6] - np.diag(want)).max() <= 1e-6 * np.abs(np.diag(want)).max()
