@@ -24,7 +24,9 @@
 #define AV_NSC 20       // max scalar constraint rows (equality + friction loss + joint limits)
 #define AV_NCAND 64     // broadphase survivors per class
 #define AV_MAX_ENVW 15   // environments (shared-memory slices) per block
+#ifndef AV_MAX_WARPS
 #define AV_MAX_WARPS 16  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
+#endif
 #define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
 #ifndef AV_BULK_PREFETCH
 #define AV_BULK_PREFETCH 0 // 1: TMA bulk prefetch of contact blocks in the solver sweep (measured slower, see avsim_solve.cuh)
