@@ -25,7 +25,7 @@
 #define AV_NCAND 64     // broadphase survivors per class
 #define AV_MAX_ENVW 15   // environments (shared-memory slices) per block
 #ifndef AV_MAX_WARPS
-#define AV_MAX_WARPS 16  // warps (= environments) per block of the step kernel: 14 x 16 KB slices fill an SM's shared memory
+#define AV_MAX_WARPS 16  // warps per block of the step kernel (16 x 32 x 128 registers = the register file); AV_MAX_ENVW of them own a slice
 #endif
 #define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
 #ifndef AV_BULK_PREFETCH
