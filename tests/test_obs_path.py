@@ -46,10 +46,24 @@ int main() { int bad = 0; for (int v = 0; v < 256; v++) { volatile float a = (fl
     assert np.array_equal((v.astype(np.float32) / np.float32(255)), (torch.from_numpy(v).float() / 255).numpy())
 
 
-def test_observation_modules_do_not_touch_the_oracle():
-    for f in ("observation.py", "replay.py"):
-        text = open(os.path.join(ROOT, "av_aloha_b200", f)).read()
-        assert "import oracle" not in text and "from oracle" not in text
+def test_product_package_never_touches_the_oracle_and_has_no_cpu_fallback():
+    """The oracle is test infrastructure: nothing under av_aloha_b200/ may import, load or execute it, and the C-ABI loader
+    must fail loudly -- not fall back -- when the CUDA library is missing."""
+    import re
+    pkg = os.path.join(ROOT, "av_aloha_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert "libavsim_oracle" not in text and "oracle/_ref" not in text, f
+    from av_aloha_b200 import capi
+    saved, capi._lib, capi.LIB_PATH = (capi._lib, capi.LIB_PATH), None, os.path.join(pkg, "csrc", "no_such_library.so")
+    try:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            capi.load_library()
+    finally:
+        capi._lib, capi.LIB_PATH = saved
 
 
 # ------------------------------------------------------------------------------------------------------------ GPU
