@@ -11,6 +11,7 @@ F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xco
 for w in 18 20; do
     [ -f $CS/libavsim_w$w.so ] || (cd $CS && nvcc $F -DAV_MAX_WARPS=$w -o libavsim_w$w.so avsim_api.cu)
 done
+echo "== IK kernels"; python tools/ik_bench.py
 echo "== default library"; python tools/variant_bench.py 4096 8 16:1:2:11,16:1:1:11
 echo "== AVSIM_KEY=0"; AVSIM_KEY=0 python tools/variant_bench.py 4096 8 16:1:2:11
 for w in 18 20; do
