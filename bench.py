@@ -326,6 +326,8 @@ def run_gpu(args):
                                    f"auto-reset inside the step", "batch_per_gpu": B, "nsubsteps": 20,
                        "solver_iters": args.solver_iters, "noslip_iters": 3,
                        "warmstart": "force cache" if args.warmstart == 2 else "qacc map", "parallelism": f"env-sharded x{world}",
+                       "kernel_shape": "1 block/SM of 16 warps in lockstep: 11 own an environment slice (11.8 KB), 5 helper warps "
+                                       "pull pooled narrowphase items (library defaults; AVSIM_WARPS / AVSIM_ENVW override)",
                        "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
                        "timing": "sum of per-step CUDA event pairs on the launching stream, max over ranks"},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(B * model.njoints * 4),
