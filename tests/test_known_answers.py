@@ -202,3 +202,81 @@ def test_free_body_mass_blocks_match_the_mjcf_numbers(slot_model_path):
         got = o.M[dof:dof + 6, dof:dof + 6]
         assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
         assert np.abs(eb.mass_diag[0, dof:dof + 6] - np.diag(want)).max() <= 1e-6 * np.abs(np.diag(want)).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Principle of virtual work: at zero velocity the bias force of the recursive Newton-Euler pass is the gradient of the
+# potential energy U(q) = sum_b m_b g z_com,b(q).  U comes from the KINEMATICS stage (body poses) and the model's masses /
+# centre-of-mass offsets; the bias from the RNE stage -- two separate code paths that only agree when the spatial
+# transforms, the joint axes (cdof) and the inertial frames are all right.  23 hinge / slide joints of the three arms.
+def _quat_rot(q, v):
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    return R @ v
+
+
+def _potential_gradient(o, avm, q0, nj, d=1e-6):
+    def U(q):
+        o.qpos[:] = q
+        o.qvel[:] = 0
+        o.forward()
+        return sum(avm["body_mass"][b] * 9.81 * (o.xpos[b] + _quat_rot(o.xquat[b], avm["body_ipos"][b]))[2]
+                   for b in range(1, o.model.nbody))
+    g = np.zeros(nj)
+    for i in range(nj):
+        qp, qm = q0.copy(), q0.copy()
+        qp[i] += d
+        qm[i] -= d
+        g[i] = (U(qp) - U(qm)) / (2 * d)
+    return g
+
+
+@pytest.fixture(scope="module")
+def virtual_work(slot_model_path):
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleEnv, OracleModel
+    avm = model_io.load_avm(slot_model_path)
+    o = OracleEnv(OracleModel(slot_model_path))
+    o.reset(free_pos=np.array([[0, 0.12, 0.3], [0.02, -0.05, 0.5]]))
+    nj = 23                                                   # hinge / slide joints: qpos index == dof index
+    assert (avm["jnt_type"][:nj] != 0).all() and (avm["jnt_qposadr"][:nj] == np.arange(nj)).all()
+    q0 = o.qpos.copy()
+    q0[:nj] += np.random.default_rng(0).normal(0, 0.2, nj)
+    grad = _potential_gradient(o, avm, q0, nj)
+    o.qpos[:] = q0
+    o.qvel[:] = 0
+    o.forward()
+    return q0, grad, o.qfrc_bias[:nj].copy(), o.ctrl.copy(), nj
+
+
+def test_oracle_bias_force_is_the_potential_gradient(virtual_work):
+    q0, grad, bias, ctrl, nj = virtual_work
+    assert np.abs(bias).max() > 1.0                           # shoulders carry a few N m
+    assert np.abs(bias - grad).max() <= 1e-6
+
+
+def test_kernel_source_bias_force_is_the_potential_gradient(virtual_work, slot_model_path):
+    from tests.emu.emu import EmuBatch
+    q0, grad, bias, ctrl, nj = virtual_work
+    eb = EmuBatch(slot_model_path, 1)
+    eb.reset(REST[None])
+    eb.qpos[0, :], eb.qvel[0, :], eb.ctrl[0, :] = q0.astype(np.float32), 0.0, ctrl.astype(np.float32)
+    eb.forward()
+    assert np.abs(eb.qfrc_bias[0, :nj] - grad).max() <= 1e-4 * np.abs(grad).max()
+
+
+@pytest.mark.gpu
+def test_gpu_bias_force_is_the_potential_gradient(virtual_work, slot_model_path):
+    from av_aloha_b200 import capi
+    q0, grad, bias, ctrl, nj = virtual_work
+    model = capi.Model(slot_model_path, 0)
+    b = capi.Batch(model, 1, seed=0)
+    b.reset(free_pos=REST[None])
+    b.set(capi.QPOS, q0.astype(np.float32)[None])
+    b.set(capi.QVEL, np.zeros((1, model.nv), np.float32))
+    b.forward()
+    got = b.get(capi.QFRC_BIAS).cpu().numpy()[0, :nj]
+    assert np.abs(got - grad).max() <= 1e-4 * np.abs(grad).max()
+    b.close()
