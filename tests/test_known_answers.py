@@ -280,3 +280,70 @@ def test_gpu_bias_force_is_the_potential_gradient(virtual_work, slot_model_path)
     got = b.get(capi.QFRC_BIAS).cpu().numpy()[0, :nj]
     assert np.abs(got - grad).max() <= 1e-4 * np.abs(grad).max()
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Kinetic energy: (1/2) v^T M v must equal the sum over bodies of (1/2) m |v_com|^2 + (1/2) w^T I w (+ the joints' armature),
+# with v_com and w obtained by finite-differencing the KINEMATICS stage's body poses along v.  Pins the composite-rigid-body
+# mass matrix (and the model's inertial frames) against an independent route.  Unit vectors give the diagonal (also
+# checked for the fp32 kernels); random directions give the full quadratic form.
+def _quat_mat(q):
+    return np.stack([_quat_rot(q, e) for e in np.eye(3)], axis=1)
+
+
+def _kinetic_energy_fd(o, avm, q0, v, nj, d=1e-6):
+    def poses(q):
+        o.qpos[:] = q
+        o.qvel[:] = 0
+        o.forward()
+        R = [_quat_mat(o.xquat[b]) for b in range(o.model.nbody)]
+        return [o.xpos[b] + R[b] @ avm["body_ipos"][b] for b in range(o.model.nbody)], R
+    qp, qm = q0.copy(), q0.copy()
+    qp[:nj] += d * v
+    qm[:nj] -= d * v
+    (cp, Rp), (cm, Rm) = poses(qp), poses(qm)
+    T = 0.5 * float(np.sum(avm["dof_armature"][:nj] * v * v))
+    for b in range(1, o.model.nbody):
+        m = avm["body_mass"][b]
+        if m == 0:
+            continue
+        vc = (cp[b] - cm[b]) / (2 * d)
+        S = (Rp[b] @ Rm[b].T - Rm[b] @ Rp[b].T) / (4 * d)      # [w]x to first order
+        w = np.array([S[2, 1], S[0, 2], S[1, 0]])
+        i6 = avm["body_inertia"][b]
+        Ib = np.array([[i6[0], i6[3], i6[4]], [i6[3], i6[1], i6[5]], [i6[4], i6[5], i6[2]]])
+        R0 = _quat_mat(_mid_quat(o, q0, b))
+        T += 0.5 * m * vc @ vc + 0.5 * w @ (R0 @ Ib @ R0.T) @ w
+    return T
+
+
+def _mid_quat(o, q0, b):
+    o.qpos[:] = q0
+    o.qvel[:] = 0
+    o.forward()
+    return o.xquat[b].copy()
+
+
+def test_mass_matrix_reproduces_the_kinetic_energy(virtual_work, slot_model_path):
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleEnv, OracleModel
+    from tests.emu.emu import EmuBatch
+    q0, _, _, ctrl, nj = virtual_work
+    avm = model_io.load_avm(slot_model_path)
+    o = OracleEnv(OracleModel(slot_model_path))
+    o.reset(free_pos=np.array([[0, 0.12, 0.3], [0.02, -0.05, 0.5]]))
+    o.qpos[:] = q0
+    o.forward()
+    M = o.M[:nj, :nj].copy()
+    diag_fd = np.array([2 * _kinetic_energy_fd(o, avm, q0, np.eye(nj)[i], nj) for i in range(nj)])
+    assert np.abs(np.diag(M) - diag_fd).max() <= 1e-6 * np.abs(diag_fd).max()
+    rng = np.random.default_rng(1)
+    for _ in range(4):
+        v = rng.normal(0, 1, nj)
+        T = _kinetic_energy_fd(o, avm, q0, v, nj)
+        assert abs(0.5 * v @ M @ v - T) <= 1e-6 * T
+    eb = EmuBatch(slot_model_path, 1)                         # the CUDA CRB stage (emulated, fp32): diagonal of M
+    eb.reset(REST[None])
+    eb.qpos[0, :], eb.qvel[0, :] = q0.astype(np.float32), 0.0
+    eb.forward()
+    assert np.abs(eb.mass_diag[0, :nj] - diag_fd).max() <= 1e-5 * np.abs(diag_fd).max()
