@@ -347,3 +347,32 @@ def test_mass_matrix_reproduces_the_kinetic_energy(virtual_work, slot_model_path
     eb.qpos[0, :], eb.qvel[0, :] = q0.astype(np.float32), 0.0
     eb.forward()
     assert np.abs(eb.mass_diag[0, :nj] - diag_fd).max() <= 1e-5 * np.abs(diag_fd).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Feasibility of the contact solve in a contact-rich state (the scripted grasp of the bench workload, 20 contacts, all condim 6
+# with elliptic cones, impratio 100): every normal force is non-negative and every friction force lies inside its elliptic cone
+# sum_i (f_i / mu_i)^2 <= f_n^2 -- a property of the solution the constraint solver must return whatever its path to it.
+def test_oracle_contact_forces_are_cone_feasible(slot_model_path):
+    from av_aloha_b200 import workload
+    from oracle.oracle import OracleEnv, OracleModel
+    obj = workload.sample_object_positions(5, 11)
+    acts = workload.slot_insertion_script(300, obj, 11)
+    o = OracleEnv(OracleModel(slot_model_path))
+    o.set_options(max_iter=100, tol=1e-10, warmstart=1)
+    o.reset(free_pos=obj[0])
+    for t in range(215):
+        o.step(acts[t, 0].astype(np.float64))
+    o.forward()
+    C, f = o.contacts(), o.efc_force
+    live = [c for c in C if not int(c[16])]
+    r = o.nefc - sum(int(c[15]) for c in live)                 # contact rows follow the scalar rows
+    active = 0
+    for c in live:
+        d = int(c[15])
+        fc, mu = f[r:r + d], c[17:17 + d - 1]
+        assert fc[0] >= -1e-12
+        assert np.sqrt(np.sum((fc[1:] / mu) ** 2)) <= fc[0] * (1 + 1e-9) + 1e-12
+        active += fc[0] > 1e-9
+        r += d
+    assert o.ncon >= 12 and active >= 8 and o.reward >= 1     # a real grasp state, not an empty one
