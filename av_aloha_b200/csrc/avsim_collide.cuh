@@ -75,7 +75,7 @@ __device__ inline void collide_sphere_box(const Shape &A, const Shape &B, PrimOu
     }
     V3 nw = mul(B.mat, nl), qw = mul(B.mat, q) + B.pos;
     o.n = 1; o.nrm = nw; o.dist[0] = dist;
-    o.pos[0] = qw + nw * (0.5f * dist);
+    o.pos[0] = qw - nw * (0.5f * dist);   // midpoint of (box surface point, deepest sphere point): |dist| / 2 beyond the surface along nw
 }
 
 // ------------------------------------------------------------------ box-box: 15-axis SAT + face clipping / edge-edge

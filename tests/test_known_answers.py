@@ -376,3 +376,72 @@ def test_oracle_contact_forces_are_cone_feasible(slot_model_path):
         active += fc[0] > 1e-9
         r += d
     assert o.ncon >= 12 and active >= 8 and o.reward >= 1     # a real grasp state, not an empty one
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Narrowphase closed forms (MuJoCo's conventions: dist = signed gap, normal from geom1 to geom2, position = midpoint between the
+# two surfaces).  Table top at z = top; the stick box (half sizes 0.17 x 0.013 x 0.02) pushed `pen` into it gives four contacts at
+# its bottom corners; a finger-pad sphere (r = 0.6 mm) gives one below its centre.  The sphere case caught a sign error in
+# round 1: the position was |dist| / 2 ABOVE the box surface instead of below it.
+def test_narrowphase_closed_forms(slot_model_path):
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleModel
+    avm = model_io.load_avm(slot_model_path)
+    names = model_io.load_names("slot_insertion", 3)["geom"]
+    om = OracleModel(slot_model_path)
+    gt, gs, gp = names.index("table"), names.index("stick"), names.index("left_left_g0")
+    tpos, eye = avm["geom_pos"][gt], np.eye(3)
+    top = tpos[2] + avm["geom_size"][gt][2]
+    pen, half = 1e-3, avm["geom_size"][gs]
+    for yaw in (0.0, 0.5):
+        c, s = np.cos(yaw), np.sin(yaw)
+        Rz = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+        centre = np.array([0.05, -0.03, top + half[2] - pen])
+        out = om.collide_pair(gt, tpos, eye, gs, centre, Rz)
+        assert len(out) == 4
+        corners = np.array([centre + Rz @ (np.array([sx, sy, -1.0]) * half) for sx in (1, -1) for sy in (1, -1)])
+        for row in out:
+            assert abs(row[0] + pen) <= 1e-12 and np.abs(row[4:7] - [0, 0, 1]).max() <= 1e-12      # dist, normal table -> stick
+            assert abs(row[3] - (top - pen / 2)) <= 1e-12                                           # midpoint height
+            assert np.abs(corners[:, :2] - row[1:3]).sum(axis=1).min() <= 1e-12                     # at a bottom corner
+        assert len({tuple(np.round(r[1:3], 9)) for r in out}) == 4
+    r, pen = float(avm["geom_size"][gp][0]), 2e-4
+    assert avm["geom_type"][gp] == 2 and r == pytest.approx(6e-4)
+    for g1, g2, sign in ((gt, gp, 1.0), (gp, gt, -1.0)):                                            # both argument orders
+        sc = np.array([0.1, 0.1, top + r - pen])
+        args = (g1, tpos, eye, g2, sc, eye) if g1 == gt else (g1, sc, eye, g2, tpos, eye)
+        out = om.collide_pair(*args)
+        assert len(out) == 1
+        assert abs(out[0][0] + pen) <= 1e-12 and np.abs(out[0][4:7] - [0, 0, sign]).max() <= 1e-12
+        assert np.abs(out[0][1:4] - [0.1, 0.1, top - pen / 2]).max() <= 1e-12                        # midpoint, BELOW the table top
+    assert len(om.collide_pair(gt, tpos, eye, gp, np.array([0.1, 0.1, top + r + 1e-6]), eye)) == 0  # separated: no contact
+
+
+def test_kernel_source_contact_records_match_the_oracle_in_a_grasp_state(slot_model_path):
+    """19 contacts incl. five finger-pad spheres on the stick and two pad-pad pairs: the CUDA narrowphase (emulated, fp32) returns
+    the oracle's contact list -- same geoms in the same order, gaps and positions to 1e-6 m, normals to 1e-3."""
+    from av_aloha_b200 import model_io, workload
+    from oracle.oracle import OracleEnv, OracleModel
+    from tests.emu.emu import EmuBatch
+    avm = model_io.load_avm(slot_model_path)
+    obj = workload.sample_object_positions(5, 11)
+    acts = workload.slot_insertion_script(300, obj, 11)
+    o = OracleEnv(OracleModel(slot_model_path))
+    o.set_options(max_iter=8, tol=0.0, warmstart=2)
+    o.reset(free_pos=obj[0])
+    for t in range(215):
+        o.step(acts[t, 0].astype(np.float64))
+    o.forward()
+    C = o.contacts()
+    spheres = [c for c in C if 2 in (avm["geom_type"][int(c[13])], avm["geom_type"][int(c[14])])]
+    assert len(C) >= 15 and len(spheres) >= 5
+    eb = EmuBatch(slot_model_path, 1)
+    eb.set_options(8)
+    eb.reset(obj[0][None])
+    eb.qpos[0, :], eb.qvel[0, :], eb.ctrl[0, :] = o.qpos.astype(np.float32), o.qvel.astype(np.float32), o.ctrl.astype(np.float32)
+    eb.forward()
+    assert eb.ncon[0] == len(C)
+    ec = eb.contacts[0].reshape(64, 16)[: len(C)]
+    assert (ec[:, 7:9] == C[:, 13:15]).all()
+    assert np.abs(ec[:, 0] - C[:, 0]).max() <= 1e-6 and np.abs(ec[:, 1:4] - C[:, 1:4]).max() <= 1e-6
+    assert np.abs(ec[:, 4:7] - C[:, 4:7]).max() <= 1e-3
