@@ -445,3 +445,36 @@ def test_kernel_source_contact_records_match_the_oracle_in_a_grasp_state(slot_mo
     assert (ec[:, 7:9] == C[:, 13:15]).all()
     assert np.abs(ec[:, 0] - C[:, 0]).max() <= 1e-6 and np.abs(ec[:, 1:4] - C[:, 1:4]).max() <= 1e-6
     assert np.abs(ec[:, 4:7] - C[:, 4:7]).max() <= 1e-3
+
+
+def test_mpr_closed_form_cylinder_on_table():
+    """The convex (MPR) path on a shape with a closed form: the HookPackage hook cylinder (r = 6 mm, half height 0.1) standing on
+    the table, pushed `pen` into it -> gap -pen, normal +z, midpoint position; with multiccd four more points on the rim
+    (the two shapes are counter-rotated by 1e-3 rad about the first contact point: depth changes by at most 2e-3 x the lever, <= 2 r); lying on its side: a line contact, multiccd finds both ends."""
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleModel
+    path = model_io.model_path("hook_package", 2)
+    avm, names = model_io.load_avm(path), model_io.load_names("hook_package", 2)["geom"]
+    om = OracleModel(path)
+    gt, gh = names.index("table"), names.index("hook")
+    assert avm["geom_type"][gh] == 5
+    r, hh = (float(x) for x in avm["geom_size"][gh][:2])
+    tpos, eye, pen = avm["geom_pos"][gt], np.eye(3), 1e-3
+    top = tpos[2] + avm["geom_size"][gt][2]
+    centre = np.array([0.1, 0.05, top + hh - pen])
+    one = om.collide_pair(gt, tpos, eye, gh, centre, eye, multiccd=0)
+    assert len(one) == 1
+    assert abs(one[0][0] + pen) <= 1e-6 and np.abs(one[0][4:7] - [0, 0, 1]).max() <= 1e-6
+    assert abs(one[0][3] - (top - pen / 2)) <= 1e-6 and np.linalg.norm(one[0][1:3] - centre[:2]) <= r + 1e-6
+    five = om.collide_pair(gt, tpos, eye, gh, centre, eye, multiccd=1)
+    assert len(five) == 5 and np.array_equal(five[0], one[0])
+    for row in five[1:]:
+        assert abs(np.linalg.norm(row[1:3] - centre[:2]) - r) <= 1e-4                 # on the rim
+        assert abs(row[0] + pen) <= 2e-3 * 2 * r + 1e-6 and np.abs(row[4:7] - [0, 0, 1]).max() <= 1e-6
+    Rx = np.array([[1, 0, 0], [0, 0, -1], [0, 1, 0.0]])                                # axis along world -y
+    side = om.collide_pair(gt, tpos, eye, gh, np.array([0.1, 0.05, top + r - pen]), Rx, multiccd=1)
+    assert len(side) >= 3 and abs(side[0][0] + pen) <= 1e-6
+    ys = sorted(row[2] - 0.05 for row in side)
+    assert ys[0] <= -0.9 * hh and ys[-1] >= 0.9 * hh                                     # both ends of the line contact
+    for row in side:
+        assert abs(row[1] - 0.1) <= 1e-4 and np.abs(row[4:7] - [0, 0, 1]).max() <= 1e-5 and abs(row[0] + pen) <= 2e-3 * 2 * hh + 1e-6
