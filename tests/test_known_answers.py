@@ -478,3 +478,22 @@ def test_mpr_closed_form_cylinder_on_table():
     assert ys[0] <= -0.9 * hh and ys[-1] >= 0.9 * hh                                     # both ends of the line contact
     for row in side:
         assert abs(row[1] - 0.1) <= 1e-4 and np.abs(row[4:7] - [0, 0, 1]).max() <= 1e-5 and abs(row[0] + pen) <= 2e-3 * 2 * hh + 1e-6
+
+
+def test_narrowphase_closed_form_sphere_sphere(slot_model_path):
+    """two finger-pad spheres (r = 0.6 mm) overlapping by `pen` along an oblique axis: gap -pen, normal along the centre line from
+    geom1 to geom2, position at the midpoint of the overlap"""
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleModel
+    avm, names = model_io.load_avm(slot_model_path), model_io.load_names("slot_insertion", 3)["geom"]
+    om = OracleModel(slot_model_path)
+    g1, g2 = names.index("left_left_g0"), names.index("left_left_g1")
+    r1, r2, pen, eye = float(avm["geom_size"][g1][0]), float(avm["geom_size"][g2][0]), 1e-4, np.eye(3)
+    n = np.array([1.0, 2.0, -2.0]) / 3.0
+    p1 = np.array([0.2, -0.1, 0.3])
+    p2 = p1 + n * (r1 + r2 - pen)
+    out = om.collide_pair(g1, p1, eye, g2, p2, eye)
+    assert len(out) == 1
+    assert abs(out[0][0] + pen) <= 1e-12 and np.abs(out[0][4:7] - n).max() <= 1e-12
+    assert np.abs(out[0][1:4] - (p1 + n * (r1 - pen / 2))).max() <= 1e-12
+    assert len(om.collide_pair(g1, p1, eye, g2, p1 + n * (r1 + r2 + 1e-7), eye)) == 0
