@@ -497,3 +497,31 @@ def test_narrowphase_closed_form_sphere_sphere(slot_model_path):
     assert abs(out[0][0] + pen) <= 1e-12 and np.abs(out[0][4:7] - n).max() <= 1e-12
     assert np.abs(out[0][1:4] - (p1 + n * (r1 - pen / 2))).max() <= 1e-12
     assert len(om.collide_pair(g1, p1, eye, g2, p1 + n * (r1 + r2 + 1e-7), eye)) == 0
+
+
+def test_narrowphase_closed_form_tilted_box(slot_model_path):
+    """the stick box rolled / pitched / both over the table: an edge gives two contacts at its ends, a corner gives one; gap = the
+    depth of the lowest corners, normal +z, position at the midpoint between that corner and the table top"""
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleModel
+    avm, names = model_io.load_avm(slot_model_path), model_io.load_names("slot_insertion", 3)["geom"]
+    om = OracleModel(slot_model_path)
+    gt, gs = names.index("table"), names.index("stick")
+    tpos, eye, half, pen = avm["geom_pos"][gt], np.eye(3), avm["geom_size"][gs], 1e-3
+    top = tpos[2] + avm["geom_size"][gt][2]
+
+    def rot(axis, deg):
+        c, s = np.cos(np.deg2rad(deg)), np.sin(np.deg2rad(deg))
+        return np.array([[1, 0, 0], [0, c, -s], [0, s, c]]) if axis == "x" else np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+    for R, npts in ((rot("x", 30), 2), (rot("y", 10), 2), (rot("x", 30) @ rot("y", 10), 1)):
+        corners = np.array([R @ (np.array([sx, sy, sz]) * half) for sx in (1, -1) for sy in (1, -1) for sz in (1, -1)])
+        low = -corners[:, 2].min()
+        centre = np.array([0.05, -0.03, top + low - pen])
+        lowest = centre + corners[np.abs(corners[:, 2] + low) <= 1e-12]          # the corners that touch first
+        assert len(lowest) == npts
+        out = om.collide_pair(gt, tpos, eye, gs, centre, R)
+        assert len(out) == npts
+        for row in out:
+            assert abs(row[0] + pen) <= 1e-9 and np.abs(row[4:7] - [0, 0, 1]).max() <= 1e-9 and abs(row[3] - (top - pen / 2)) <= 1e-9
+            assert np.abs(lowest[:, :2] - row[1:3]).sum(axis=1).min() <= 1e-9
