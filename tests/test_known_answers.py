@@ -525,3 +525,38 @@ def test_narrowphase_closed_form_tilted_box(slot_model_path):
         for row in out:
             assert abs(row[0] + pen) <= 1e-9 and np.abs(row[4:7] - [0, 0, 1]).max() <= 1e-9 and abs(row[3] - (top - pen / 2)) <= 1e-9
             assert np.abs(lowest[:, :2] - row[1:3]).sum(axis=1).min() <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Position actuators (reference assets/joint_position_actuators.xml + aloha_sim.xml:33-48, 95): force =
+# clip(kp (clip(ctrl, ctrlrange) - q) - kv qdot, actuatorfrcrange).  Commands far beyond the pose saturate first the ctrl range
+# (wrist_rotate: 10.4 x 3.14158 = 32.67 N m < 35; gripper: 0.037 is the open pose, force 0) and then the joint's force range
+# (35 / 144 / 59 / 22 N m).  The oracle exposes qfrc_actuator; the CUDA smooth stage is checked through qacc_smooth at that state.
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_actuator_force_saturation_closed_form(slot_model_path, sign):
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleEnv, OracleModel
+    from tests.emu.emu import EmuBatch
+    avm = model_io.load_avm(slot_model_path)
+    o = OracleEnv(OracleModel(slot_model_path))
+    o.reset(free_pos=REST)
+    rng = np.random.default_rng(3)
+    o.qvel[:23] = rng.normal(0, 0.3, 23)
+    o.ctrl[:] = o.ctrl + sign * 10.0
+    ctrl_cmd = o.ctrl.copy()
+    o.forward()
+    kp, kv, qa, da = avm["act_kp"], avm["act_kv"], avm["act_qadr"], avm["act_dof"]
+    u = np.clip(ctrl_cmd, avm["act_ctrl_lo"], avm["act_ctrl_hi"])
+    want = np.zeros(o.model.nv)
+    want[da] = kp * (u - o.qpos[qa]) - kv * o.qvel[da]
+    lim = avm["dof_frc_limited"].astype(bool)
+    want[lim] = np.clip(want[lim], avm["dof_frc_lo"][lim], avm["dof_frc_hi"][lim])
+    assert np.abs(o.qfrc_actuator - want).max() <= 1e-9
+    sat = np.isclose(np.abs(want[da]), avm["dof_frc_hi"][da])
+    assert sat.sum() >= 12 and abs(abs(want[da[5]]) - 10.4 * 3.14158) <= 0.3 * 10.4 + 1e-9      # force range and ctrl range both bite
+    eb = EmuBatch(slot_model_path, 1)
+    eb.reset(REST[None])
+    eb.qvel[0, :], eb.ctrl[0, :] = o.qvel.astype(np.float32), ctrl_cmd.astype(np.float32)
+    eb.forward()
+    scale = np.abs(o.qacc_smooth).max()
+    assert np.abs(eb.qacc_smooth[0] - o.qacc_smooth).max() <= 1e-4 * scale
