@@ -560,3 +560,35 @@ def test_actuator_force_saturation_closed_form(slot_model_path, sign):
     eb.forward()
     scale = np.abs(o.qacc_smooth).max()
     assert np.abs(eb.qacc_smooth[0] - o.qacc_smooth).max() <= 1e-4 * scale
+
+
+def test_oracle_friction_loss_is_dry_friction_and_fingers_stay_coupled(slot_model_path):
+    """Scalar constraint rows during the reach of the scripted policy: the two finger-coupling equalities (J = [1, -1]) keep each
+    gripper's fingers together, and the six friction-loss rows (shoulder 2.0, elbow 1.15 N m, aloha_sim.xml:40,44) behave as dry
+    friction: |f| <= frictionloss always, and f = -frictionloss sign(qdot) on every joint that is moving."""
+    from av_aloha_b200 import model_io, workload
+    from oracle.oracle import OracleEnv, OracleModel
+    avm = model_io.load_avm(slot_model_path)
+    obj = workload.sample_object_positions(5, 11)
+    acts = workload.slot_insertion_script(300, obj, 11)
+    o = OracleEnv(OracleModel(slot_model_path))
+    o.set_options(max_iter=100, tol=1e-10, warmstart=1)
+    o.reset(free_pos=obj[0])
+    for k in range(60):
+        o.step(acts[k, 0].astype(np.float64))
+    o.forward()
+    nsc = o.nefc - sum(int(c[15]) for c in o.contacts() if not int(c[16]))
+    J, f = o.efc_J[:nsc], o.efc_force[:nsc]
+    fl_dofs = np.nonzero(avm["dof_frictionloss"])[0]
+    assert nsc >= 2 + len(fl_dofs) and list(fl_dofs) == [1, 2, 9, 10, 17, 18]
+    for r, (a, b) in enumerate(((6, 7), (14, 15))):                      # finger coupling rows
+        assert np.array_equal(np.nonzero(J[r])[0], [a, b]) and np.allclose(J[r][[a, b]], [1, -1])
+        assert abs(o.qpos[a] - o.qpos[b]) <= 2e-4                        # soft equality: the fingers stay within 0.2 mm
+    moving = 0
+    for r, d in enumerate(fl_dofs, start=2):
+        fl = avm["dof_frictionloss"][d]
+        assert np.array_equal(np.nonzero(J[r])[0], [d]) and abs(f[r]) <= fl + 1e-9
+        if abs(o.qvel[d]) > 1e-2:
+            moving += 1
+            assert abs(f[r] + fl * np.sign(o.qvel[d])) <= 1e-6
+    assert moving >= 3
