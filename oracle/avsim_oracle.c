@@ -1116,6 +1116,16 @@ int ora_ncon(const ora_data *d) { return d->ncon; }
 int ora_nefc(const ora_data *d) { return d->nefc; }
 int ora_solver_iters(const ora_data *d) { return d->solver_iters; }
 int ora_reward(const ora_data *d) { return d->reward; }
+/* test hook: the staged reward of an explicit contact list (geom id pairs) and latch state; clobbers the contact list */
+int ora_reward_from_pairs(ora_data *d, const int *pairs, int n, int latch_in, int *latch_out) {
+    if (n > NCON_MAX) return -1;
+    d->ncon = n;
+    for (int c = 0; c < n; c++) { d->con[c].geom1 = pairs[2 * c]; d->con[c].geom2 = pairs[2 * c + 1]; }
+    d->latch = latch_in;
+    int r = stage_reward(d);
+    if (latch_out) *latch_out = d->latch;
+    return r;
+}
 int *ora_latch(ora_data *d) { return &d->latch; }
 double *ora_efc_force(ora_data *d) { return d->efc_force; }
 double *ora_efc_aref(ora_data *d) { return d->efc_aref; }

@@ -161,6 +161,15 @@ class OracleEnv:
             lib().ora_contact_get(self.ptr, c, _dp(out[c]))
         return out
 
+    def reward_from_pairs(self, pairs, latch=0):
+        """(reward, latch) of an explicit contact list [(geom1, geom2), ...] -- test hook for the reward tables"""
+        arr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1))
+        out = C.c_int(0)
+        fn = lib().ora_reward_from_pairs
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int)]
+        r = fn(self.ptr, arr.ctypes.data_as(C.POINTER(C.c_int)), len(arr) // 2, int(latch), C.byref(out))
+        return int(r), int(out.value)
+
     def set_options(self, max_iter=3000, tol=1e-14, noslip_iter=-1, multiccd=-1, warmstart=1):
         lib().ora_set_options(self.ptr, max_iter, tol, noslip_iter, multiccd, warmstart)
 

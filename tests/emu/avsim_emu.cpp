@@ -120,6 +120,25 @@ void emu_reset(EmuBatch *b, const float *free_pos) {
         emu::run_block(blk, nb, [&]() { avsim_reset_kernel(b->pk.dm, b->st, nullptr, free_pos, AV_HOME); });
     emu_forward(b);
 }
+// test hook: stage_reward (the CUDA source) on an explicit contact list of geom id pairs; returns the reward, writes the latch back
+int emu_reward_from_pairs(EmuBatch *b, const int *pairs, int n, int latch_in, int *latch_out) {
+    if (n > AV_NCON) return -1;
+    int reward = -1, latch = latch_in;
+    emu::run_block(0, 1, [&]() {
+        EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
+        int lane = threadIdx.x;
+        if (lane == 0) {
+            S.ncon = n;
+            for (int c = 0; c < n; c++) S.c_info[c] = pairs[2 * c] | (pairs[2 * c + 1] << 8) | (3 << 16);
+        }
+        __syncwarp();
+        int l = latch_in;
+        int r = stage_reward(b->pk.dm, S, lane, l);
+        if (lane == 0) { reward = r; latch = l; }
+    });
+    if (latch_out) *latch_out = latch;
+    return reward;
+}
 // IK kernels (thread per problem): arm 0 left, 1 right, 2 middle
 void emu_fk(EmuBatch *b, int arm, const float *q, int n, float *T_out) {
     int nb = (n + 31) / 32;

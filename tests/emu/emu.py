@@ -89,6 +89,16 @@ class EmuBatch:
         lib().emu_reset(self.ptr, fp)
 
 
+def emu_reward_from_pairs(eb, pairs, latch=0):
+    """(reward, latch) of stage_reward (CUDA source, emulated) on an explicit contact list [(geom1, geom2), ...]"""
+    arr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1))
+    out = C.c_int(0)
+    fn = lib().emu_reward_from_pairs
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    r = fn(eb.ptr, arr.ctypes.data_as(C.POINTER(C.c_int)), len(arr) // 2, int(latch), C.byref(out))
+    return int(r), int(out.value)
+
+
 # ---- IK kernels through the emulator (same parameter structs as the C-ABI)
 def _ik_setup():
     from av_aloha_b200.capi import DiffIKParams, GradIKParams
