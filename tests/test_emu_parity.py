@@ -112,3 +112,26 @@ def test_force_cache_warm_start_matches_oracle(ctx):
         r = o.step(act)
     assert eb.ncon[0] == o.ncon and eb.reward[0] == r and eb.status[0] == 0
     assert np.abs(eb.qpos[0] - o.qpos).max() <= 2e-4
+
+
+def test_action_to_ctrl_and_agent_pos_follow_the_reference_maps(ctx):
+    """reference env.py:156-161 (gripper ctrlrange affine maps), 169-178 (agent_pos = L[6 joints + normalised gripper], R, M) and
+    204-215 (ctrl write): a zero-substep env.step through the CUDA source shows exactly these maps.  The observed finger is
+    left_left_finger for the left arm but right_RIGHT_finger for the right arm (constants.py:29-46), while both gripper
+    actuators drive the *_left_finger joint (joint_position_actuators.xml:9,17)."""
+    EmuBatch, om, OracleEnv, path = ctx
+    lo, hi = 0.002, 0.037                                   # aloha_sim.xml:95 ctrlrange of the gripper actuators
+    rng = np.random.default_rng(9)
+    eb = EmuBatch(path, 1)
+    eb.reset(np.array([[[0.0, 0.12, 0.0], [0.02, -0.05, 0.0]]]))
+    a = rng.uniform(-0.5, 0.5, 21).astype(np.float32)
+    a[6], a[13] = 0.3, 0.8                                  # 1 = open, 0 = closed
+    eb.qpos[0, 6], eb.qpos[0, 15] = 0.010, 0.030            # the observed finger joints, somewhere inside their range
+    eb.step(a[None], 0)
+    want_ctrl = a.astype(np.float64).copy()
+    want_ctrl[6], want_ctrl[13] = 0.3 * (hi - lo) + lo, np.float32(0.8) * (hi - lo) + lo
+    assert np.abs(eb.ctrl[0] - want_ctrl).max() <= 1e-7
+    q = eb.qpos[0].astype(np.float64)
+    want_obs = np.concatenate([q[0:6], [(q[6] - lo) / (hi - lo)], q[8:14], [(q[15] - lo) / (hi - lo)], q[16:23]])
+    assert np.abs(eb.agent_pos[0] - want_obs).max() <= 1e-6
+    assert abs(eb.agent_pos[0, 6] - (0.010 - lo) / (hi - lo)) <= 1e-6 and abs(eb.agent_pos[0, 13] - 0.8) <= 1e-6
