@@ -121,3 +121,22 @@ def test_oracle_is_thread_safe(slot_model_path):
         threaded = list(ex.map(run, range(6)))
     for a, b in zip(serial, threaded):
         assert np.array_equal(a, b)
+
+
+def test_ik_zero_pose_geometry_matches_an_independent_walk_of_the_mjcf():
+    """ik_w0 / ik_p0 / ik_site0 of the compiled model -- what the reference's create_fk_fn reads from mujoco at q = 0
+    (kinematics.py:9-15) and what the IK goldens were generated from -- against tests/golden/ik_geometry.json, computed from
+    aloha_sim.xml by a separate XML walk (tools/gen_ik_geometry_golden.py: xml.etree + scipy, no code shared with the compiler)."""
+    import json
+    from av_aloha_b200 import model_io
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ik_geometry.json")))
+    for task, arms in (("slot_insertion", 3), ("hook_package", 3), ("insert_peg", 3)):
+        avm = model_io.load_avm(model_io.model_path(task, arms))
+        for a, arm in enumerate(("left", "right", "middle")):
+            n = len(gold[arm]["joints"])
+            assert int(avm["ik_ndof"][a]) == n == (6, 6, 7)[a]
+            assert np.abs(np.array(gold[arm]["w0"]) - avm["ik_w0"][a, :n]).max() <= 1e-12
+            assert np.abs(np.array(gold[arm]["p0"]) - avm["ik_p0"][a, :n]).max() <= 1e-12
+            assert np.abs(np.array(gold[arm]["site0"]) - avm["ik_site0"][a]).max() <= 1e-12
+    w = np.array(gold["left"]["w0"])
+    assert np.allclose(np.linalg.norm(w, axis=1), 1.0) and np.allclose(np.abs(w[0]), [0, 0, 1])      # the waist turns about z

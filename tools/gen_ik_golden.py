@@ -8,7 +8,8 @@ The reference files data_collection_scripts/{transform_utils,kinematics,diff_ik,
                                 compiler derived from aloha_sim.xml (arrays ik_w0, ik_p0, ik_site0, ik_range of the
                                 compiled .avm).  So the golden vectors pin the IK *algorithms* (PoE FK, space Jacobian,
                                 damped least squares + null space, finite-difference descent); the q = 0 geometry is
-                                pinned separately by tests/test_model_compile.py against the XML itself.
+                                pinned separately against the XML itself: tests/test_host_logic.py compares it with an independent walk
+                                of aloha_sim.xml (tools/gen_ik_geometry_golden.py -> tests/golden/ik_geometry.json).
 The reference cannot travel to the GPU box, so the outputs are committed as a small fixture.
 
     python tools/gen_ik_golden.py           # ~2 min (numba cold JIT of the reference closures)
