@@ -140,3 +140,18 @@ def test_ik_zero_pose_geometry_matches_an_independent_walk_of_the_mjcf():
             assert np.abs(np.array(gold[arm]["site0"]) - avm["ik_site0"][a]).max() <= 1e-12
     w = np.array(gold["left"]["w0"])
     assert np.allclose(np.linalg.norm(w, axis=1), 1.0) and np.allclose(np.abs(w[0]), [0, 0, 1])      # the waist turns about z
+
+
+def test_link_inertials_match_an_independent_walk_of_the_mjcf():
+    """mass, centre of mass and body-frame inertia tensor of the 28 robot links with an explicit <inertial> (aloha_sim.xml:121 ff.;
+    diaginertia rotated by the inertial quat) against the same independent XML walk"""
+    import json
+    from av_aloha_b200 import model_io
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ik_geometry.json")))["inertials"]
+    assert len(gold) == 28
+    for task, arms in (("slot_insertion", 3), ("tube_transfer", 3), ("slot_insertion", 2)):
+        avm, names = model_io.load_avm(model_io.model_path(task, arms)), model_io.load_names(task, arms)["body"]
+        for name, d in gold.items():
+            b = names.index(name)
+            assert abs(avm["body_mass"][b] - d["mass"]) <= 1e-12 and np.abs(avm["body_ipos"][b] - d["ipos"]).max() <= 1e-12
+            assert np.abs(avm["body_inertia"][b] - d["inertia"]).max() <= 1e-12 * max(1.0, np.abs(d["inertia"]).max())

@@ -82,6 +82,18 @@ def main():
 
     walk(root.find("worldbody"), np.eye(3), np.zeros(3), None)
     out = {}
+    # explicit <inertial> elements (aloha_sim.xml:121 ff.): mass, centre of mass and the inertia tensor in the body frame
+    # (diaginertia rotated by the inertial quat); non-normalised quats are normalised as MuJoCo does
+    inertials = {}
+    for b in root.iter("body"):
+        el = b.find("inertial")
+        if el is None:
+            continue
+        R = local_rotation(el)
+        I = R @ np.diag(vec(el.get("diaginertia"), None)) @ R.T
+        inertials[b.get("name")] = {"mass": float(el.get("mass")), "ipos": vec(el.get("pos"), [0, 0, 0]).tolist(),
+                                    "inertia": [I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]]}
+    out["inertials"] = inertials
     for arm, (names, site) in ARMS.items():
         out[arm] = {"joints": names, "site": site, "w0": [joints[n][0].tolist() for n in names],
                     "p0": [joints[n][1].tolist() for n in names], "site0": sites[site].tolist()}
