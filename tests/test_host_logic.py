@@ -155,3 +155,46 @@ def test_link_inertials_match_an_independent_walk_of_the_mjcf():
             b = names.index(name)
             assert abs(avm["body_mass"][b] - d["mass"]) <= 1e-12 and np.abs(avm["body_ipos"][b] - d["ipos"]).max() <= 1e-12
             assert np.abs(avm["body_inertia"][b] - d["inertia"]).max() <= 1e-12 * max(1.0, np.abs(d["inertia"]).max())
+
+
+def test_compiled_hulls_match_the_stl_support_functions():
+    """Every collision hull against support values computed straight from the reference's STL vertices by an independent reader
+    (tools/gen_hull_golden.py -> tests/golden/hull_support.json; 48 Fibonacci directions).  Hull vertices are stored relative to
+    the hull centroid, so widths h(d) + h(-d) are compared: exact hulls to 2e-9 m (float32 STL coordinates), the thinned /
+    merged fine hulls from inside by at most 0.15 mm.  The absolute placement is checked through
+    the compiled geom pose of the finger geoms, whose XML pose (aloha_sim.xml:179, 192) is restated here."""
+    import json
+    from av_aloha_b200 import model_io
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "hull_support.json")))
+    n = 48
+    k = np.arange(n) + 0.5
+    phi, z = np.pi * (1 + 5 ** 0.5) * k, 1 - 2 * k / n
+    D = np.stack([np.sqrt(1 - z * z) * np.cos(phi), np.sqrt(1 - z * z) * np.sin(phi), z], axis=1)
+    avm, names = model_io.load_avm(model_io.model_path("slot_insertion", 3)), model_io.load_names("slot_insertion", 3)
+    assert set(names["hull"]) == set(gold)
+    thinned = 0
+    for h, name in enumerate(names["hull"]):
+        v = avm["hull_vert"][avm["hull_adr"][h]:avm["hull_adr"][h] + avm["hull_num"][h]]
+        proj = v @ D.T
+        err = (proj.max(axis=0) - proj.min(axis=0)) - (np.array(gold[name]["support"]) + np.array(gold[name]["support_neg"]))
+        assert err.max() <= 2e-9 and err.min() >= -1.5e-4, (name, err.min(), err.max())      # never outside the true hull
+        thinned += err.min() < -2e-9
+        assert len(v) <= 642
+    assert thinned <= 6
+
+    def quat_mat(q):                                          # (w, x, y, z), normalised as MuJoCo does
+        w, x, y, z = np.asarray(q, float) / np.linalg.norm(q)
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    for geom, pos, quat in (("left_left_finger", [0.0141637, 0.0211727, 0.06], [1, 1, 1, -1]),
+                            ("left_right_finger", [0.0141637, -0.0211727, 0.0597067], [1, -1, -1, -1])):
+        gi = names["geom"].index(geom)
+        h = int(avm["geom_hull"][gi])
+        v = avm["hull_vert"][avm["hull_adr"][h]:avm["hull_adr"][h] + avm["hull_num"][h]]
+        R, Rc = quat_mat(quat), quat_mat(avm["geom_quat"][gi])
+        Dw = D @ R.T                                          # mesh-frame directions seen from the body frame
+        got = Dw @ avm["geom_pos"][gi] + ((v @ Rc.T) @ Dw.T).max(axis=0)
+        want = Dw @ np.array(pos) + np.array(gold[names["hull"][h]]["support"])
+        assert np.abs(got - want).max() <= 2e-9, geom
