@@ -135,3 +135,22 @@ def test_action_to_ctrl_and_agent_pos_follow_the_reference_maps(ctx):
     want_obs = np.concatenate([q[0:6], [(q[6] - lo) / (hi - lo)], q[8:14], [(q[15] - lo) / (hi - lo)], q[16:23]])
     assert np.abs(eb.agent_pos[0] - want_obs).max() <= 1e-6
     assert abs(eb.agent_pos[0, 6] - (0.010 - lo) / (hi - lo)) <= 1e-6 and abs(eb.agent_pos[0, 13] - 0.8) <= 1e-6
+
+
+def test_reset_state_follows_the_reference_reset(ctx):
+    """reference env.py:228-244 + constants.py:26-28: arm joints at the home poses, all four fingers at unnorm(1) = 0.037 (the
+    0.02239 of the pose lists is overwritten by the gripper-joint bind that follows), ctrl = home with the gripper entries at
+    0.037, velocities zero; objects where the host put them with identity orientation (env.py:536-537)."""
+    EmuBatch, om, OracleEnv, path = ctx
+    fp = np.array([[[0.03, 0.12, 0.0], [-0.02, -0.05, 0.0]]])
+    eb = EmuBatch(path, 1)
+    eb.qvel[0, :] = 1.0
+    eb.reset(fp)
+    arm, mid = [0, -0.082, 1.06, 0, -0.953, 0], [0, -0.8, 0.8, 0, 0.5, 0, 0]
+    want_q = np.array(arm + [0.037, 0.037] + arm + [0.037, 0.037] + mid)
+    assert np.abs(eb.qpos[0, :23] - want_q).max() <= 1e-7
+    assert np.abs(eb.ctrl[0] - np.array(arm + [0.037] + arm + [0.037] + mid)).max() <= 1e-7
+    assert np.abs(eb.qvel[0]).max() == 0.0
+    assert np.abs(eb.qpos[0, 23:26] - fp[0, 0]).max() <= 1e-7 and np.abs(eb.qpos[0, 26:30] - [1, 0, 0, 0]).max() == 0.0
+    assert np.abs(eb.qpos[0, 30:33] - fp[0, 1]).max() <= 1e-7 and np.abs(eb.qpos[0, 33:37] - [1, 0, 0, 0]).max() == 0.0
+    assert np.abs(eb.agent_pos[0, [6, 13]] - 1.0).max() <= 1e-6 and eb.reward[0] == 0
