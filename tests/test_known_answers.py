@@ -592,3 +592,25 @@ def test_oracle_friction_loss_is_dry_friction_and_fingers_stay_coupled(slot_mode
             moving += 1
             assert abs(f[r] + fl * np.sign(o.qvel[d])) <= 1e-6
     assert moving >= 3
+
+
+def test_contact_parameters_follow_mujocos_mixing_rules(slot_model_path):
+    """contact dimension = max of the two geoms' condim, friction = element-wise max of their (sliding, torsional, rolling)
+    coefficients, expanded to (mu, mu, torsion, roll, roll) -- with the MJCF numbers: the slot rails (friction 0.05,
+    task_slot_insertion.xml:7-8) against the condim-6 `collision`-class table still slide at the table's coefficient."""
+    from av_aloha_b200 import model_io
+    avm, names = model_io.load_avm(slot_model_path), model_io.load_names("slot_insertion", 3)["geom"]
+    o = _settled_oracle(slot_model_path)
+    C = o.contacts()
+    assert len(C) >= 8
+    seen = set()
+    for c in C:
+        g1, g2 = int(c[13]), int(c[14])
+        f = np.maximum(avm["geom_friction"][g1], avm["geom_friction"][g2])
+        assert int(c[15]) == max(int(avm["geom_condim"][g1]), int(avm["geom_condim"][g2]))
+        assert np.abs(c[17:22] - [f[0], f[0], f[1], f[2], f[2]]).max() <= 1e-12
+        seen.add((names[g1], names[g2]))
+    assert ("table", "stick") in seen and ("table", "slot-1") in seen
+    gs, gt = names.index("slot-1"), names.index("table")
+    assert avm["geom_friction"][gs][0] == pytest.approx(0.05) and avm["geom_friction"][gt][0] >= 0.05
+    assert avm["geom_condim"][gt] == 6
