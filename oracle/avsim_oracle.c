@@ -9,7 +9,7 @@
  * PARITY UNPINNED: MuJoCo (mujoco ^3.2.2, gym_guided_vision/pyproject.toml:10) cannot be installed in
  * the build container and the reference tree holds no golden qpos/qvel/contact vectors, so this file
  * restates MuJoCo's *published* pipeline and is validated by closed forms and
- * invariants (tests/test_known_answers.py: free fall + spin, static equilibrium, box inertias, virtual work,
+ * invariants (tests/test_physics_known_answers.py: free fall + spin, static equilibrium, box inertias, virtual work,
  * kinetic energy, cone feasibility, box-box / sphere-box / MPR narrowphase), not against MuJoCo outputs.  Where the algorithm is a free choice
  * (box-box manifold, MPR penetration after libccd, block PGS on the dual), the choice is stated here
  * and the CUDA path (av_aloha_b200/csrc) follows the same statement in fp32, written independently.
