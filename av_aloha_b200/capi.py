@@ -16,15 +16,16 @@ LIB_PATH = os.environ.get("AVSIM_LIB") or os.path.join(_HERE, "csrc", "libavsim.
 
 # avsim_field
 QPOS, QVEL, CTRL, WARMSTART, AGENT_POS, REWARD, SUCCESS, NCON, CONTACTS, STATUS, LATCH, QACC, XPOS, QFRC_BIAS, \
-    QACC_SMOOTH, MASS_DIAG, ENV_CYCLES, FC_KEY, FC_N, FC_VAL = range(20)
+    QACC_SMOOTH, MASS_DIAG, ENV_CYCLES, FC_KEY, FC_N, FC_VAL, SOLVER_STAT = range(21)
 MAX_CONTACTS = 64
 
 SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
     "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render", "avsim_set_warmstart",
-    "avsim_pixels_to_float", "avsim_jac",
+    "avsim_pixels_to_float", "avsim_jac", "avsim_set_solver",
 ]
+SOLVER_PGS, SOLVER_NEWTON = 0, 1
 
 
 class DiffIKParams(C.Structure):
@@ -60,6 +61,7 @@ def load_library():
     L.avsim_destroy.argtypes = [vp]
     L.avsim_set_options.argtypes = [vp, i32, i32, i32]
     L.avsim_set_warmstart.argtypes = [vp, i32]
+    L.avsim_set_solver.argtypes = [vp, i32, i32, i32, C.c_float]
     L.avsim_reset.argtypes = [vp, vp, vp]
     L.avsim_step.argtypes = [vp, vp, i32]
     L.avsim_forward.argtypes = [vp]
@@ -174,6 +176,7 @@ class Batch:
             XPOS: ((m.nbody, 3), torch.float32), QFRC_BIAS: (m.nv, torch.float32), QACC_SMOOTH: (m.nv, torch.float32),
             MASS_DIAG: (m.nv, torch.float32), ENV_CYCLES: (None, torch.int64),
             FC_KEY: (MAX_CONTACTS + 20, torch.int32), FC_N: (2, torch.int32), FC_VAL: (MAX_CONTACTS * 6 + 20, torch.float32),
+            SOLVER_STAT: (4, torch.float32),
         }
 
     def close(self):
@@ -189,6 +192,12 @@ class Batch:
 
     def set_options(self, solver_iters=20, noslip_iters=-1, multiccd=-1):
         check(self.lib.avsim_set_options(self.ptr, solver_iters, noslip_iters, multiccd))
+
+    def set_solver(self, solver="newton", max_iter=0, ls_iter=0, tol=0.0):
+        """'newton' (default of a new batch): Newton on the primal, the reference's solver; 'pgs': fixed-sweep block Gauss-Seidel
+        on the dual (sweep count from set_options).  max_iter / ls_iter / tol <= 0 keep the current Newton settings."""
+        code = {"pgs": SOLVER_PGS, "newton": SOLVER_NEWTON}[solver] if isinstance(solver, str) else int(solver)
+        check(self.lib.avsim_set_solver(self.ptr, code, int(max_iter), int(ls_iter), float(tol)))
 
     def set_warmstart(self, mode):
         """1: MuJoCo-style warm start from the previous qacc (default); 2: per-constraint force cache."""

@@ -17,6 +17,7 @@
 #include "avsim_render.cuh"
 
 #define AV_SORT_MAX 8192
+#define AV_MAX_GROUPS 8
 #ifndef AV_DEFAULT_HEAVY_TASKS
 #define AV_DEFAULT_HEAVY_TASKS 0
 #define AV_DEFAULT_HEAVY_WARPS 0
@@ -114,7 +115,13 @@ struct avsim_batch {
     const avsim_model *model;
     BatchState st;
     cudaStream_t stream;
-    int grid, fwd_grid, warps, envw;
+    int grid, fwd_grid, warps, envw, solve_grid, split;
+    // split pipeline: the environments are cut into `ngroups` contiguous groups, each stepped by its own launch chain on its own
+    // stream, so that the tail of one group's solver kernel (a few environments that need many Newton iterations) overlaps with
+    // the other groups' kernels instead of idling the GPU
+    int ngroups = 1, per_sm = 1, sms = 1, solve_per_sm = 1;
+    cudaStream_t gstream[AV_MAX_GROUPS] = {};
+    cudaEvent_t ev_start = nullptr, ev_done[AV_MAX_GROUPS] = {};
     int64_t launches = 0;
     std::vector<void *> allocs;
     float *h_action = nullptr, *h_agent = nullptr;   // pinned staging for the host-buffer path
@@ -144,6 +151,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     memset(&s, 0, sizeof s);
     s.num_envs = num_envs; s.seed = seed;
     s.solver_iters = 20; s.noslip_iters = d.noslip_iterations; s.multiccd = d.multiccd; s.warm_mode = 1;
+    s.solver = AVSIM_SOLVER_NEWTON; s.newton_iters = 30; s.newton_ls = 20; s.newton_tol = 1e-6f;   // the reference's solver (aloha_sim.xml:4-6)
     size_t B = num_envs;
     bool ok = dalloc(b, &s.qpos, B * d.nq) && dalloc(b, &s.qvel, B * d.nv) && dalloc(b, &s.ctrl, B * d.nu) &&
               dalloc(b, &s.warm, B * d.nv) && dalloc(b, &s.agent_pos, B * d.nj_obs) && dalloc(b, &s.reward, B) &&
@@ -151,7 +159,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
               dalloc(b, &s.contacts, B * AV_NCON * 16) && dalloc(b, &s.qacc, B * d.nv) && dalloc(b, &s.xpos, B * 3 * d.nbody) &&
               dalloc(b, &s.qfrc_bias, B * d.nv) && dalloc(b, &s.qacc_smooth, B * d.nv) && dalloc(b, &s.mass_diag, B * d.nv) &&
               dalloc(b, &s.scratch, B * AV_SCRATCH_FLOATS) && dalloc(b, &s.env_cycles, B) && dalloc(b, &s.fc_key, B * (AV_NCON + AV_NSC)) && dalloc(b, &s.fc_n, B * 2) &&
-              dalloc(b, &s.fc_val, B * (AV_NCON * 6 + AV_NSC)) && dalloc(b, &s.order, B) && dalloc(b, &s.queue, 1) && dalloc(b, &b->d_action, B * d.nj_obs);
+              dalloc(b, &s.fc_val, B * (AV_NCON * 6 + AV_NSC)) && dalloc(b, &s.nw_stat, B * 4) && dalloc(b, &s.heads, B * AV_HEAD_FLOATS) && dalloc(b, &s.order_b, B) && dalloc(b, &s.queue_b, AV_MAX_GROUPS) && dalloc(b, &s.env_cycles_b, B) && dalloc(b, &s.order, B) && dalloc(b, &s.queue, AV_MAX_GROUPS) && dalloc(b, &b->d_action, B * d.nj_obs);
     if (!ok) { fail(AVSIM_ERR_CUDA, "avsim_create: device allocation failed"); avsim_destroy(b); return nullptr; }
     if (cudaMallocHost(&b->h_action, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
         cudaMallocHost(&b->h_agent, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
@@ -183,6 +191,28 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     per_sm = std::max(1, std::min(per_sm, 64 / b->warps));                    // 64 resident warps per SM
     CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
+    CUP(cudaFuncSetAttribute(avsim_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
+    CUP(cudaFuncSetAttribute(avsim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SOLVE_WARPS * (int)AV_SOLVER_SLICE_BYTES));
+    {   // solver kernel: AV_SOLVE_WARPS free-running warps per block, as many blocks per SM as shared memory and registers allow
+        const char *esb = getenv("AVSIM_SOLVE_BLOCKS"), *esp = getenv("AVSIM_SPLIT");
+        int per = smem_sm / (AV_SOLVE_WARPS * (int)AV_SOLVER_SLICE_BYTES + 1024);
+        per = std::max(1, std::min(per, 16 / AV_SOLVE_WARPS));          // 128 registers per thread: 16 warps per SM
+        if (esb) per = std::max(1, std::min(per, atoi(esb)));
+        b->solve_grid = std::min((num_envs + AV_SOLVE_WARPS - 1) / AV_SOLVE_WARPS, per * sms);
+        b->solve_per_sm = per;
+        b->split = esp ? atoi(esp) : 1;
+        const char *eg = getenv("AVSIM_GROUPS");
+        int ng = eg ? atoi(eg) : 4;
+        ng = std::max(1, std::min(ng, AV_MAX_GROUPS));
+        while (ng > 1 && num_envs / ng < b->envw * sms / 2) ng--;   // a group should still be a good fraction of a wave
+        b->ngroups = ng;
+        for (int g = 0; g < ng && ng > 1; g++) {
+            CUP(cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking));
+            CUP(cudaEventCreateWithFlags(&b->ev_done[g], cudaEventDisableTiming));
+        }
+        if (ng > 1) CUP(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
+    }
+    b->sms = sms;
     CUP(cudaFuncSetAttribute(avsim_render_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SORT_MAX * (int)sizeof(unsigned long long)));
     // heavy tasks (BatchState::heavy_tasks): only when the batch is at least two rounds of resident slots, so that the slots the
@@ -194,6 +224,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     s.heavy_tasks = ht; s.heavy_warps = ht ? hw : 0;
     int tasks = ht + (num_envs - ht * s.heavy_warps + b->envw - 1) / b->envw;
     b->grid = std::min(tasks, per_sm * sms);
+    b->per_sm = per_sm;
     b->fwd_grid = std::min(num_envs, 8 * sms);
     if (avsim_reset(b, nullptr, nullptr) != 0) { avsim_destroy(b); return nullptr; }
     return b;
@@ -202,6 +233,11 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
 extern "C" void avsim_destroy(avsim_batch *b) {
     if (!b) return;
     cudaStreamSynchronize(b->stream);
+    for (int g = 0; g < AV_MAX_GROUPS; g++) {
+        if (b->gstream[g]) { cudaStreamSynchronize(b->gstream[g]); cudaStreamDestroy(b->gstream[g]); }
+        if (b->ev_done[g]) cudaEventDestroy(b->ev_done[g]);
+    }
+    if (b->ev_start) cudaEventDestroy(b->ev_start);
     for (void *p : b->allocs) cudaFree(p);
     if (b->h_action) cudaFreeHost(b->h_action);
     if (b->h_agent) cudaFreeHost(b->h_agent);
@@ -214,6 +250,15 @@ extern "C" int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_it
     b->st.solver_iters = solver_iters;
     b->st.noslip_iters = noslip_iters >= 0 ? noslip_iters : b->model->dm.noslip_iterations;
     b->st.multiccd = multiccd >= 0 ? multiccd : b->model->dm.multiccd;
+    return AVSIM_OK;
+}
+
+extern "C" int avsim_set_solver(avsim_batch *b, int solver, int max_iter, int ls_iter, float tol) {
+    if (!b || (solver != AVSIM_SOLVER_PGS && solver != AVSIM_SOLVER_NEWTON)) return fail(AVSIM_ERR_ARG, "avsim_set_solver: solver must be AVSIM_SOLVER_PGS or AVSIM_SOLVER_NEWTON");
+    b->st.solver = solver;
+    if (max_iter > 0) b->st.newton_iters = max_iter;
+    if (ls_iter > 0) b->st.newton_ls = ls_iter;
+    if (tol > 0.f) b->st.newton_tol = tol;
     return AVSIM_OK;
 }
 
@@ -240,16 +285,66 @@ extern "C" int avsim_reset(avsim_batch *b, const uint8_t *mask_dev, const float 
     return launch_forward(b, mask_dev);   // physics.forward() + first observation of the reset envs (reference env.py:244-246)
 }
 
+static void launch_order(avsim_batch *b, const BatchState &st, cudaStream_t stream) {
+    // queue order: costliest environment of the previous step first (single-block sort up to 8192 environments)
+    int n = st.num_envs, n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    if (n2 <= AV_SORT_MAX) avsim_order_kernel<<<1, 1024, n2 * sizeof(unsigned long long), stream>>>(st, n2);
+    else avsim_identity_order_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st);
+    b->launches++;
+}
+
+// the view of environments [e0, e0 + n) of a batch: every per-environment array offset, own queue heads (slot g)
+static BatchState group_view(const avsim_batch *b, int e0, int n, int g) {
+    const DevModel &d = b->model->dm;
+    BatchState v = b->st;
+    size_t o = (size_t)e0;
+    v.num_envs = n;
+    v.qpos += o * d.nq; v.qvel += o * d.nv; v.ctrl += o * d.nu; v.warm += o * d.nv; v.agent_pos += o * d.nj_obs;
+    v.reward += o; v.status += o; v.latch += o; v.ncon += o; v.episode += o;
+    v.contacts += o * AV_NCON * 16;
+    v.qacc += o * d.nv; v.xpos += o * 3 * d.nbody; v.qfrc_bias += o * d.nv; v.qacc_smooth += o * d.nv; v.mass_diag += o * d.nv;
+    v.scratch += o * AV_SCRATCH_FLOATS;
+    v.order += o; v.queue += g; v.order_b += o; v.queue_b += g;
+    v.fc_key += o * (AV_NCON + AV_NSC); v.fc_n += o * 2; v.fc_val += o * (AV_NCON * 6 + AV_NSC);
+    v.env_cycles += o; v.env_cycles_b += o; v.heads += o * AV_HEAD_FLOATS; v.nw_stat += o * 4;
+    return v;
+}
+
 extern "C" int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps) {
     if (!b || nsubsteps < 0) return fail(AVSIM_ERR_ARG, "avsim_step: bad arguments");
     CU(cudaSetDevice(b->model->device));
-    // queue order: costliest environment of the previous step first (single-block sort up to 8192 environments)
-    int n = b->st.num_envs, n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    if (n2 <= AV_SORT_MAX) avsim_order_kernel<<<1, 1024, n2 * sizeof(unsigned long long), b->stream>>>(b->st, n2);
-    else avsim_identity_order_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->st);
-    avsim_step_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->envw, b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
-    b->launches += 2;
+    if (b->split && b->st.solver == AVSIM_SOLVER_NEWTON) {
+        // split pipeline (avsim_kernels.cuh): lockstep substep kernel + free-running solver kernel, 2 nsub + 1 launches per group
+        const DevModel &d = b->model->dm;
+        int G = b->ngroups, n = b->st.num_envs;
+        if (G > 1) CU(cudaEventRecord(b->ev_start, b->stream));
+        for (int g = 0; g < G; g++) {
+            cudaStream_t st = G > 1 ? b->gstream[g] : b->stream;
+            int e0 = (int)((long long)n * g / G), e1 = (int)((long long)n * (g + 1) / G), ng = e1 - e0;
+            if (G > 1) CU(cudaStreamWaitEvent(st, b->ev_start, 0));
+            BatchState v = group_view(b, e0, ng, g), vb = v;   // vb: the solver kernel's queue, same sort keyed by its own cycles
+            vb.env_cycles = v.env_cycles_b; vb.order = v.order_b; vb.queue = v.queue_b;
+            launch_order(b, v, st);
+            launch_order(b, vb, st);
+            int tasks = (ng + b->envw - 1) / b->envw;
+            int grid = std::min(tasks, b->per_sm * b->sms), sgrid = std::min((ng + AV_SOLVE_WARPS - 1) / AV_SOLVE_WARPS, b->solve_per_sm * b->sms);
+            const float *act = action_dev ? action_dev + (size_t)e0 * d.nj_obs : nullptr;
+            for (int s = 0; s <= nsubsteps; s++) {
+                avsim_substep_kernel<<<grid, dim3(32, b->warps), sizeof(EnvS) * b->envw, st>>>(d, v, act, s, nsubsteps);
+                if (s < nsubsteps) avsim_solve_kernel<<<sgrid, dim3(32, AV_SOLVE_WARPS), AV_SOLVE_WARPS * AV_SOLVER_SLICE_BYTES, st>>>(d, v);
+            }
+            b->launches += 2 * nsubsteps + 1;
+            if (G > 1) {
+                CU(cudaEventRecord(b->ev_done[g], st));
+                CU(cudaStreamWaitEvent(b->stream, b->ev_done[g], 0));
+            }
+        }
+    } else {
+        launch_order(b, b->st, b->stream);
+        avsim_step_kernel<<<b->grid, dim3(32, b->warps), sizeof(EnvS) * b->envw, b->stream>>>(b->model->dm, b->st, action_dev, nsubsteps);
+        b->launches++;
+    }
     CU(cudaGetLastError());
     return AVSIM_OK;
 }
@@ -284,6 +379,7 @@ static int field_ptr(avsim_batch *b, int field, void **p, size_t *bytes) {
     case AVSIM_FC_KEY: *p = s.fc_key; *bytes = B * (AV_NCON + AV_NSC) * 4; break;
     case AVSIM_FC_N: *p = s.fc_n; *bytes = B * 2 * 4; break;
     case AVSIM_FC_VAL: *p = s.fc_val; *bytes = B * (AV_NCON * 6 + AV_NSC) * 4; break;
+    case AVSIM_SOLVER_STAT: *p = s.nw_stat; *bytes = B * 4 * 4; break;
     default: return fail(AVSIM_ERR_ARG, "unknown field");
     }
     return AVSIM_OK;

@@ -128,7 +128,7 @@ __device__ inline void collide_box_box(const Shape &A, const Shape &B, PrimOut &
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
             float len2 = 1.f - R[i][j] * R[i][j];
-            if (len2 < 1e-8f) continue;
+            if (len2 < 1e-4f) continue;   // edges within 0.6 deg of parallel (same rule as the oracle): the cross axis is a 0/0 in fp32
             int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
             float il = rsqrtf(len2);
             float s = (fabsf(dA[i2] * R[i1][j] - dA[i1] * R[i2][j]) -
@@ -148,6 +148,7 @@ __device__ inline void collide_box_box(const Shape &A, const Shape &B, PrimOut &
         V3 w = pa - pb;
         float ab = R[i][j], wa = dot(w, a[i]), wb = dot(w, b[j]), den = 1.f - ab * ab;
         float s = (ab * wb - wa) / den, t = (wb - ab * wa) / den;
+        s = fminf(fmaxf(s, -hA[i]), hA[i]); t = fminf(fmaxf(t, -hB[j]), hB[j]);   // the closest points lie ON the two edges
         o.n = 1; o.nrm = L; o.dist[0] = ebest;
         o.pos[0] = ((pa + a[i] * s) + (pb + b[j] * t)) * 0.5f;
         return;

@@ -27,11 +27,15 @@
 #ifndef AV_MAX_WARPS
 #define AV_MAX_WARPS 16  // warps per block of the step kernel (16 x 32 x 128 registers = the register file); AV_MAX_ENVW of them own a slice
 #endif
+#ifndef AV_SOLVE_WARPS
+#define AV_SOLVE_WARPS 4   // warps (= environments) per block of the solver kernel
+#endif
 #define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
 #ifndef AV_BULK_PREFETCH
 #define AV_BULK_PREFETCH 0 // 1: TMA bulk prefetch of contact blocks in the solver sweep (measured slower, see avsim_solve.cuh)
 #endif
 #define AV_JW 16        // columns of a contact Jacobian block: 8 dofs of tree1 | 8 dofs of tree2
+#define AV_NHP (AV_NV * (AV_NV + 1) / 2)   // packed lower triangle of the Newton solver's Hessian
 
 enum { AV_JNT_FREE = 0, AV_JNT_SLIDE = 2, AV_JNT_HINGE = 3 };
 enum { AV_GEOM_SPHERE = 2, AV_GEOM_CYLINDER = 5, AV_GEOM_BOX = 6, AV_GEOM_MESH = 7 };
@@ -95,8 +99,18 @@ struct BatchState {
     float *fc_val;                                  // [B][AV_NCON * 6 + AV_NSC]
     int warm_mode;                                  // 1: MuJoCo-style map of qacc_warmstart, 2: force cache
     long long *env_cycles;                          // [B] SM cycles the last step kernel spent on each environment
+    // split pipeline (avsim_substep_kernel / avsim_solve_kernel): per-environment head image, the solver kernel's own queue
+    float *heads;                                   // [B][AV_HEAD_FLOATS]
+    int *order_b, *queue_b;                         // environments sorted by the solver cycles of the previous step; queue head
+    long long *env_cycles_b;                        // [B] SM cycles of the last solver launch per environment
     uint64_t seed;
     int solver_iters, noslip_iters, multiccd;
+    // constraint solver: 0 = block PGS on the dual (solver_iters sweeps), 1 = Newton on the primal (the reference's solver:
+    // at most newton_iters iterations, newton_ls line-search evaluations each, stop at scaled gradient < newton_tol); both
+    // are followed by noslip_iters noslip sweeps
+    int solver, newton_iters, newton_ls;
+    float newton_tol;
+    float *nw_stat;                                 // [B][4] Newton statistics of the last launch (NwStat, avsim_kernels.cuh)
     // The first `heavy_tasks` entries of the work queue hand out only `heavy_warps` environments per block (the costliest ones:
     // the queue is sorted); the block's remaining warps carry no environment and only pull pooled narrowphase items, which
     // shortens the launch's critical path (the block with the costliest environments).  0 = every task takes a full block.

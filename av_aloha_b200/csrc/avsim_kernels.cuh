@@ -23,21 +23,64 @@ __device__ inline void env_pipe_init(EnvS &S, int lane) {
 #endif
 }
 
-__device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane) {
-    for (int i = lane; i < m.nq; i += 32) S.qpos[i] = B.qpos[(size_t)env * m.nq + i];
-    for (int i = lane; i < m.nv; i += 32) { S.qvel[i] = B.qvel[(size_t)env * m.nv + i]; S.warm[i] = B.warm[(size_t)env * m.nv + i]; }
-    for (int i = lane; i < m.nu; i += 32) S.ctrl[i] = B.ctrl[(size_t)env * m.nu + i];
-    // world-welded bodies keep their compile-time pose
+// per-launch constants of a slice: world-welded bodies keep their compile-time pose; the per-tree dof table
+__device__ inline void env_consts(const DevModel &m, EnvS &S, int lane) {
     for (int b = lane; b < m.nbody; b += 32)
         if (m.body_tree[b] < 0) {
             st3(S.xpos + 3 * b, ld3(m.body_xpos0 + 3 * b));
             Q4 q = ldq(m.body_xquat0 + 4 * b);
             stq(S.xquat + 4 * b, q);
         }
+    if (lane < m.ntree) S.tree_pk[lane] = m.tree_dofadr[lane] | (m.tree_dofnum[lane] << 6);
+}
+__device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane) {
+    for (int i = lane; i < m.nq; i += 32) S.qpos[i] = B.qpos[(size_t)env * m.nq + i];
+    for (int i = lane; i < m.nv; i += 32) { S.qvel[i] = B.qvel[(size_t)env * m.nv + i]; S.warm[i] = B.warm[(size_t)env * m.nv + i]; }
+    for (int i = lane; i < m.nu; i += 32) S.ctrl[i] = B.ctrl[(size_t)env * m.nu + i];
+    env_consts(m, S, lane);
     // padding of the per-tree 8x8 blocks must be finite: block_apply multiplies it by exact zeros
     for (int i = lane; i < AV_MBLK; i += 32) S.Minv[i] = 0.f;
     if (lane == 0) { S.status = 0; S.ncon = 0; S.nsc = 0; }
     __syncwarp();
+}
+// ---- the head record of a slice <-> its image in global memory (split pipeline).  On the device one lane issues ONE bulk
+// asynchronous copy (TMA engine: cp.async.bulk, UBLKCP in SASS) per direction and the warp waits on an mbarrier / bulk group;
+// -DAV_TMA_HEAD=0 falls back to 128-bit loads and stores by all lanes (the A/B is in profiles/).
+#ifndef AV_TMA_HEAD
+#define AV_TMA_HEAD 1
+#endif
+__device__ inline void head_load(EnvS &S, const float *img, int n_floats, unsigned long long *bar, unsigned &phase, int lane) {
+#if defined(__CUDA_ARCH__) && AV_TMA_HEAD
+    __syncwarp();
+    if (lane == 0) {
+        fence_proxy_async();   // this warp's earlier generic accesses to the slice are ordered before the async write
+        bulk_g2s(&S, img, (unsigned)n_floats * 4u, bar);
+    }
+    while (!mbar_wait(bar, phase & 1u)) {}
+    phase++;
+#else
+    (void)bar; (void)phase;
+    const float4 *src = reinterpret_cast<const float4 *>(img);
+    float4 *dst = reinterpret_cast<float4 *>(&S);
+    for (int i = lane; i < n_floats / 4; i += 32) dst[i] = src[i];
+    __syncwarp();
+#endif
+}
+__device__ inline void head_store(const EnvS &S, float *img, int n_floats, int lane) {
+#if defined(__CUDA_ARCH__) && AV_TMA_HEAD
+    __syncwarp();
+    if (lane == 0) {
+        fence_proxy_async();   // the slice was written through the generic proxy
+        bulk_s2g(img, &S, (unsigned)n_floats * 4u);
+        bulk_commit_wait();    // the slice may be overwritten (next task) once the engine has read it
+    }
+    __syncwarp();
+#else
+    const float4 *src = reinterpret_cast<const float4 *>(&S);
+    float4 *dst = reinterpret_cast<float4 *>(img);
+    for (int i = lane; i < n_floats / 4; i += 32) dst[i] = src[i];
+    __syncwarp();
+#endif
 }
 __device__ inline void env_store(const DevModel &m, const BatchState &B, EnvS &S, int env, int lane) {
     for (int i = lane; i < m.nq; i += 32) B.qpos[(size_t)env * m.nq + i] = S.qpos[i];
@@ -83,11 +126,26 @@ __device__ __forceinline__ FCache env_fcache(const BatchState &B, int env) {
     fc.key = B.fc_key + (size_t)env * (AV_NCON + AV_NSC);
     fc.val = B.fc_val + (size_t)env * (AV_NCON * 6 + AV_NSC);
     fc.n = B.fc_n + 2 * (size_t)env;
-    fc.mode = B.warm_mode;
+    fc.mode = B.solver == 1 ? 3 : B.warm_mode;   // 3: primal solver, no dual warm start (rows skip it; Lc = noslip factor)
     return fc;
 }
 
-__device__ __forceinline__ void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf, const FCache &fc) {
+// per-environment solver statistics of one launch: Newton iterations summed over the substeps, the largest scaled gradient
+// a solve ended with, the most iterations one solve took, solves that hit the iteration cap (B.nw_stat, 4 floats per env)
+struct NwStat {
+    float iters = 0.f, grad = 0.f, worst = 0.f, capped = 0.f;
+    __device__ __forceinline__ void add(int ni, float gr, int cap) {
+        iters += (float)ni; grad = fmaxf(grad, gr); worst = fmaxf(worst, (float)ni); capped += ni >= cap ? 1.f : 0.f;
+    }
+    __device__ __forceinline__ void store(const BatchState &B, int env, int lane) const {
+        if (lane == 0) {
+            float *o = B.nw_stat + 4 * (size_t)env;
+            o[0] = iters; o[1] = grad; o[2] = worst; o[3] = capped;
+        }
+    }
+};
+
+__device__ __forceinline__ void env_forward(const DevModel &m, const BatchState &B, EnvS &S, float *scratch, int lane, Prof &pf, const FCache &fc, NwStat &nw, float *bias_out) {
     stage_kinematics(m, S, lane);
     pf.mark(PF_KIN, lane);
     stage_inertia(m, S, lane);
@@ -95,11 +153,19 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
     stage_collision(m, S, scratch, lane, B.multiccd != 0, pf);
     stage_smooth(m, S, lane);
     pf.mark(PF_SMOOTH, lane);
+    if (bias_out)   // parity dump (forward kernel): the Newton solve reuses S.qfrc_bias
+        for (int i = lane; i < m.nv; i += 32) bias_out[i] = S.qfrc_bias[i];
     stage_rows_scalar(m, S, lane, fc);
     pf.mark(PF_ROWS_S, lane);
     stage_rows_contact(m, S, scratch, lane, fc);
     pf.mark(PF_ROWS_C, lane);
-    stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters, B.warm_mode);   // physics.forward(): the force cache is read, not updated
+    if (B.solver == 1) {   // Newton on the primal, then the noslip sweeps on its forces
+        float gr = 0.f;
+        int ni = stage_newton(m, S, scratch, lane, B.newton_iters, B.newton_ls, B.newton_tol, gr, pf);
+        nw.add(ni, gr, B.newton_iters);
+        stage_solve(m, S, scratch, lane, 0, B.noslip_iters, 2, true);
+    } else
+        stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters, B.warm_mode);   // physics.forward(): the force cache is read, not updated
     pf.mark(PF_SOLVE, lane);
 }
 
@@ -204,6 +270,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
         const FCache fc = env_fcache(B, env);
         pf.start();
         long long own = 0;
+        NwStat nw;
         if (active) {
             env_load(m, B, S, env, lane);
             pf.mark(PF_LOAD, lane);
@@ -220,16 +287,19 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
             block_collision(m, B, S, scratch, lane, warp, W, active, pf, own);
             AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane, fc); pf.mark(PF_ROWS_S, lane);
                           stage_rows_contact(m, S, scratch, lane, fc); pf.mark(PF_ROWS_C, lane));
-            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, B.warm_mode));
-            for (int it = 0; it < B.solver_iters + B.noslip_iters; it++) {   // sync 3: the sweeps in lockstep too
+            const int sweeps = B.solver == 1 ? 0 : B.solver_iters;   // Newton replaces the regularised sweeps; noslip follows either
+            if (B.solver == 1) AV_STAGE_SYNC(float gr = 0.f; int ni = stage_newton(m, S, scratch, lane, B.newton_iters, B.newton_ls, B.newton_tol, gr, pf);
+                                             nw.add(ni, gr, B.newton_iters));
+            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, B.solver == 1 ? 2 : B.warm_mode));
+            for (int it = 0; it < sweeps + B.noslip_iters; it++) {   // sync 3: the sweeps in lockstep too
                 if (active) {
                     long long t0 = clock64();
-                    solve_sweep(m, S, scratch, lane, it >= B.solver_iters);
+                    solve_sweep(m, S, scratch, lane, it >= sweeps, B.solver == 1);
                     own += clock64() - t0;
                 }
                 if (B.sync >= 3) __syncthreads();
             }
-            if (active) stage_cache_store(m, S, lane, fc);
+            if (active && B.solver != 1) stage_cache_store(m, S, lane, fc);
             pf.mark(PF_SOLVE, lane);
             if (B.sync == 2) __syncthreads();
             AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
@@ -241,8 +311,133 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
             env_outputs(m, B, S, scratch, env, lane, true);
             pf.mark(PF_OUT, lane);
             if (lane == 0) B.env_cycles[env] = own;
+            nw.store(B, env, lane);
             __syncwarp();
         }
+    }
+}
+
+// ------------------------------------------------------------------ split pipeline: substep kernel + solver kernel
+// One env.step = for s in 0..nsub: avsim_substep_kernel(s); if (s < nsub) avsim_solve_kernel();   (2 nsub + 1 launches)
+//
+// Why two kernels.  The Newton solve takes 1..17 iterations depending on how many contacts change zone in that substep.  Inside
+// the lockstep blocks of the fused kernel every solve costs its block the iterations of the block's SLOWEST environment
+// (measured: 11 ms per step per mean Newton iteration; profiles/r2_summary.md), and letting the warps free-run through the
+// whole pipeline instead thrashes the instruction cache (AVSIM_SYNC=0: 73 vs 46 ms).  The solver kernel holds only the solver's
+// code, so its warps can free-run: one warp = one environment pulled from a cost-sorted queue, no barrier anywhere, an
+// environment that needs 17 iterations delays nobody.  The substep kernel keeps the lockstep blocks + pooled narrowphase for
+// everything else (whose cost per environment is far more uniform).
+// What crosses the kernel boundary is the slice's head record (AV_HEAD_FLOATS floats, 6.7 KB: state, mass matrix and its
+// block inverse, smooth forces, scalar rows, contact ids) -- one bulk copy per direction through an L2-resident image -- and
+// the contact blocks, which already live in the global scratch.  Per env.step that is 2 x 20 x 6.7 KB x 2 = 0.5 MB per
+// environment of L2 traffic (2.2 GB per launch pair at B = 4096, ~0.4 ms at L2 bandwidth).
+__global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
+                                                                             const float *__restrict__ action, int s, int nsub) {
+    const int lane = threadIdx.x, warp = threadIdx.y, W = blockDim.y, EW = B.env_warps;
+    EnvS &S = *(reinterpret_cast<EnvS *>(av_smem_raw) + (warp < EW ? warp : 0));   // helper warps (warp >= EW) never touch S
+    AV_SHARED int s_base;
+    AV_SHARED unsigned long long s_hbar[AV_MAX_WARPS];
+    unsigned hphase = 0;
+    Prof pf;
+    if (lane == 0) mbar_init(&s_hbar[warp], 1);
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) *B.queue_b = 0;   // rewind the solver kernel's queue (it is not running now)
+    __syncthreads();
+    for (;;) {
+        if (warp == 0 && lane == 0) s_base = atomicAdd(B.queue, 1);
+        __syncthreads();
+        const int task = s_base;
+        __syncthreads();
+        const int nenv = task < B.heavy_tasks ? B.heavy_warps : EW;
+        const int base = task < B.heavy_tasks ? task * B.heavy_warps : B.heavy_tasks * B.heavy_warps + (task - B.heavy_tasks) * EW;
+        if (base >= B.num_envs) break;
+        const bool active = warp < nenv && base + warp < B.num_envs;
+        const int env = active ? B.order[base + warp] : 0;
+        float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
+        float *img = B.heads + (size_t)env * AV_HEAD_FLOATS;
+        const FCache fc = env_fcache(B, env);
+        pf.start();
+        long long own = 0;
+        if (active) {
+            if (s == 0) {
+                env_load(m, B, S, env, lane);
+                if (action && lane < m.nj_obs) {
+                    float a = action[(size_t)env * m.nj_obs + lane];
+                    if (lane == 6 || lane == 13) a = a * (m.act_ctrl_hi[lane] - m.act_ctrl_lo[lane]) + m.act_ctrl_lo[lane];
+                    S.ctrl[lane] = a;
+                }
+                if (lane == 0) { float *o = B.nw_stat + 4 * (size_t)env; o[0] = o[1] = o[2] = o[3] = 0.f; B.env_cycles_b[env] = 0; }
+            } else {
+                head_load(S, img, AV_HEAD_FLOATS, &s_hbar[warp], hphase, lane);   // state + the solver's acc
+                env_consts(m, S, lane);
+            }
+            pf.mark(PF_LOAD, lane);
+            __syncwarp();
+        }
+        if (s > 0) AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
+        AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); if (s < nsub) { stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane); });
+        block_collision(m, B, S, scratch, lane, warp, W, active, pf, own);
+        if (s < nsub) {
+            AV_STAGE_SYNC(stage_smooth(m, S, lane); pf.mark(PF_SMOOTH, lane); stage_rows_scalar(m, S, lane, fc); pf.mark(PF_ROWS_S, lane);
+                          stage_rows_contact(m, S, scratch, lane, fc); pf.mark(PF_ROWS_C, lane));
+            if (active) {
+                head_store(S, img, AV_HEAD_FLOATS, lane);
+                if (lane == 0) B.env_cycles[env] = (s == 0 ? 0 : B.env_cycles[env]) + own;
+            }
+        } else if (active) {   // trailing position pass done: publish the step
+            env_store(m, B, S, env, lane);
+            env_outputs(m, B, S, scratch, env, lane, true);
+            pf.mark(PF_OUT, lane);
+            if (lane == 0) B.env_cycles[env] += own;
+            __syncwarp();
+        }
+    }
+}
+
+// The constraint solve of one substep for every environment: free-running warps, one environment each, pulled from a queue
+// sorted by the solver cycles of the previous step.  Slices hold only the head record and the solver scratch.
+__global__ void __launch_bounds__(32 * AV_SOLVE_WARPS, 4) avsim_solve_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B) {
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    EnvS &S = *reinterpret_cast<EnvS *>(reinterpret_cast<char *>(av_smem_raw) + (size_t)warp * AV_SOLVER_SLICE_BYTES);
+    AV_SHARED unsigned long long s_hbar[AV_SOLVE_WARPS];
+    unsigned hphase = 0;
+    Prof pf;
+    if (lane == 0) mbar_init(&s_hbar[warp], 1);
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) *B.queue = 0;   // rewind the substep kernel's queue
+    __syncwarp();
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(B.queue_b, 1);
+        idx = __shfl_sync(AV_FULL, idx, 0);
+        if (idx >= B.num_envs) break;
+        const int env = B.order_b[idx];
+        float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
+        float *img = B.heads + (size_t)env * AV_HEAD_FLOATS;
+        const FCache fc = env_fcache(B, env);
+        pf.start();
+        long long t0 = clock64();
+        head_load(S, img, AV_HEAD_FLOATS, &s_hbar[warp], hphase, lane);
+        pf.mark(PF_LOAD, lane);
+        int sweeps = B.solver_iters;
+        if (B.solver == 1) {
+            float gr = 0.f;
+            int ni = stage_newton(m, S, scratch, lane, B.newton_iters, B.newton_ls, B.newton_tol, gr, pf);
+            if (lane == 0) {
+                float *o = B.nw_stat + 4 * (size_t)env;
+                o[0] += (float)ni; o[1] = fmaxf(o[1], gr); o[2] = fmaxf(o[2], (float)ni); o[3] += ni >= B.newton_iters ? 1.f : 0.f;
+            }
+            sweeps = 0;
+        }
+        stage_solve_begin(m, S, scratch, lane, B.solver == 1 ? 2 : B.warm_mode);
+        for (int it = 0; it < sweeps + B.noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= sweeps, B.solver == 1);
+        if (B.solver != 1) stage_cache_store(m, S, lane, fc);
+        pf.mark(PF_SOLVE, lane);
+        // back to the image: the constraint acceleration and the status word are all the integrator needs from here
+        for (int i = lane; i < AV_NVP; i += 32) img[offsetof(EnvS, acc) / 4 + i] = S.acc[i];
+        if (lane == 0) {
+            reinterpret_cast<int *>(img)[offsetof(EnvS, status) / 4] = S.status;
+            B.env_cycles_b[env] += clock64() - t0;
+        }
+        __syncwarp();
     }
 }
 
@@ -258,11 +453,12 @@ __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const 
         pf.start();
         env_load(m, B, S, env, lane);
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
-        env_forward(m, B, S, scratch, lane, pf, env_fcache(B, env));
+        NwStat nw;
+        env_forward(m, B, S, scratch, lane, pf, env_fcache(B, env), nw, B.qfrc_bias + (size_t)env * m.nv);
+        nw.store(B, env, lane);
         for (int i = lane; i < m.nv; i += 32) {
             B.qacc[(size_t)env * m.nv + i] = S.qacc_smooth[i] + S.acc[i];
             B.qacc_smooth[(size_t)env * m.nv + i] = S.qacc_smooth[i];
-            B.qfrc_bias[(size_t)env * m.nv + i] = S.qfrc_bias[i];
             int t = m.dof_tree[i], dl = i - m.tree_dofadr[t];
             B.mass_diag[(size_t)env * m.nv + i] = S.M[t * AV_MTRI + av_mtri(dl, dl)];
         }

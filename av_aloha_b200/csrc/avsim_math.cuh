@@ -203,7 +203,17 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned pari
     }
     return false;
 }
+// shared -> global bulk copy (bulk async-group completion) and the wait for its source reads
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 #else
+static inline void bulk_s2g(void *dst, const void *src, unsigned bytes) { memcpy(dst, src, bytes); }
+static inline void bulk_commit_wait() {}
 static inline void mbar_init(unsigned long long *, int) {}
 static inline void fence_proxy_async() {}
 static inline void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }

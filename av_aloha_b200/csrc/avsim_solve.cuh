@@ -37,6 +37,11 @@ __device__ __forceinline__ int tr_dof(int tr, int col) {   // dof of this lane's
     return dl < n ? base + dl : -1;
 }
 __device__ __forceinline__ int tr_tree(int tr, int col) { return (tr >> ((col & 8) ? 23 : 20)) & 7; }
+// the same descriptor rebuilt from the two tree ids kept in c_info (7 = none) and the per-tree table in shared memory
+__device__ __forceinline__ int c_tr(const EnvS &S, int c) {
+    int info = S.c_info[c], t1 = (info >> 21) & 7, t2 = (info >> 24) & 7;
+    return (t1 < 7 ? S.tree_pk[t1] | (t1 << 20) : 0) | (t2 < 7 ? (S.tree_pk[t2] << 10) | (t2 << 23) : 0);
+}
 
 // sum of three per-lane values over the 16 lanes of a half-warp; every lane of the half gets the sums
 __device__ __forceinline__ void half_sum3(float &r0, float &r1, float &r2) {
@@ -228,7 +233,7 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
         float vv[6], aa[6], ww[6];
         block_rows(j0, j1, j2, xv, half, vv);
         block_rows(j0, j1, j2, xa, half, aa);
-        if (fc.mode != 2) block_rows(j0, j1, j2, xw, half, ww);   // J qacc_warmstart: only the MuJoCo-style warm start needs it
+        if (fc.mode == 1) block_rows(j0, j1, j2, xw, half, ww);   // J qacc_warmstart: only the MuJoCo-style warm start needs it
         else {
 #pragma unroll
             for (int k = 0; k < 6; k++) ww[k] = 0.f;
@@ -261,7 +266,7 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
             blk[AV_CB_PAR] = R[0]; blk[AV_CB_PAR + 1] = R[1]; blk[AV_CB_PAR + 2] = R[3]; blk[AV_CB_PAR + 3] = R[4];
             blk[AV_CB_PAR + 4] = mu0; blk[AV_CB_PAR + 5] = mu1; blk[AV_CB_PAR + 6] = mu2;
             blk[AV_CB_PAR + 7] = 1.0f / mu0; blk[AV_CB_PAR + 8] = 1.0f / mu1; blk[AV_CB_PAR + 9] = 1.0f / mu2;
-            S.c_tree[c] = tr;
+            S.c_info[c] = info | ((t1 < 0 ? 7 : t1) << 21) | ((t2 < 0 ? 7 : t2) << 24);
             S.c_lam[c] = 0.f;
         }
         // AR = J MinvJT^T + R, packed lower triangle (21 entries), lane = entry
@@ -294,9 +299,16 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
         for (int i = 0; i < 5; i++)
 #pragma unroll
             for (int j = 0; j <= i; j++) A[TRI(i, j)] = blk[AV_CB_AR + TRI(i + 1, j + 1)];
+        if (fc.mode == 3) {   // Newton solver: only the noslip sweeps use the factor, and they drop the regulariser of the live rows
+            int dim = (info >> 16) & 0xf;
+            float Rf = blk[AV_CB_PAR + 1], Rt = blk[AV_CB_PAR + 2], Rr = blk[AV_CB_PAR + 3];
+            A[TRI(0, 0)] -= Rf; A[TRI(1, 1)] -= Rf;
+            if (dim > 3) { A[TRI(2, 2)] -= Rt; A[TRI(3, 3)] -= Rr; A[TRI(4, 4)] -= Rr; }
+        }
         chol5(A, 0.f, Lc);
 #pragma unroll
         for (int k = 0; k < 15; k++) blk[AV_CB_LC + k] = Lc[k];
+        if (fc.mode == 3) continue;   // the primal solver publishes its own forces
         float *f = S.c_f + 6 * c;
         if (fc.mode == 2) {   // warm start from the force this contact carried in the previous solve (0 when it is new)
             int key = contact_key(S, c), nc = fc.n[0], hit = -1;
@@ -329,7 +341,7 @@ __device__ AV_STAGE void stage_rows_contact(const DevModel &m, EnvS &S, float *s
 // ellipsoid of radius f_n.  Noslip sweep: friction rows only, unregularised A, normal force fixed.  Both modes share ONE
 // instance of the QCQP code: the sweep loop is the hottest code of the kernel and has to stay inside the SM's
 // instruction cache (ncu showed 'no_instruction' as the top stall when each mode carried its own copy).
-__device__ __forceinline__ void contact_block_update(const CBlk &cb, int dim, bool noslip, float (&res)[6], const float (&old)[6],
+__device__ __forceinline__ void contact_block_update(const CBlk &cb, int dim, bool noslip, bool lc_noslip, float (&res)[6], const float (&old)[6],
                                                      float &lam, float (&f)[6]) {
 #pragma unroll
     for (int k = 0; k < 6; k++) { res[k] += cb.b[k] + (noslip ? 0.f : cb.R[k] * old[k]); f[k] = old[k]; }
@@ -371,14 +383,14 @@ __device__ __forceinline__ void contact_block_update(const CBlk &cb, int dim, bo
         }
         bc[k - 1] = s;
     }
-    qcqp5(Ac, bc, cb.mu, cb.imu, f[0], cb.Lc, !noslip, lam, y);
+    qcqp5(Ac, bc, cb.mu, cb.imu, f[0], cb.Lc, noslip == lc_noslip, lam, y);   // Lc factors the block of exactly one of the two modes
 #pragma unroll
     for (int k = 1; k < 6; k++) f[k] = y[k - 1];
 }
 
 // one Gauss-Seidel sweep over the scalar rows and the contact blocks (the hot loop; its own function so that its code
 // is contiguous and small)
-__device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float *scratch, int lane, bool noslip) {
+__device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float *scratch, int lane, bool noslip, bool lc_noslip = false) {
     int col = lane & 15, half = lane >> 4;
     // scalar rows: every lane computes the (uniform) update, lanes < nt apply it
     for (int r = 0; r < S.nsc; r++) {
@@ -404,7 +416,7 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
         const int c = (half && cb_ != 0xff) ? cb_ : ca;        // an idle second half mirrors the first (results discarded)
         const int info = S.c_info[c], dim = (info >> 16) & 0xf;
         const float *blk = scratch + c * AV_CBLK;
-        const int tr = S.c_tree[c], dof = tr_dof(tr, col);
+        const int tr = c_tr(S, c), dof = tr_dof(tr, col);
         const float *J = blk + AV_CB_J;
         float jc[6], res[6], old[6], f[6], df[6];
 #pragma unroll
@@ -421,7 +433,7 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
 #pragma unroll
         for (int k = 0; k < 6; k++) old[k] = S.c_f[6 * c + k];
         float lam = S.c_lam[c];
-        contact_block_update(cb, dim, noslip, res, old, lam, f);
+        contact_block_update(cb, dim, noslip, lc_noslip, res, old, lam, f);
 #pragma unroll
         for (int k = 0; k < 6; k++) df[k] = f[k] - old[k];
         __syncwarp();
@@ -451,7 +463,7 @@ __device__ __noinline__ void solve_sweep(const DevModel &m, EnvS &S, const float
 __device__ inline void solve_schedule(EnvS &S, int lane) {
     auto tmask = [&](int c) {
         if (c >= S.ncon || ((S.c_info[c] >> 20) & 1)) return -1;          // no rows: never scheduled
-        int tr = S.c_tree[c];
+        int tr = c_tr(S, c);
         return (((tr >> 6) & 15) ? 1 << ((tr >> 20) & 7) : 0) | (((tr >> 16) & 15) ? 1 << ((tr >> 23) & 7) : 0);
     };
     const int m0 = tmask(lane), m1 = tmask(lane + 32);
@@ -491,7 +503,7 @@ __device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *sc
         float df[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) df[k] = S.c_f[6 * c + k];
-        block_apply(S, j0, j1, j2, df, S.c_tree[c], lane);
+        block_apply(S, j0, j1, j2, df, c_tr(S, c), lane);
         __syncwarp();
     }
     float cost = 0.f;
@@ -504,7 +516,7 @@ __device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *sc
         for (int c = 0; c < S.ncon; c++) {
             if ((S.c_info[c] >> 20) & 1) continue;
             const float *blk = scratch + c * AV_CBLK;
-            int tr = S.c_tree[c], dof = tr_dof(tr, col);
+            int tr = c_tr(S, c), dof = tr_dof(tr, col);
             const float *J = blk + AV_CB_J;
             float j0 = J[(3 * half) * AV_JW + col], j1 = J[(3 * half + 1) * AV_JW + col], j2 = J[(3 * half + 2) * AV_JW + col];
             float res[6];
@@ -541,7 +553,7 @@ __device__ inline void stage_cache_store(const DevModel &m, EnvS &S, int lane, c
     if (lane == 0) { fc.n[0] = S.ncon; fc.n[1] = S.nsc; }
     __syncwarp();
 }
-__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters, int warm_mode) {
+__device__ inline void stage_solve(const DevModel &m, EnvS &S, float *scratch, int lane, int iters, int noslip_iters, int warm_mode, bool lc_noslip = false) {
     stage_solve_begin(m, S, scratch, lane, warm_mode);
-    for (int it = 0; it < iters + noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= iters);
+    for (int it = 0; it < iters + noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= iters, lc_noslip);
 }

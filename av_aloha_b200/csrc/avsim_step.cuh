@@ -18,7 +18,7 @@ static_assert((AV_CB_GEO * 4) % 16 == 0 && (AV_CBLK * 4) % 16 == 0, "bulk copies
 
 // ---- optional per-stage cycle counters (-DAVSIM_PROFILE; read back with avsim_stage_cycles)
 enum { PF_LOAD = 0, PF_KIN, PF_INERTIA, PF_BROAD, PF_PRIM, PF_CONVEX, PF_SMOOTH, PF_ROWS_S, PF_ROWS_C, PF_SOLVE, PF_INTEGRATE,
-       PF_OUT, PF_N };
+       PF_OUT, PF_NW_INIT, PF_NW_GRAD, PF_NW_HESS, PF_NW_CHOL, PF_NW_LS, PF_N };
 #ifdef AVSIM_PROFILE
 __device__ unsigned long long g_prof[PF_N];
 struct Prof {
@@ -45,33 +45,22 @@ struct Prof {
 //           J staging of the contact being assembled + M^-1 J^T of the scalar rows (rows_scalar..solve)
 //   u1    : broadphase candidates + world AABBs (kinematics..collision) | cvel, cdofdot (smooth) | contact forces, multipliers
 //           (rows_contact..solve)
-//   u2    : cinert, xipos (kinematics..smooth) | tree descriptors, solver schedule (rows_contact..solve)
+//   u2    : cinert, xipos (kinematics..smooth) | solver schedule (solve_begin..solve)
+//   u1+u2 : the Newton solver's Hessian (stage_newton only)
 //   u3    : geom centres (kinematics..collision) | scalar constraint rows (rows_scalar..solve)
 struct EnvS {
+    // ---- head: everything that crosses a kernel boundary of the split pipeline (substep kernel -> solver kernel -> substep
+    // kernel; avsim_kernels.cuh).  One contiguous, 16-byte aligned record of AV_HEAD_FLOATS floats that is moved between the
+    // per-environment image in global memory (BatchState::heads, L2 resident) and shared memory by one bulk copy each way.
     float qpos[AV_NQ], qvel[AV_NVP], ctrl[24], warm[AV_NVP];
-    float xpos[AV_NB * 3], xquat[AV_NB * 4];
-    float torig[AV_NTREE * 3];
-    float cdof[AV_NV * 6];
+    float M[AV_MPK], Minv[AV_MBLK];   // M: packed lower triangles (av_mtri), read by the two factorisations and one mat-vec per substep
+    float qfrc_smooth[AV_NVP], qacc_smooth[AV_NVP], acc[AV_NVP], qfrc_bias[AV_NVP];
     union {
         float crb[AV_NB * 12];
         float L[AV_MBLK];
         struct {                                      // rows_scalar .. solve: the region is free between smooth and integrate
             __align__(16) float stage[2 * 6 * AV_JW];  // J | MinvJT of the contact being assembled
             float sc_MJ[AV_NSC * AV_TD];
-        };
-    };
-    float M[AV_MPK], Minv[AV_MBLK];   // M: packed lower triangles (av_mtri), read by the two factorisations and one mat-vec per substep
-    float qfrc_smooth[AV_NVP], qacc_smooth[AV_NVP], acc[AV_NVP], qfrc_bias[AV_NVP];
-    union {
-        struct { float gaabb[AV_NG * 3]; int cand_p[AV_NCAND], cand_c[AV_NCAND], keep_c[AV_NKEEP]; };
-        struct { float cvel[AV_NB * 6], cdofdot[AV_NV * 6]; };
-        struct { float c_f[AV_NCON * 6], c_lam[AV_NCON]; };   // contact forces and cone multipliers (rows_contact..solve, cache store)
-    };
-    union {
-        struct { float cinert[AV_NB * 10], xipos[AV_NB * 3]; };
-        struct {
-            int c_tree[AV_NCON];  // packed dof ranges / tree ids of the two kinematic trees (tr_pack)
-            unsigned short c_slot[AV_NCON];  // solver schedule: contact a | contact b << 8 (0xff: none) per half-warp slot
         };
     };
     union {
@@ -83,7 +72,30 @@ struct EnvS {
         };
     };
     // contacts (collision .. outputs); position / frame / distance / friction live in the contact's global scratch block
-    int c_info[AV_NCON];  // geom1 | geom2 << 8 | dim << 16 | excluded << 20
+    int c_info[AV_NCON];  // geom1 | geom2 << 8 | dim << 16 | excluded << 20 | tree1 << 21 | tree2 << 24 (7: none; set by the row assembly)
+    int tree_pk[AV_NTREE + 2];   // per kinematic tree: dofadr | dofnum << 6 (copy of the model table; the contact's trees sit in c_info)
+    int ncon, nsc, ncand_p, ncand_c, nkeep, nslot, status, pad_;
+    // ---- solver scratch: also resident in the solver kernel's (smaller) slices
+    union {
+        struct {
+            union {
+                struct { float gaabb[AV_NG * 3]; int cand_p[AV_NCAND], cand_c[AV_NCAND], keep_c[AV_NKEEP]; };
+                struct { float cvel[AV_NB * 6], cdofdot[AV_NV * 6]; };
+                struct { float c_f[AV_NCON * 6], c_lam[AV_NCON]; };   // contact forces and cone multipliers (rows_contact..solve, cache store)
+            };
+            union {
+                struct { float cinert[AV_NB * 10], xipos[AV_NB * 3]; };
+                unsigned short c_slot[AV_NCON];  // solver schedule: contact a | contact b << 8 (0xff: none) per half-warp slot
+            };
+        };
+        // Newton solve (avsim_newton.cuh): Hessian / its Cholesky factor as a packed lower triangle.  Alive from the end of the row
+        // assembly until the solver publishes its forces into c_f; the sweep schedule (c_slot) is built after that.
+        float H[AV_NHP];
+    };
+    // ---- substep kernel only (recomputed every substep)
+    float xpos[AV_NB * 3], xquat[AV_NB * 4];
+    float torig[AV_NTREE * 3];
+    float cdof[AV_NV * 6];
     // optional solver pipeline (-DAV_BULK_PREFETCH=1): double buffer for the contact block being updated / prefetched by
     // bulk async copies, its two mbarriers and how often each buffer has been filled (phase parity)
 #if AV_BULK_PREFETCH
@@ -91,10 +103,13 @@ struct EnvS {
     unsigned long long mbar[2];
     unsigned cuse[2];
 #endif
-    int ncon, nsc, ncand_p, ncand_c, nkeep, nslot, status;
 };
+#define AV_HEAD_FLOATS ((int)(offsetof(EnvS, H) / 4))
+#define AV_SOLVER_SLICE_BYTES (offsetof(EnvS, xpos))
+static_assert((AV_HEAD_FLOATS * 4) % 16 == 0 && AV_SOLVER_SLICE_BYTES % 16 == 0, "bulk copies move 16-byte multiples");
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[2 * 6 * AV_JW + AV_NSC * AV_TD]), "row staging must fit inside crb");
+static_assert(AV_NHP <= AV_NG * 3 + 2 * AV_NCAND + AV_NKEEP + AV_NB * 13, "the Hessian must fit inside the two unions it overlays");
 static_assert(sizeof(EnvS) % 16 == 0, "slices must keep 16-byte alignment");
 
 // per-environment view of the constraint-force cache in global memory (BatchState.fc_*)
@@ -672,6 +687,7 @@ __device__ AV_STAGE void stage_rows_scalar(const DevModel &m, EnvS &S, int lane,
 }
 
 #include "avsim_solve.cuh"
+#include "avsim_newton.cuh"
 
 // ------------------------------------------------------------------ K7: Euler with implicit joint damping
 __device__ AV_STAGE void stage_integrate(const DevModel &m, EnvS &S, int lane) {

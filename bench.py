@@ -214,6 +214,7 @@ def run_gpu(args):
     batch = capi.Batch(model, B, seed=1234 + rank)
     batch.set_options(solver_iters=args.solver_iters)
     batch.set_warmstart(args.warmstart)
+    batch.set_solver(args.solver, args.newton_iters, args.newton_ls, args.newton_tol)
     obj, acts_np, masks_np, phase = make_workload(B, 1234 + rank)
     acts = torch.as_tensor(acts_np, device=dev)                       # [T, B, 21] resident in HBM
     masks = torch.as_tensor(masks_np, device=dev)                     # [T, B] u8: envs whose episode restarts at step t
@@ -286,6 +287,10 @@ def run_gpu(args):
     cyc_stats = {"mean": float(cyc.mean().item()), "p99": float(cyc.quantile(0.99).item()), "max": float(cyc.max().item())}
     rew = batch.get(capi.REWARD)
     rew_max, rew_mean = int(rew.max().item()), float(rew.float().mean().item())
+    nws = batch.get(capi.SOLVER_STAT).double()
+    solver_stat = {"newton_iters_per_substep_mean": float(nws[:, 0].mean().item()) / 20.0, "scaled_gradient_max": float(nws[:, 1].max().item()),
+                   "scaled_gradient_p99": float(nws[:, 1].quantile(0.99).item()), "iters_one_solve_max": float(nws[:, 2].max().item()),
+                   "capped_solves": float(nws[:, 3].sum().item())}
 
     # ---- end-to-end arm: host numpy buffers through avsim_step_host, copies inside the timed region
     for _ in range(min(args.warmup, 3)):
@@ -342,7 +347,8 @@ def run_gpu(args):
             "health": {"blown_up_envs": n_bad, "contact_overflow_envs": n_ovf, "ncon_mean": ncon_mean,
                        "reward_max": rew_max, "reward_mean": rew_mean, "successes": n_succ, "wall_s": wall,
                        "preroll_steps": args.preroll, "preroll_s": preroll_s,
-                       "step_ms_min": float(min(kern_ms)), "step_ms_max": float(max(kern_ms)), "env_sm_cycles": cyc_stats},
+                       "step_ms_min": float(min(kern_ms)), "step_ms_max": float(max(kern_ms)), "env_sm_cycles": cyc_stats,
+                       "solver": args.solver, "solver_stat": solver_stat},
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
@@ -367,6 +373,10 @@ def main():
     ap.add_argument("--solver-iters", type=int, default=8, dest="solver_iters")
     ap.add_argument("--warmstart", type=int, default=2, choices=[1, 2],
                     help="1: MuJoCo-style qacc map, 2: per-constraint force cache (profiles/r1_warmstart_accuracy.txt)")
+    ap.add_argument("--solver", default="newton", choices=["newton", "pgs"])
+    ap.add_argument("--newton-iters", type=int, default=30, dest="newton_iters")
+    ap.add_argument("--newton-ls", type=int, default=20, dest="newton_ls")
+    ap.add_argument("--newton-tol", type=float, default=1e-6, dest="newton_tol")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", dest="no_clocks", help="diagnostic: do not poll nvidia-smi during the run")
     ap.add_argument("--no-flush", action="store_true", dest="no_flush", help="diagnostic: do not flush L2 between timed steps")

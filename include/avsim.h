@@ -39,7 +39,7 @@ enum avsim_field {
     AVSIM_SUCCESS = 6,     /* i32 [1]       reward == max_reward         (env.py:224)                          */
     AVSIM_NCON = 7,        /* i32 [1]       data.ncon                                                          */
     AVSIM_CONTACTS = 8,    /* f32 [AVSIM_MAX_CONTACTS][16]: dist,pos3,normal3,geom1,geom2,dim,excluded,force_n,pad4 */
-    AVSIM_STATUS = 9,      /* i32 [1]       bit0 numerical blow-up, bit1 contact overflow (> 64), bit2 scalar-row overflow, bit3 block prefetch timed out */
+    AVSIM_STATUS = 9,      /* i32 [1]       bit0 numerical blow-up, bit1 contact overflow (> 64), bit2 scalar-row overflow, bit3 block prefetch timed out, bit4 Newton Hessian not positive definite in fp32 */
     AVSIM_LATCH = 10,      /* i32 [1]       SewNeedle _threaded_needle   (env.py:602,631,673)                  */
     AVSIM_QACC = 11,       /* f32 [nv]      data.qacc of the last forward pass                                 */
     AVSIM_XPOS = 12,       /* f32 [nbody*3] data.xpos of the last forward pass                                 */
@@ -49,7 +49,9 @@ enum avsim_field {
     AVSIM_ENV_CYCLES = 16, /* i64 [1]       SM cycles the last avsim_step spent on this environment (load-balance diagnostics) */
     AVSIM_FC_KEY = 17,     /* i32 [84]      force cache: identity keys of the constraints of the last solve (64 contacts | 20 scalar rows) */
     AVSIM_FC_N = 18,       /* i32 [2]       force cache: number of contact keys, number of scalar-row keys                      */
-    AVSIM_FC_VAL = 19      /* f32 [404]     force cache: 64 x 6 contact forces | 20 scalar-row forces                           */
+    AVSIM_FC_VAL = 19,     /* f32 [404]     force cache: 64 x 6 contact forces | 20 scalar-row forces                           */
+    AVSIM_SOLVER_STAT = 20 /* f32 [4]       Newton solver over the last launch: iterations summed over the substeps, largest scaled
+                                            gradient a solve ended with, most iterations of one solve, solves that hit the cap      */
 };
 #define AVSIM_MAX_CONTACTS 64
 
@@ -68,7 +70,17 @@ void avsim_destroy(avsim_batch *b);
  * multiccd < 0 takes the model's flag (aloha_sim.xml:5). */
 int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_iters, int multiccd);
 
-/* warm start of the constraint solve.  1 (default): MuJoCo's scheme, the previous qacc mapped to forces (what the reference
+/* constraint solver.  AVSIM_SOLVER_NEWTON (default): Newton on the primal problem -- the solver the reference runs, since
+ * aloha_sim.xml:4-6 leaves MuJoCo's default -- warm-started from the previous qacc, at most max_iter iterations with an exact
+ * line search of at most ls_iter evaluations, stopping when the scaled gradient drops below tol; values <= 0 keep the current
+ * setting (defaults 30, 20, 1e-6).  AVSIM_SOLVER_PGS: block projected Gauss-Seidel on the dual with the fixed sweep count of
+ * avsim_set_options (converges to the same optimum, slowly: an approximate, fixed-cost mode).  Both are followed by the
+ * model's noslip sweeps. */
+#define AVSIM_SOLVER_PGS 0
+#define AVSIM_SOLVER_NEWTON 1
+int avsim_set_solver(avsim_batch *b, int solver, int max_iter, int ls_iter, float tol);
+
+/* warm start of the constraint solve (PGS solver only; Newton always starts from the better of qacc_smooth and the previous qacc).  1 (default): MuJoCo's scheme, the previous qacc mapped to forces (what the reference
  * does through data.qacc_warmstart).  2: every constraint starts from the force it carried in the previous solve, matched
  * by identity (geom pair + ordinal); same optimum, but Gauss-Seidel then needs far fewer sweeps for the same accuracy
  * (profiles/r1_warmstart_accuracy.txt). */

@@ -208,6 +208,8 @@ typedef struct {
     int multiccd;       /* -1: take from model */
     int warmstart;
     int sweep_mode;     /* 0: forward sweeps (what the CUDA kernel does); 1: alternate forward / backward (experiment) */
+    int solver;         /* 0: block PGS on the dual; 1: Newton on the primal (the reference's solver, aloha_sim.xml:4-6 leaves MuJoCo's default) */
+    int newton_ls;      /* Newton: line-search evaluations per iteration (<= 0: run the line search to convergence) */
 } ora_options;
 
 typedef struct ora_data {
@@ -241,6 +243,8 @@ typedef struct ora_data {
     int cache_n, cache_key[NEFC_MAX], cache_frozen;   /* frozen: physics.forward() reads the cache but does not update it */
     double cache_f[NEFC_MAX][6];
     long *pair_hist;   /* optional [npair] histogram of pairs reaching the narrowphase (diagnostics) */
+    int inject_n;      /* >= 0: stage_collision takes this contact list instead of running the narrowphase */
+    double inject[NCON_MAX * 9];   /* dist, pos 3, normal 3, geom1, geom2 */
 } ora_data;
 
 ora_data *ora_data_new(const ora_model *m) {
@@ -249,6 +253,7 @@ ora_data *ora_data_new(const ora_model *m) {
     d->A = (double *)calloc((size_t)NEFC_MAX * NEFC_MAX, sizeof(double));
     d->MinvJT = (double *)calloc((size_t)NEFC_MAX * NV_MAX, sizeof(double));
     d->opt.max_iter = 3000; d->opt.tol = 1e-14; d->opt.noslip_iter = -1; d->opt.multiccd = -1; d->opt.warmstart = 1;
+    d->inject_n = -1;
     memcpy(d->qpos, m->qpos0, m->nq * sizeof(double));
     return d;
 }
@@ -264,6 +269,12 @@ long *ora_pair_hist(ora_data *d) {
     return d->pair_hist;
 }
 void ora_set_sweep_mode(ora_data *d, int mode) { d->opt.sweep_mode = mode; }
+/* n < 0 switches back to the narrowphase */
+void ora_inject_contacts(ora_data *d, int n, const double *rec) {
+    d->inject_n = n > NCON_MAX ? NCON_MAX : n;
+    if (n > 0) memcpy(d->inject, rec, (size_t)d->inject_n * 9 * sizeof(double));
+}
+void ora_set_solver(ora_data *d, int solver, int newton_ls) { d->opt.solver = solver; d->opt.newton_ls = newton_ls; }
 void ora_set_options(ora_data *d, int max_iter, double tol, int noslip_iter, int multiccd, int warmstart) {
     d->opt.max_iter = max_iter; d->opt.tol = tol; d->opt.noslip_iter = noslip_iter; d->opt.multiccd = multiccd;
     d->opt.warmstart = warmstart;
@@ -711,6 +722,210 @@ static double dual_cost(const ora_data *d, const double *f) {
     return c;
 }
 
+
+/* ---- primal Newton (MuJoCo's default solver, mj_solPrimal with flg_Newton [third-party; restated from its published
+ * description, SURVEY.md Appendix A]).  Unconstrained convex problem in the acceleration a:
+ *     minimise  0.5 (a - a_smooth)' M (a - a_smooth)  +  sum_blocks s(J a - aref)
+ * where s is the convex conjugate of the dual block problem that the PGS path solves: equality rows quadratic
+ * 0.5 D y^2; friction loss Huber (|force| <= frictionloss); limits / frictionless one-sided quadratic; elliptic
+ * contacts three zones (top: 0, bottom: quadratic, middle: 0.5 Dm (N - mu T)^2 with N = mu y_0, T = |friction_j y_j|,
+ * mu = friction_0 sqrt(R_1 / R_0), Dm = D_0 / (mu^2 (1 + mu^2))).  Same optimum as the dual (strictly convex), which
+ * tests/test_solver_newton.py checks numerically against the PGS path run to convergence. */
+/* cost of one block at constraint-space value y; writes force = -ds/dy and (optionally) the block Hessian */
+static double block_cost(const ora_data *d, int i, int dim, const double *y, double *force, double H[6][6]) {
+    int type = d->efc_type[i];
+    if (H) memset(H, 0, 36 * sizeof(double));
+    if (type != ROW_CONTACT) {
+        double D = 1.0 / d->efc_R[i], yy = y[0];
+        if (type == ROW_EQ) { force[0] = -D * yy; if (H) H[0][0] = D; return 0.5 * D * yy * yy; }
+        if (type == ROW_FLOSS) {
+            double fl = d->efc_floss[i], Rf = d->efc_R[i] * fl;
+            if (yy <= -Rf) { force[0] = fl; return -0.5 * Rf * fl - fl * yy; }
+            if (yy >= Rf) { force[0] = -fl; return -0.5 * Rf * fl + fl * yy; }
+            force[0] = -D * yy; if (H) H[0][0] = D; return 0.5 * D * yy * yy;
+        }
+        if (yy >= 0) { force[0] = 0; return 0; }            /* limit: one-sided */
+        force[0] = -D * yy; if (H) H[0][0] = D; return 0.5 * D * yy * yy;
+    }
+    const ora_contact *con = &d->con[d->efc_id[i]];
+    if (dim == 1) {
+        double D = 1.0 / d->efc_R[i];
+        if (y[0] >= 0) { force[0] = 0; return 0; }
+        force[0] = -D * y[0]; if (H) H[0][0] = D; return 0.5 * D * y[0] * y[0];
+    }
+    double mu = con->friction[0] * sqrt(d->efc_R[i + 1] / d->efc_R[i]);
+    double sc[6], U[6], T2 = 0;
+    sc[0] = mu;
+    for (int k = 1; k < dim; k++) sc[k] = con->friction[k - 1];
+    for (int k = 0; k < dim; k++) U[k] = sc[k] * y[k];
+    for (int k = 1; k < dim; k++) T2 += U[k] * U[k];
+    double N = U[0], T = sqrt(T2);
+    if (N >= mu * T || (T <= 0 && N >= 0)) {                 /* top zone: inside the polar cone, no force */
+        for (int k = 0; k < dim; k++) force[k] = 0;
+        return 0;
+    }
+    if (mu * N + T <= 0 || (T <= 0 && N < 0)) {              /* bottom zone: inside the cone, plain quadratic */
+        double c = 0;
+        for (int k = 0; k < dim; k++) {
+            double D = 1.0 / d->efc_R[i + k];
+            force[k] = -D * y[k]; c += 0.5 * D * y[k] * y[k];
+            if (H) H[k][k] = D;
+        }
+        return c;
+    }
+    double Dm = 1.0 / (d->efc_R[i] * mu * mu * (1 + mu * mu)), e = N - mu * T;   /* middle zone: on the cone surface */
+    force[0] = -Dm * e * mu;
+    for (int k = 1; k < dim; k++) force[k] = Dm * e * mu * U[k] / T * sc[k];
+    if (H) {
+        double HU[6][6];
+        HU[0][0] = Dm;
+        for (int k = 1; k < dim; k++) HU[0][k] = HU[k][0] = -Dm * mu * U[k] / T;
+        for (int k = 1; k < dim; k++)
+            for (int l = 1; l < dim; l++)
+                HU[k][l] = Dm * (mu * mu * U[k] * U[l] / T2 - e * mu * ((k == l) - U[k] * U[l] / T2) / T);
+        for (int k = 0; k < dim; k++)
+            for (int l = 0; l < dim; l++) H[k][l] = sc[k] * HU[k][l] * sc[l];
+    }
+    return 0.5 * Dm * e * e;
+}
+static int block_dim(const ora_data *d, int i) { return d->efc_type[i] == ROW_CONTACT ? d->con[d->efc_id[i]].dim : 1; }
+
+/* total primal cost at acc = a - a_smooth (jar = J acc + b); fills force and, when H != NULL, the Hessian M + J' Hc J */
+static double primal_eval(const ora_data *d, const double *acc, const double *jar, double *force, double (*H)[NV_MAX]) {
+    int nv = d->m->nv, n = d->nefc;
+    double cost = 0;
+    for (int i = 0; i < nv; i++) {
+        double s = 0;
+        for (int j = 0; j < nv; j++) s += d->M[i][j] * acc[j];
+        cost += 0.5 * acc[i] * s;
+        if (H) for (int j = 0; j < nv; j++) H[i][j] = d->M[i][j];
+    }
+    for (int i = 0; i < n;) {
+        int dim = block_dim(d, i);
+        double Hc[6][6];
+        cost += block_cost(d, i, dim, jar + i, force + i, H ? Hc : NULL);
+        if (H)
+            for (int k = 0; k < dim; k++)
+                for (int l = 0; l < dim; l++) {
+                    if (Hc[k][l] == 0) continue;
+                    const double *Jk = d->efc_J[i + k], *Jl = d->efc_J[i + l];
+                    for (int a = 0; a < nv; a++) {
+                        if (Jk[a] == 0) continue;
+                        double t = Jk[a] * Hc[k][l];
+                        for (int c = 0; c < nv; c++) H[a][c] += t * Jl[c];
+                    }
+                }
+        i += dim;
+    }
+    return cost;
+}
+
+static long g_stat_refactor = 0, g_stat_lseval = 0;
+long ora_stat_lseval(void) { return g_stat_lseval; }
+long ora_stat_refactor(void) { return g_stat_refactor; }
+static void solve_newton(ora_data *d, double *f) {
+    const ora_model *m = d->m;
+    int nv = m->nv, n = d->nefc;
+    static __thread double H[NV_MAX][NV_MAX], Lh[NV_MAX][NV_MAX];
+    double acc[NV_MAX], jar[NEFC_MAX], grad[NV_MAX], p[NV_MAX], jv[NEFC_MAX], ftmp[NEFC_MAX], Mp[NV_MAX];
+    double trM = 0;
+    for (int i = 0; i < nv; i++) trM += d->M[i][i];
+    double scale = 1.0 / trM;    /* MuJoCo: 1 / (meaninertia * max(1, nv)) */
+    /* start: the better of a_smooth (acc = 0) and the warm start (MuJoCo mj_fwdConstraint) */
+    memset(acc, 0, sizeof acc);
+    for (int r = 0; r < n; r++) jar[r] = d->efc_b[r];
+    double cost = primal_eval(d, acc, jar, f, NULL);
+    if (d->opt.warmstart) {
+        double aw[NV_MAX], jw[NEFC_MAX];
+        for (int i = 0; i < nv; i++) aw[i] = d->qacc_warmstart[i] - d->qacc_smooth[i];
+        for (int r = 0; r < n; r++) jw[r] = rowdot(d, r, aw) + d->efc_b[r];
+        double cw = primal_eval(d, aw, jw, ftmp, NULL);
+        if (cw < cost) { cost = cw; memcpy(acc, aw, sizeof aw); memcpy(jar, jw, n * sizeof(double)); }
+    }
+    for (int it = 0; it < d->opt.max_iter; it++) {
+        cost = primal_eval(d, acc, jar, f, H);
+        for (int i = 0; i < nv; i++) {
+            double s = 0;
+            for (int j = 0; j < nv; j++) s += d->M[i][j] * acc[j];
+            for (int r = 0; r < n; r++) s -= d->efc_J[r][i] * f[r];
+            grad[i] = s;
+        }
+        double gn = 0;
+        for (int i = 0; i < nv; i++) gn += grad[i] * grad[i];
+        d->solver_iters = it;
+        if (scale * sqrt(gn) < (getenv("ORA_TOLG") ? atof(getenv("ORA_TOLG")) : d->opt.tol)) break;
+        {   /* experiment (ORA_REFRESH=m): re-factor the Hessian only every m-th iteration, preconditioned CG in between */
+            static __thread double gprev[NV_MAX], zprev[NV_MAX], pprev[NV_MAX];
+            int refresh = getenv("ORA_REFRESH") ? atoi(getenv("ORA_REFRESH")) : 1;
+            if (it % refresh == 0) { if (chol_factor(nv, H, Lh)) break; g_stat_refactor++; }
+            double z[NV_MAX];
+            for (int i = 0; i < nv; i++) z[i] = grad[i];
+            chol_solve(nv, Lh, z);
+            double beta = 0;
+            if (it % refresh != 0 && getenv("ORA_PCG")) {
+                double num = 0, den = 0;
+                for (int i = 0; i < nv; i++) { num += z[i] * (grad[i] - gprev[i]); den += zprev[i] * gprev[i]; }
+                beta = den > 0 ? fmax(0, num / den) : 0;
+            }
+            for (int i = 0; i < nv; i++) { p[i] = -z[i] + beta * pprev[i]; gprev[i] = grad[i]; zprev[i] = z[i]; pprev[i] = p[i]; }
+        }
+        /* stop on the Newton decrement: 0.5 g' H^-1 g is the decrease the quadratic model predicts -- MuJoCo's
+         * 'improvement' test without the cancellation of a difference of two costs (which fp32 cannot resolve) */
+        double dec = 0;
+        for (int i = 0; i < nv; i++) dec -= grad[i] * p[i];
+        if (0.5 * scale * dec < d->opt.tol) break;
+        for (int r = 0; r < n; r++) jv[r] = rowdot(d, r, p);
+        double pMp = 0, pMa = 0;
+        for (int i = 0; i < nv; i++) {
+            double s = 0;
+            for (int j = 0; j < nv; j++) s += d->M[i][j] * p[j];
+            Mp[i] = s; pMp += p[i] * s;
+        }
+        for (int i = 0; i < nv; i++) pMa += Mp[i] * acc[i];
+        /* exact line search: safeguarded Newton on phi'(alpha); phi is convex and C1.  The step taken is the evaluated
+         * point with the lowest cost (alpha = 0 included), so a truncated search can never increase the cost. */
+        double lo = 0, hi = -1, alpha = 0, d1_0 = 0, best_alpha = 0, best_phi = 0, d1lo = 0, d1hi = 0;
+        int nls = d->opt.newton_ls > 0 ? d->opt.newton_ls : 60;
+        double lstol = getenv("ORA_LSTOL") ? atof(getenv("ORA_LSTOL")) : 1e-13;
+        int secant = getenv("ORA_LS_SECANT") != NULL;
+        for (int k = 0; k <= nls; k++) {
+            double d1 = pMa + alpha * pMp, d2 = pMp, y[6], Hc[6][6];
+            double phi = alpha * pMa + 0.5 * alpha * alpha * pMp;      /* Gauss part relative to alpha = 0 */
+            for (int i = 0; i < n;) {
+                int dim = block_dim(d, i);
+                for (int q = 0; q < dim; q++) y[q] = jar[i + q] + alpha * jv[i + q];
+                phi += block_cost(d, i, dim, y, ftmp + i, Hc);
+                for (int q = 0; q < dim; q++) {
+                    d1 -= ftmp[i + q] * jv[i + q];
+                    for (int l = 0; l < dim; l++) d2 += jv[i + q] * Hc[q][l] * jv[i + l];
+                }
+                i += dim;
+            }
+            g_stat_lseval++;
+            if (k == 0) { d1_0 = d1; best_phi = phi; }
+            else {
+                if (phi < best_phi) { best_phi = phi; best_alpha = alpha; }
+                if (fabs(d1) <= lstol * fabs(d1_0) || k == nls) break;
+            }
+            if (d1 < 0) { lo = alpha; d1lo = d1; } else { hi = alpha; d1hi = d1; }
+            double next = alpha - d1 / d2;
+            if (next <= lo || (hi >= 0 && next >= hi)) {
+                if (hi < 0) next = 2 * alpha + 1e-12;
+                else if (secant) next = lo - d1lo * (hi - lo) / (d1hi - d1lo);
+                else next = 0.5 * (lo + hi);
+            }
+            alpha = next;
+        }
+        alpha = best_alpha;
+        if (getenv("ORA_NEWTON_TRACE")) fprintf(stderr, "  it %d cost %.12g |g| %.3e alpha %.4g d1_0 %.3e\n", it, cost, sqrt(gn), alpha, d1_0);
+        for (int i = 0; i < nv; i++) acc[i] += alpha * p[i];
+        for (int r = 0; r < n; r++) jar[r] += alpha * jv[r];
+        d->solver_iters = it + 1;
+        if (alpha == 0) break;
+    }
+    primal_eval(d, acc, jar, f, NULL);   /* forces of the final iterate */
+}
+
 static void stage_solve(ora_data *d) {
     const ora_model *m = d->m;
     int nv = m->nv, n = d->nefc;
@@ -801,7 +1016,8 @@ static void stage_solve(ora_data *d) {
                 if (!used[b] && !(cmask[a] & cmask[b])) { used[b] = 1; blk_start[nblk++] = cstart[b]; break; }
         }
     }
-    for (int it = 0; it < d->opt.max_iter; it++) {
+    if (d->opt.solver == 1) solve_newton(d, f);
+    for (int it = 0; it < d->opt.max_iter && d->opt.solver == 0; it++) {
         double improvement = 0; /* decrease of the dual cost over this sweep (exact, block by block) */
         for (int kk = 0; kk < nblk; kk++) {
             int i = blk_start[(d->opt.sweep_mode == 1 && (it & 1)) ? nblk - 1 - kk : kk];

@@ -44,6 +44,8 @@ def lib():
         L.ora_data_new.argtypes = [C.c_void_p]
         L.ora_data_free.argtypes = [C.c_void_p]
         L.ora_set_options.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.ora_set_solver.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ora_inject_contacts.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         for fn in ("ora_forward", "ora_substep"):
             getattr(L, fn).argtypes = [C.c_void_p]
         L.ora_position_pass.argtypes = [C.c_void_p]
@@ -172,6 +174,19 @@ class OracleEnv:
 
     def set_options(self, max_iter=3000, tol=1e-14, noslip_iter=-1, multiccd=-1, warmstart=1):
         lib().ora_set_options(self.ptr, max_iter, tol, noslip_iter, multiccd, warmstart)
+
+    def set_solver(self, solver="pgs", newton_ls=0):
+        """'pgs': block projected Gauss-Seidel on the dual; 'newton': Newton on the primal (the reference's solver)"""
+        lib().ora_set_solver(self.ptr, {"pgs": 0, "newton": 1}[solver], int(newton_ls))
+
+    def inject_contacts(self, records):
+        """Use this contact list [n][9] = (dist, pos 3, normal 3, geom1, geom2) instead of the narrowphase (None: back to the
+        narrowphase).  Lets a test check the constraint solve on exactly the contacts another implementation found."""
+        if records is None:
+            lib().ora_inject_contacts(self.ptr, -1, None)
+            return
+        r = np.ascontiguousarray(records, dtype=np.float64).reshape(-1, 9)
+        lib().ora_inject_contacts(self.ptr, len(r), _dp(r))
 
     def reset(self, free_pos=None, arm_pose=HOME):
         ap = np.ascontiguousarray(arm_pose, dtype=np.float64)

@@ -47,6 +47,7 @@ void run_block(int block, int grid, const std::function<void()> &body) {
 
 unsigned long long av_keys[8192];
 float4 av_smem_raw[(sizeof(EnvS) + 15) / 16 + 1];
+#include <cstddef>
 
 struct EmuBatch {
     avpack::PackedModel pk;
@@ -54,8 +55,9 @@ struct EmuBatch {
     std::vector<float> f[16];
     std::vector<int> iv[8];
     std::vector<long long> cyc;
-    std::vector<int> order, queue, fckey, fcn;
-    std::vector<float> fcval;
+    std::vector<int> order, queue, fckey, fcn, order_b, queue_b;
+    std::vector<float> fcval, heads;
+    std::vector<long long> cyc_b;
 };
 
 extern "C" {
@@ -73,17 +75,24 @@ EmuBatch *emu_create(const char *path, int num_envs) {
     s.qpos = F(0, B * d.nq); s.qvel = F(1, B * d.nv); s.ctrl = F(2, B * d.nu); s.warm = F(3, B * d.nv);
     s.agent_pos = F(4, B * d.nj_obs); s.contacts = F(5, B * AV_NCON * 16); s.qacc = F(6, B * d.nv);
     s.xpos = F(7, B * 3 * d.nbody); s.qfrc_bias = F(8, B * d.nv); s.qacc_smooth = F(9, B * d.nv);
-    s.mass_diag = F(10, B * d.nv); s.scratch = F(11, B * AV_SCRATCH_FLOATS);
+    s.mass_diag = F(10, B * d.nv); s.scratch = F(11, B * AV_SCRATCH_FLOATS); s.nw_stat = F(12, B * 4);
     b->cyc.assign(B, 0); s.env_cycles = b->cyc.data();
     b->fckey.assign(B * (AV_NCON + AV_NSC), 0); b->fcn.assign(B * 2, 0); b->fcval.assign(B * (AV_NCON * 6 + AV_NSC), 0.f);
     s.fc_key = b->fckey.data(); s.fc_n = b->fcn.data(); s.fc_val = b->fcval.data(); s.warm_mode = 1;
     b->order.resize(B); b->queue.assign(1, 0); s.order = b->order.data(); s.queue = b->queue.data();
+    b->heads.assign(B * AV_HEAD_FLOATS, 0.f); s.heads = b->heads.data();
+    b->order_b.resize(B); for (size_t i = 0; i < B; i++) b->order_b[i] = (int)i;
+    b->queue_b.assign(1, 0); b->cyc_b.assign(B, 0);
+    s.order_b = b->order_b.data(); s.queue_b = b->queue_b.data(); s.env_cycles_b = b->cyc_b.data();
     s.env_warps = 1; s.key_pooled = 1;   // the emulated block is one warp = one environment
     s.reward = I(0, B); s.status = I(1, B); s.latch = I(2, B); s.ncon = I(3, B); s.episode = I(4, B);
     return b;
 }
 void emu_destroy(EmuBatch *b) { delete b; }
 void emu_set_warmstart(EmuBatch *b, int mode) { b->st.warm_mode = mode; }
+void emu_set_solver(EmuBatch *b, int solver, int max_iter, int ls_iter, float tol) {
+    b->st.solver = solver; b->st.newton_iters = max_iter; b->st.newton_ls = ls_iter; b->st.newton_tol = tol;
+}
 void emu_set_options(EmuBatch *b, int iters, int noslip, int multiccd) {
     b->st.solver_iters = iters;
     b->st.noslip_iters = noslip >= 0 ? noslip : b->pk.dm.noslip_iterations;
@@ -96,7 +105,7 @@ int emu_dim(EmuBatch *b, int what) {
 }
 float *emu_f(EmuBatch *b, int k) {
     BatchState &s = b->st;
-    float *p[] = {s.qpos, s.qvel, s.ctrl, s.warm, s.agent_pos, s.contacts, s.qacc, s.xpos, s.qfrc_bias, s.qacc_smooth, s.mass_diag};
+    float *p[] = {s.qpos, s.qvel, s.ctrl, s.warm, s.agent_pos, s.contacts, s.qacc, s.xpos, s.qfrc_bias, s.qacc_smooth, s.mass_diag, s.nw_stat};
     return p[k];
 }
 int *emu_i(EmuBatch *b, int k) {
@@ -112,7 +121,13 @@ void emu_step(EmuBatch *b, const float *action, int nsub) {
     int n2 = 1;
     while (n2 < b->st.num_envs) n2 <<= 1;
     emu::run_block(0, 1, [&]() { avsim_order_kernel(b->st, n2); });   // same queue order as the device
-    emu::run_block(0, 1, [&]() { avsim_step_kernel(b->pk.dm, b->st, action, nsub); });   // one block drains the queue
+    if (b->st.solver == 1) {   // split pipeline, as avsim_step launches it
+        for (int s = 0; s <= nsub; s++) {
+            emu::run_block(0, 1, [&]() { avsim_substep_kernel(b->pk.dm, b->st, action, s, nsub); });
+            if (s < nsub) emu::run_block(0, 1, [&]() { avsim_solve_kernel(b->pk.dm, b->st); });
+        }
+    } else
+        emu::run_block(0, 1, [&]() { avsim_step_kernel(b->pk.dm, b->st, action, nsub); });   // one block drains the queue
 }
 void emu_reset(EmuBatch *b, const float *free_pos) {
     int nb = (b->st.num_envs + 31) / 32;

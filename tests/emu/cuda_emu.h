@@ -24,6 +24,7 @@
 #define __shared__
 #define AV_SHARED static
 #define __grid_constant__
+#define __constant__ static const
 static inline float __fdividef(float a, float b) { return a / b; }
 #define __align__(n) alignas(n)
 

@@ -33,6 +33,7 @@ def lib():
         _lib.emu_destroy.argtypes = [C.c_void_p]
         _lib.emu_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.emu_set_warmstart.argtypes = [C.c_void_p, C.c_int]
+        _lib.emu_set_solver.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
         _lib.emu_dim.argtypes = [C.c_void_p, C.c_int]
         _lib.emu_f.restype = C.POINTER(C.c_float)
         _lib.emu_f.argtypes = [C.c_void_p, C.c_int]
@@ -45,7 +46,7 @@ def lib():
 
 
 _F = dict(qpos=0, qvel=1, ctrl=2, warm=3, agent_pos=4, contacts=5, qacc=6, xpos=7, qfrc_bias=8, qacc_smooth=9,
-          mass_diag=10)
+          mass_diag=10, nw_stat=11)
 _I = dict(reward=0, status=1, latch=2, ncon=3, episode=4)
 
 
@@ -57,7 +58,7 @@ class EmuBatch:
         d = lambda k: lib().emu_dim(self.ptr, k)
         self.nq, self.nv, self.nu, self.nbody, self.nj, self.nfree = (d(k) for k in range(6))
         self._w = dict(qpos=self.nq, qvel=self.nv, ctrl=self.nu, warm=self.nv, agent_pos=self.nj, contacts=64 * 16,
-                       qacc=self.nv, xpos=3 * self.nbody, qfrc_bias=self.nv, qacc_smooth=self.nv, mass_diag=self.nv)
+                       qacc=self.nv, xpos=3 * self.nbody, qfrc_bias=self.nv, qacc_smooth=self.nv, mass_diag=self.nv, nw_stat=4)
 
     def __getattr__(self, name):
         if name in _F:
@@ -73,6 +74,9 @@ class EmuBatch:
 
     def set_warmstart(self, mode):
         lib().emu_set_warmstart(self.ptr, mode)
+
+    def set_solver(self, solver="newton", max_iter=30, ls_iter=20, tol=1e-6):
+        lib().emu_set_solver(self.ptr, {"pgs": 0, "newton": 1}[solver], max_iter, ls_iter, tol)
 
     def forward(self):
         lib().emu_forward(self.ptr)

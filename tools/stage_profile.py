@@ -18,20 +18,21 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 nsteps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 NAMES = ["load", "kinematics", "inertia", "broadphase", "prim_narrow", "convex_narrow", "smooth", "rows_scalar",
-         "rows_contact", "solve", "integrate", "outputs"]
+         "rows_contact", "solve", "integrate", "outputs", "newton_init", "newton_grad", "newton_hess", "newton_chol", "newton_ls"]
 model, batch, acts, masks, mask_any, fp, t0 = steady.restore(B, iters)
+batch.set_solver(os.environ.get('SOLVER', 'newton'))
 lib = capi.load_library()
-buf = (C.c_uint64 * 16)()
+buf = (C.c_uint64 * 32)()
 steady.step(batch, acts, masks, mask_any, fp, t0)
 torch.cuda.synchronize()
-lib.avsim_stage_cycles(buf, 16, 1)
+lib.avsim_stage_cycles(buf, 32, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for k in range(nsteps):
     steady.step(batch, acts, masks, mask_any, fp, t0 + 1 + k)
 e1.record()
 torch.cuda.synchronize()
-n = lib.avsim_stage_cycles(buf, 16, 1)
+n = lib.avsim_stage_cycles(buf, 32, 1)
 cyc = np.array(buf[:n], dtype=np.float64)
 ncon = batch.get(capi.NCON).float()
 print(f"B={B} iters={iters}: {e0.elapsed_time(e1) / nsteps:.1f} ms/step; ncon mean {ncon.mean().item():.1f} max {int(ncon.max().item())}; "
