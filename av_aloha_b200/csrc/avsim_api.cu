@@ -151,7 +151,8 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     memset(&s, 0, sizeof s);
     s.num_envs = num_envs; s.seed = seed;
     s.solver_iters = 20; s.noslip_iters = d.noslip_iterations; s.multiccd = d.multiccd; s.warm_mode = 1;
-    s.solver = AVSIM_SOLVER_NEWTON; s.newton_iters = 30; s.newton_ls = 20; s.newton_tol = 1e-6f;   // the reference's solver (aloha_sim.xml:4-6)
+    s.solver = AVSIM_SOLVER_NEWTON; s.newton_iters = 30; s.newton_ls = 20; s.newton_tol = 3e-7f;   // the reference's solver (aloha_sim.xml:4-6); tolerance: see DESIGN.md section 4
+    if (const char *et = getenv("AVSIM_NEWTON_TOL")) s.newton_tol = (float)atof(et);   // diagnostic override
     size_t B = num_envs;
     bool ok = dalloc(b, &s.qpos, B * d.nq) && dalloc(b, &s.qvel, B * d.nv) && dalloc(b, &s.ctrl, B * d.nu) &&
               dalloc(b, &s.warm, B * d.nv) && dalloc(b, &s.agent_pos, B * d.nj_obs) && dalloc(b, &s.reward, B) &&

@@ -191,8 +191,38 @@ __device__ inline void collide_box_box(const Shape &A, const Shape &B, PrimOut &
 }
 
 // ------------------------------------------------------------------ warp-cooperative MPR
+// The support points are fp32 (vertex scan, one per lane-strided chunk); everything that DECIDES -- which side of a portal
+// edge the origin ray passes, when the portal has converged, the distance of the origin to the final portal -- runs in fp64 on
+// the exact difference of the two fp32 support points.  In fp32 those triple products (three 5 cm vectors that differ by
+// millimetres) keep 2-4 significant digits, and whenever the origin ray leaves the Minkowski difference within ~1e-3 of an
+// edge the portal walked onto the neighbouring face: 5 % of the hull contacts of the bench workload came out with another
+// normal (up to 60 degrees off) and up to 0.9 mm another depth than the fp64 oracle (profiles/r2_mpr_fp64.txt).  The decisions
+// are a few dozen scalar operations per iteration next to a scan over hundreds of vertices: B200's fp64 pipe makes them free.
+struct D3 {
+    double x, y, z;
+};
+__device__ __forceinline__ D3 d3(double x, double y, double z) { D3 r = {x, y, z}; return r; }
+__device__ __forceinline__ D3 d3(V3 a) { return d3((double)a.x, (double)a.y, (double)a.z); }
+__device__ __forceinline__ V3 f3(D3 a) { return v3((float)a.x, (float)a.y, (float)a.z); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 operator-(D3 a) { return d3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ double norm(D3 a) { return sqrt(dot(a, a)); }
+// unit vector: fp32 reciprocal square root + two Newton steps in fp64 (no fp64 sqrt / division on the portal loop's critical path)
+__device__ __forceinline__ D3 normalized(D3 a) {
+    double n2 = dot(a, a);
+    if (!(n2 > 1e-60)) return a;
+    double r = (double)rsqrtf((float)n2);
+    r = r * (1.5 - 0.5 * n2 * r * r);
+    r = r * (1.5 - 0.5 * n2 * r * r);
+    return a * r;
+}
 struct Sup {
-    V3 v, v1, v2;
+    D3 v;        // v1 - v2, exact
+    V3 v1, v2;   // support points on the two shapes
 };
 
 // support point of S in world direction dir; uniform across the warp
@@ -254,47 +284,47 @@ __device__ __noinline__ void mpr_support_ni(const Shape &A, const Shape &B, floa
     V3 dir = v3(dx, dy, dz);
     s.v1 = support_world(A, dir, lane);
     s.v2 = support_world(B, -dir, lane);
-    s.v = s.v1 - s.v2;
+    s.v = d3(s.v1) - d3(s.v2);
 }
-__device__ __forceinline__ Sup mpr_support(const Shape &A, const Shape &B, V3 dir, int lane) {
+__device__ __forceinline__ Sup mpr_support(const Shape &A, const Shape &B, D3 dir, int lane) {
     Sup s;
-    mpr_support_ni(A, B, dir.x, dir.y, dir.z, lane, s);
+    mpr_support_ni(A, B, (float)dir.x, (float)dir.y, (float)dir.z, lane, s);
     return s;
 }
-__device__ __forceinline__ V3 portal_dir(const Sup *p) { return normalized(cross(p[2].v - p[1].v, p[3].v - p[1].v)); }
+__device__ __forceinline__ D3 portal_dir(const Sup *p) { return normalized(cross(p[2].v - p[1].v, p[3].v - p[1].v)); }
 __device__ __forceinline__ void expand_portal(Sup *p, const Sup &v4) {
-    V3 v4v0 = cross(v4.v, p[0].v);
+    D3 v4v0 = cross(v4.v, p[0].v);
     if (dot(p[1].v, v4v0) > 0) {
         if (dot(p[2].v, v4v0) > 0) p[1] = v4; else p[3] = v4;
     } else {
         if (dot(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4;
     }
 }
-__device__ __forceinline__ bool reach_tolerance(const Sup *p, const Sup &v4, V3 dir) {
-    float dv4 = dot(v4.v, dir);
-    float dt = fminf(fminf(dv4 - dot(p[1].v, dir), dv4 - dot(p[2].v, dir)), dv4 - dot(p[3].v, dir));
-    return dt <= AV_MPR_TOL;
+__device__ __forceinline__ bool reach_tolerance(const Sup *p, const Sup &v4, D3 dir) {
+    double dv4 = dot(v4.v, dir);
+    double dt = fmin(fmin(dv4 - dot(p[1].v, dir), dv4 - dot(p[2].v, dir)), dv4 - dot(p[3].v, dir));
+    return dt <= (double)AV_MPR_TOL;
 }
-__device__ inline float origin_tri_dist2(V3 a, V3 b, V3 c, V3 &wit) {
-    V3 ab = b - a, ac = c - a, ap = -a;
-    float d1 = dot(ab, ap), d2 = dot(ac, ap), s, t;
+__device__ inline double origin_tri_dist2(D3 a, D3 b, D3 c, D3 &wit) {
+    D3 ab = b - a, ac = c - a, ap = -a;
+    double d1 = dot(ab, ap), d2 = dot(ac, ap), s, t;
     if (d1 <= 0 && d2 <= 0) { s = 0; t = 0; }
     else {
-        float d3 = dot(ab, -b), d4 = dot(ac, -b);
-        if (d3 >= 0 && d4 <= d3) { s = 1; t = 0; }
+        double d3_ = dot(ab, -b), d4 = dot(ac, -b);
+        if (d3_ >= 0 && d4 <= d3_) { s = 1; t = 0; }
         else {
-            float vc = d1 * d4 - d3 * d2;
-            if (vc <= 0 && d1 >= 0 && d3 <= 0) { s = d1 / (d1 - d3); t = 0; }
+            double vc = d1 * d4 - d3_ * d2;
+            if (vc <= 0 && d1 >= 0 && d3_ <= 0) { s = d1 / (d1 - d3_); t = 0; }
             else {
-                float d5 = dot(ab, -c), d6 = dot(ac, -c);
+                double d5 = dot(ab, -c), d6 = dot(ac, -c);
                 if (d6 >= 0 && d5 <= d6) { s = 0; t = 1; }
                 else {
-                    float vb = d5 * d2 - d1 * d6;
+                    double vb = d5 * d2 - d1 * d6;
                     if (vb <= 0 && d2 >= 0 && d6 <= 0) { s = 0; t = d2 / (d2 - d6); }
                     else {
-                        float va = d3 * d6 - d5 * d4;
-                        if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) { t = (d4 - d3) / ((d4 - d3) + (d5 - d6)); s = 1 - t; }
-                        else { float den = 1.0f / (va + vb + vc); s = vb * den; t = vc * den; }
+                        double va = d3_ * d6 - d5 * d4;
+                        if (va <= 0 && (d4 - d3_) >= 0 && (d5 - d6) >= 0) { t = (d4 - d3_) / ((d4 - d3_) + (d5 - d6)); s = 1 - t; }
+                        else { double den = 1.0 / (va + vb + vc); s = vb * den; t = vc * den; }
                     }
                 }
             }
@@ -304,13 +334,13 @@ __device__ inline float origin_tri_dist2(V3 a, V3 b, V3 c, V3 &wit) {
     return dot(wit, wit);
 }
 __device__ inline V3 find_pos(const Sup *p) {
-    V3 dir = portal_dir(p);
-    float b[4];
+    D3 dir = portal_dir(p);
+    double b[4];
     b[0] = dot(cross(p[1].v, p[2].v), p[3].v);
     b[1] = dot(cross(p[3].v, p[2].v), p[0].v);
     b[2] = dot(cross(p[0].v, p[1].v), p[3].v);
     b[3] = dot(cross(p[2].v, p[1].v), p[0].v);
-    float sum = b[0] + b[1] + b[2] + b[3];
+    double sum = b[0] + b[1] + b[2] + b[3];
     if (sum <= 0) {
         b[0] = 0;
         b[1] = dot(cross(p[2].v, p[3].v), dir);
@@ -318,26 +348,27 @@ __device__ inline V3 find_pos(const Sup *p) {
         b[3] = dot(cross(p[1].v, p[2].v), dir);
         sum = b[1] + b[2] + b[3];
     }
-    float inv = 1.0f / sum;
-    V3 p1 = v3(0, 0, 0), p2 = v3(0, 0, 0);
-    for (int i = 0; i < 4; i++) { p1 = p1 + p[i].v1 * b[i]; p2 = p2 + p[i].v2 * b[i]; }
-    return (p1 + p2) * (0.5f * inv);
+    double inv = 1.0 / sum;
+    D3 p1 = d3(0, 0, 0), p2 = d3(0, 0, 0);
+    for (int i = 0; i < 4; i++) { p1 = p1 + d3(p[i].v1) * b[i]; p2 = p2 + d3(p[i].v2) * b[i]; }
+    return f3((p1 + p2) * (0.5 * inv));
 }
 
 // returns true (warp-uniform) and depth / direction A->B / position when the shapes intersect
-__device__ __noinline__ bool mpr_penetration(const Shape &A, const Shape &B, int lane, float &depth, V3 &dir, V3 &pos) {
+__device__ __noinline__ bool mpr_penetration(const Shape &A, const Shape &B, int lane, float &depth, V3 &dir_out, V3 &pos) {
     Sup p[4], v4;
-    p[0].v1 = A.pos; p[0].v2 = B.pos; p[0].v = A.pos - B.pos;
-    if (norm(p[0].v) < 1e-9f) p[0].v.x += 1e-6f;
+    D3 dir;
+    p[0].v1 = A.pos; p[0].v2 = B.pos; p[0].v = d3(A.pos) - d3(B.pos);
+    if (norm(p[0].v) < 1e-9) p[0].v.x += 1e-6;
     dir = normalized(-p[0].v);
     p[1] = mpr_support(A, B, dir, lane);
     if (dot(p[1].v, dir) <= 0) return false;
     dir = cross(p[0].v, p[1].v);
-    if (norm(dir) < 1e-12f) {
+    if (norm(dir) < 1e-12) {
         pos = (p[1].v1 + p[1].v2) * 0.5f;
-        if (norm(p[1].v) < 1e-9f) { depth = 0; dir = v3(0, 0, 0); return true; }
-        depth = norm(p[1].v);
-        dir = normalized(p[1].v);
+        if (norm(p[1].v) < 1e-9) { depth = 0; dir_out = v3(0, 0, 0); return true; }
+        depth = (float)norm(p[1].v);
+        dir_out = f3(normalized(p[1].v));
         return true;
     }
     dir = normalized(dir);
@@ -366,10 +397,10 @@ __device__ __noinline__ bool mpr_penetration(const Shape &A, const Shape &B, int
         dir = portal_dir(p);
         v4 = mpr_support(A, B, dir, lane);
         if (reach_tolerance(p, v4, dir) || it > AV_MPR_ITERS) {
-            V3 wit;
-            float d2 = origin_tri_dist2(p[1].v, p[2].v, p[3].v, wit);
-            depth = sqrtf(d2);
-            if (depth >= 1e-9f) dir = normalized(wit);
+            D3 wit;
+            double d2 = origin_tri_dist2(p[1].v, p[2].v, p[3].v, wit);
+            depth = (float)sqrt(d2);
+            dir_out = f3(depth >= 1e-9f ? normalized(wit) : dir);
             pos = find_pos(p);
             return true;
         }

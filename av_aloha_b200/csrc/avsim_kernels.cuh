@@ -163,7 +163,7 @@ __device__ __forceinline__ void env_forward(const DevModel &m, const BatchState 
         float gr = 0.f;
         int ni = stage_newton(m, S, scratch, lane, B.newton_iters, B.newton_ls, B.newton_tol, gr, pf);
         nw.add(ni, gr, B.newton_iters);
-        stage_solve(m, S, scratch, lane, 0, B.noslip_iters, 2, true);
+        stage_solve(m, S, scratch, lane, 0, B.noslip_iters, 3, true);
     } else
         stage_solve(m, S, scratch, lane, B.solver_iters, B.noslip_iters, B.warm_mode);   // physics.forward(): the force cache is read, not updated
     pf.mark(PF_SOLVE, lane);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
             const int sweeps = B.solver == 1 ? 0 : B.solver_iters;   // Newton replaces the regularised sweeps; noslip follows either
             if (B.solver == 1) AV_STAGE_SYNC(float gr = 0.f; int ni = stage_newton(m, S, scratch, lane, B.newton_iters, B.newton_ls, B.newton_tol, gr, pf);
                                              nw.add(ni, gr, B.newton_iters));
-            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, B.solver == 1 ? 2 : B.warm_mode));
+            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, B.solver == 1 ? 3 : B.warm_mode));
             for (int it = 0; it < sweeps + B.noslip_iters; it++) {   // sync 3: the sweeps in lockstep too
                 if (active) {
                     long long t0 = clock64();
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(32 * AV_SOLVE_WARPS, 4) avsim_solve_kernel(con
             }
             sweeps = 0;
         }
-        stage_solve_begin(m, S, scratch, lane, B.solver == 1 ? 2 : B.warm_mode);
+        stage_solve_begin(m, S, scratch, lane, B.solver == 1 ? 3 : B.warm_mode);
         for (int it = 0; it < sweeps + B.noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= sweeps, B.solver == 1);
         if (B.solver != 1) stage_cache_store(m, S, lane, fc);
         pf.mark(PF_SOLVE, lane);

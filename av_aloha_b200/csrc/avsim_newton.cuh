@@ -450,7 +450,7 @@ __device__ AV_STAGE int stage_newton(const DevModel &m, EnvS &S, float *scratch,
             float dec = -((i0 < nv ? g[i0] * p0 : 0.f) + (i1 < nv ? g[i1] * p1 : 0.f));
             dec = warp_sum(dec);   // Newton decrement: the decrease the quadratic model predicts is dec / 2
             __syncwarp();
-            stop = !(0.5f * scale * dec >= 1e-4f * tol);   // also catches NaN / a non-descent direction
+            stop = !(0.5f * scale * dec >= 1e-6f * tol);   // also catches NaN / a non-descent direction
             pf.mark(PF_NW_CHOL, lane);
             if (!stop) {
                 // ---- line search along p

@@ -487,6 +487,10 @@ __device__ inline void solve_schedule(EnvS &S, int lane) {
 
 __device__ AV_STAGE void stage_solve_begin(const DevModel &m, EnvS &S, float *scratch, int lane, int warm_mode) {
     int col = lane & 15, half = lane >> 4;
+    if (warm_mode == 3) {   // after the primal (Newton) solve: S.acc IS the solution and S.sc_f / S.c_f its forces.  The noslip
+        solve_schedule(S, lane);   // sweeps add M^-1 J' df on top of it.  Rebuilding acc as M^-1 J' f instead (what a dual solver
+        return;                    // has to do) would push the solve's residual g = M acc - J' f through M^-1 -- the UNCONSTRAINED
+    }                              // inverse: 0.25 rad/s^2 on a finger dof from a scaled residual of 2.6e-5 (profiles/r2_newton_parity.txt)
     // acc <- M^-1 J^T f_warm  (constraint part of the acceleration); dual cost of the warm start
     for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
     __syncwarp();

@@ -111,6 +111,16 @@ def _model(task, num_arms, device):
     return _MODEL_CACHE[key]
 
 
+def _configure_solver(batch, solver, solver_iterations, warmstart):
+    """One default for every environment class: "newton" = Newton on the primal run to its tolerance, the solver the reference
+    uses (assets/aloha_sim.xml:4-6 leaves MuJoCo's default).  "pgs" = the fixed-cost approximate mode: `solver_iterations`
+    block Gauss-Seidel sweeps on the dual with warm start `warmstart` (1: previous qacc, 2: per-constraint force cache)."""
+    batch.set_solver(solver)
+    if solver == "pgs":
+        batch.set_options(solver_iters=solver_iterations)
+        batch.set_warmstart(warmstart)
+
+
 def _check_cameras(cameras):
     assert all(c in CAMERAS for c in cameras), f"Invalid camera names: {cameras}"
 
@@ -128,7 +138,7 @@ class GuidedVisionEnv(_EnvBase):
     max_reward = 0
 
     def __init__(self, task: str | None = None, num_arms: int = 3, cameras=(), observation_height: int = 480,
-                 observation_width: int = 640, device: int = 0, solver_iterations: int = 50, seed: int = 0):
+                 observation_width: int = 640, device: int = 0, solver: str = "newton", solver_iterations: int = 50, seed: int = 0):
         assert num_arms in [2, 3], f"Invalid number of arms: {num_arms}"
         self.task = task or self.task
         self.cameras = list(cameras)
@@ -137,7 +147,7 @@ class GuidedVisionEnv(_EnvBase):
         self.observation_height, self.observation_width = observation_height, observation_width
         self._model = _model(self.task, num_arms, device)
         self._batch = capi.Batch(self._model, 1, seed=seed)
-        self._batch.set_options(solver_iters=solver_iterations)
+        _configure_solver(self._batch, solver, solver_iterations, 1)
         self.max_reward = self._model.max_reward
         self._free_joints = model_io.load_names(self.task, num_arms)["free_joint"]
         self.observation_space = spaces.Dict({
@@ -277,7 +287,8 @@ class GuidedVisionVectorEnv:
     metadata = GuidedVisionEnv.metadata
 
     def __init__(self, task: str, num_envs: int, num_arms: int = 3, cameras=(), max_episode_steps: int = 300,
-                 device: int = 0, solver_iterations: int = 8, warmstart: int = 2, seed: int = 0, reference_rng: bool = False,
+                 device: int = 0, solver: str = "newton", solver_iterations: int = 8, warmstart: int = 2, seed: int = 0,
+                 reference_rng: bool = False,
                  observation_height: int = 480, observation_width: int = 640):
         self.task = TASK_OF.get(task, task)
         self.cameras = list(cameras)
@@ -288,8 +299,7 @@ class GuidedVisionVectorEnv:
         self.reference_rng = reference_rng
         self._model = _model(self.task, num_arms, device)
         self._batch = capi.Batch(self._model, self.num_envs, seed=seed)
-        self._batch.set_options(solver_iters=solver_iterations)
-        self._batch.set_warmstart(warmstart)
+        _configure_solver(self._batch, solver, solver_iterations, warmstart)
         self.max_reward = self._model.max_reward
         self._free_joints = model_io.load_names(self.task, num_arms)["free_joint"]
         self._elapsed = np.zeros(self.num_envs, np.int64)

@@ -69,8 +69,8 @@ def rerender_episode(task: str, all_qpos, cameras, num_arms: int = 3, height: in
     return out
 
 
-def audit_rewards(task: str, first_qpos, actions, num_arms: int = 3, device: int = 0, solver_iterations: int = 8,
-                  warmstart: int = 2, lengths=None):
+def audit_rewards(task: str, first_qpos, actions, num_arms: int = 3, device: int = 0, solver: str = "newton",
+                  solver_iterations: int = 8, warmstart: int = 2, lengths=None):
     """Replays recorded actions for all episodes at once and reports which reach the maximum reward.
 
     first_qpos: [E, nq] (``all_qpos[0]`` of every episode); actions: [E, T, 14|21] float (``/action``), padded to a
@@ -101,8 +101,10 @@ def audit_rewards(task: str, first_qpos, actions, num_arms: int = 3, device: int
     dev = torch.device("cuda", device)
     batch = capi.Batch(model, E, seed=0)
     try:
-        batch.set_options(solver_iters=solver_iterations)
-        batch.set_warmstart(warmstart)
+        batch.set_solver(solver)
+        if solver == "pgs":
+            batch.set_options(solver_iters=solver_iterations)
+            batch.set_warmstart(warmstart)
         batch.reset()                                    # env.reset(options={}) ...
         batch.set(capi.QPOS, q0)                         # ... then env.unwrapped.set_qpos(all_qpos[0])
         batch.forward()

@@ -374,9 +374,9 @@ def main():
     ap.add_argument("--warmstart", type=int, default=2, choices=[1, 2],
                     help="1: MuJoCo-style qacc map, 2: per-constraint force cache (profiles/r1_warmstart_accuracy.txt)")
     ap.add_argument("--solver", default="newton", choices=["newton", "pgs"])
-    ap.add_argument("--newton-iters", type=int, default=30, dest="newton_iters")
-    ap.add_argument("--newton-ls", type=int, default=20, dest="newton_ls")
-    ap.add_argument("--newton-tol", type=float, default=1e-6, dest="newton_tol")
+    ap.add_argument("--newton-iters", type=int, default=0, dest="newton_iters", help="<= 0: the library default (30)")
+    ap.add_argument("--newton-ls", type=int, default=0, dest="newton_ls", help="<= 0: the library default (20)")
+    ap.add_argument("--newton-tol", type=float, default=0.0, dest="newton_tol", help="<= 0: the library default (3e-7)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", dest="no_clocks", help="diagnostic: do not poll nvidia-smi during the run")
     ap.add_argument("--no-flush", action="store_true", dest="no_flush", help="diagnostic: do not flush L2 between timed steps")

@@ -73,7 +73,7 @@ int avsim_set_options(avsim_batch *b, int solver_iters, int noslip_iters, int mu
 /* constraint solver.  AVSIM_SOLVER_NEWTON (default): Newton on the primal problem -- the solver the reference runs, since
  * aloha_sim.xml:4-6 leaves MuJoCo's default -- warm-started from the previous qacc, at most max_iter iterations with an exact
  * line search of at most ls_iter evaluations, stopping when the scaled gradient drops below tol; values <= 0 keep the current
- * setting (defaults 30, 20, 1e-6).  AVSIM_SOLVER_PGS: block projected Gauss-Seidel on the dual with the fixed sweep count of
+ * setting (defaults 30, 20, 3e-7: what fp32 reaches; MuJoCo's 1e-8 is an fp64 figure).  AVSIM_SOLVER_PGS: block projected Gauss-Seidel on the dual with the fixed sweep count of
  * avsim_set_options (converges to the same optimum, slowly: an approximate, fixed-cost mode).  Both are followed by the
  * model's noslip sweeps. */
 #define AVSIM_SOLVER_PGS 0

@@ -253,6 +253,7 @@ ora_data *ora_data_new(const ora_model *m) {
     d->A = (double *)calloc((size_t)NEFC_MAX * NEFC_MAX, sizeof(double));
     d->MinvJT = (double *)calloc((size_t)NEFC_MAX * NV_MAX, sizeof(double));
     d->opt.max_iter = 3000; d->opt.tol = 1e-14; d->opt.noslip_iter = -1; d->opt.multiccd = -1; d->opt.warmstart = 1;
+    d->opt.solver = 1;   /* Newton, like the reference (aloha_sim.xml:4-6 leaves MuJoCo's default); ora_set_solver(d, 0, 0) selects the dual PGS */
     d->inject_n = -1;
     memcpy(d->qpos, m->qpos0, m->nq * sizeof(double));
     return d;
@@ -842,7 +843,7 @@ static void solve_newton(ora_data *d, double *f) {
         double cw = primal_eval(d, aw, jw, ftmp, NULL);
         if (cw < cost) { cost = cw; memcpy(acc, aw, sizeof aw); memcpy(jar, jw, n * sizeof(double)); }
     }
-    for (int it = 0; it < d->opt.max_iter; it++) {
+    for (int it = 0; it < d->opt.max_iter && it < 200; it++) {
         cost = primal_eval(d, acc, jar, f, H);
         for (int i = 0; i < nv; i++) {
             double s = 0;

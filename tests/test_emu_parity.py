@@ -26,7 +26,7 @@ def test_forward_random_state_converged(ctx):
     rng = np.random.default_rng(0)
     fp = _fp(B, rng)
     eb = EmuBatch(path, B)
-    eb.set_options(150)
+    eb.set_solver("pgs"); eb.set_options(150)
     eb.reset(fp)
     eb.qpos[:, :23] += rng.normal(0, 0.05, size=(B, 23)).astype(np.float32)
     eb.qvel[:] = rng.normal(0, 0.3, size=(B, eb.nv))
@@ -48,7 +48,7 @@ def test_one_env_step_resting_contacts(ctx):
     EmuBatch, om, OracleEnv, path = ctx
     fp = np.array([[[0.01, 0.12, 0.0], [0.02, -0.05, 0.0]]])
     eb = EmuBatch(path, 1)
-    eb.set_options(50)
+    eb.set_solver("pgs"); eb.set_options(50)
     eb.reset(fp)
     act = HOME.copy()
     act[6] = act[13] = 1.0
@@ -67,10 +67,10 @@ def test_mixed_primitive_and_convex_contacts_keep_oracle_order(ctx):
     EmuBatch, om, OracleEnv, path = ctx
     fp = np.array([[[0.0, 0.12, -0.002], [0.06, -0.011, 0.133]]])
     eb = EmuBatch(path, 1)
-    eb.set_options(30)
+    eb.set_solver("pgs"); eb.set_options(30)
     eb.reset(fp)
     o = OracleEnv(om)
-    o.set_options(max_iter=30, tol=0.0)
+    o.set_solver("pgs"); o.set_options(max_iter=30, tol=0.0)
     o.reset(free_pos=fp[0])
     o.forward()
     assert o.ncon == eb.ncon[0] and o.ncon >= 6
@@ -99,11 +99,11 @@ def test_force_cache_warm_start_matches_oracle(ctx):
     EmuBatch, om, OracleEnv, path = ctx
     fp = np.array([[[0.0, 0.12, -0.002], [0.06, -0.011, 0.133]]])
     eb = EmuBatch(path, 1)
-    eb.set_options(8)
+    eb.set_solver("pgs"); eb.set_options(8)
     eb.set_warmstart(2)
     eb.reset(fp)
     o = OracleEnv(om)
-    o.set_options(max_iter=8, tol=0.0, warmstart=2)
+    o.set_solver("pgs"); o.set_options(max_iter=8, tol=0.0, warmstart=2)
     o.reset(free_pos=fp[0])
     act = HOME.copy()
     act[6] = act[13] = 0.3

@@ -123,7 +123,7 @@ def test_teleop_pose_action_step_tracks_targets():
     from av_aloha_b200 import env, kinematics, model_io
 
     B = 4
-    v = env.GuidedVisionVectorEnv("slot_insertion", B, num_arms=3, cameras=[], seed=1, solver_iterations=30)
+    v = env.GuidedVisionVectorEnv("slot_insertion", B, num_arms=3, cameras=[], seed=1)
     v.reset()
     home = {"left": env.LEFT_ARM_POSE[:6], "right": env.RIGHT_ARM_POSE[:6], "middle": env.MIDDLE_ARM_POSE}
     poses = {}
@@ -183,7 +183,6 @@ def test_config1_insert_peg_two_arms_plumbing():
     assert obs0["pixels"] == {}
     np.random.seed(1000)
     o = OracleEnv(OracleModel(model_io.model_path("insert_peg", 2)))
-    o.set_options(max_iter=50, tol=0.0, warmstart=1)
     o.reset(free_pos=env.reference_reset_draws("insert_peg", model_io.load_names("insert_peg", 2)["free_joint"]))
     a21 = np.concatenate([a, HOME[14:]]).astype(np.float64)
     worst, at300 = 0.0, None

@@ -36,7 +36,7 @@ def test_forward_contact_free(setup):
     B = 8
     rng = np.random.default_rng(0)
     batch = capi.Batch(model, B, seed=1)
-    batch.set_options(solver_iters=100)   # parity is on the converged solution (equality + friction-loss rows are live)
+    batch.set_solver("pgs"); batch.set_options(solver_iters=100)   # parity is on the converged solution (equality + friction-loss rows are live)
     fp = np.stack([np.array([[rng.uniform(-0.05, 0.05), rng.uniform(0.1, 0.15), 0.0],
                              [rng.uniform(-0.08, 0.08), rng.uniform(-0.1, 0.0), 0.0]]) for _ in range(B)])
     batch.reset(free_pos=fp)
@@ -69,7 +69,7 @@ def test_env_steps_resting_contacts(setup):
     torch, capi, model, om, OracleEnv = setup
     B = 4
     batch = capi.Batch(model, B, seed=1)
-    batch.set_options(solver_iters=50)
+    batch.set_solver("pgs"); batch.set_options(solver_iters=50)
     fp = np.array([[[0.01 * e, 0.12, 0.0], [0.02, -0.05 + 0.01 * e, 0.0]] for e in range(B)])
     batch.reset(free_pos=fp)
     act = np.tile(_hold_action(model.njoints), (B, 1)).astype(np.float32)
@@ -112,7 +112,7 @@ def test_force_cache_warm_start_parity(setup):
     torch, capi, model, om, OracleEnv = setup
     B = 3
     batch = capi.Batch(model, B, seed=1)
-    batch.set_options(solver_iters=8)
+    batch.set_solver("pgs"); batch.set_options(solver_iters=8)
     batch.set_warmstart(2)
     # (the stick wedged under the left fingers; offsets kept small: at larger ones the fp32 MPR depth of one hull pair
     #  differs from the fp64 one by 0.2 mm in a near-degenerate face-face configuration)
@@ -125,7 +125,7 @@ def test_force_cache_warm_start_parity(setup):
     envs = []
     for e in range(B):
         o = OracleEnv(om)
-        o.set_options(max_iter=8, tol=0.0, warmstart=2)
+        o.set_solver("pgs"); o.set_options(max_iter=8, tol=0.0, warmstart=2)
         o.reset(free_pos=fp[e])
         envs.append(o)
     for step in range(3):

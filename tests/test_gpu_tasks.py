@@ -26,7 +26,7 @@ def test_env_step_parity_other_tasks(task, arms):
     free = model_io.load_names(task, arms)["free_joint"]
     fp = np.stack([env.reference_reset_draws(task, free, rng) for _ in range(B)])
     b = capi.Batch(model, B, seed=1)
-    b.set_options(solver_iters=60)
+    b.set_solver("pgs"); b.set_options(solver_iters=60)
     b.reset(free_pos=fp)
     nj = model.njoints
     act = np.tile(_hold(nj), (B, 1)).astype(np.float32)
@@ -34,7 +34,7 @@ def test_env_step_parity_other_tasks(task, arms):
     oras = []
     for e in range(B):
         o = OracleEnv(om)
-        o.set_options(max_iter=60, tol=0.0)
+        o.set_solver("pgs"); o.set_options(max_iter=60, tol=0.0)
         o.reset(free_pos=fp[e])
         oras.append(o)
     for step in range(2):

@@ -108,7 +108,7 @@ def test_oracle_is_thread_safe(slot_model_path):
 
     def run(e):
         o = OracleEnv(om)
-        o.set_options(max_iter=10, tol=0.0)
+        o.set_solver("pgs"); o.set_options(max_iter=10, tol=0.0)
         o.reset(free_pos=np.array([[0.01 * e, 0.12, 0.0], [0.02, -0.05 + 0.005 * e, 0.0]]))
         a = act.copy()
         a[0] += 0.05 * e

@@ -111,7 +111,7 @@ def test_preprocess_observation_matches_reference_contract():
     from av_aloha_b200 import observation
     from av_aloha_b200.env import GuidedVisionVectorEnv
     cams = ["zed_cam_left", "wrist_cam_right"]
-    env = GuidedVisionVectorEnv("slot_insertion", 3, cameras=cams, observation_height=48, observation_width=64, solver_iterations=8)
+    env = GuidedVisionVectorEnv("slot_insertion", 3, cameras=cams, observation_height=48, observation_width=64)
     obs, _ = env.reset()
     got = observation.preprocess_observation(obs)
     assert set(got) == {"observation.images.zed_cam_left", "observation.images.wrist_cam_right", "observation.state"}
@@ -226,8 +226,6 @@ def test_audit_rewards_equals_episode_by_episode_replay():
     lengths = np.array([T, 100, T, 1, 0])
     for e in range(E):
         b = capi.Batch(model, 1, seed=0)
-        b.set_options(solver_iters=8)
-        b.set_warmstart(2)
         b.reset(free_pos=obj[e][None])
         first[e] = b.get(capi.QPOS).cpu().numpy()[0]
         b.reset()
@@ -243,6 +241,15 @@ def test_audit_rewards_equals_episode_by_episode_replay():
         assert np.array_equal(out["rewards"][e, :n], seq[e, :n]), e
         assert int(out["episode_max"][e]) == (int(seq[e, :n].max()) if n else 0)
     assert out["episode_max"].max() >= 2                       # the scripted policy grasps the stick in episode 0 (step 198)
+    # ... and against an independent implementation: the fp64 oracle replays episode 1 (100 steps) the way the reference's
+    # check_dataset_reward.py does (set_qpos(all_qpos[0]); step_action; get_reward) -- same staged rewards, step by step
+    from oracle.oracle import OracleEnv, OracleModel
+    o = OracleEnv(OracleModel(model_io.model_path("slot_insertion", 3)))
+    o.reset()
+    o.qpos[:] = first[1]
+    o.forward()
+    ora = [o.step(acts[1, t].astype(np.float64)) for t in range(int(lengths[1]))]
+    assert np.array_equal(out["rewards"][1, :len(ora)], np.array(ora, np.int32))
     assert out["not_max_reward_episodes"] == [int(i) for i in np.nonzero(~out["max_reward_reached"])[0]]
     assert 4 in out["not_max_reward_episodes"]                 # the empty episode can not have reached it
     with pytest.raises(ValueError):

@@ -55,7 +55,7 @@ def test_kernel_source_free_fall_and_spin_closed_form(slot_model_path):
     from tests.emu.emu import EmuBatch
     avm, qadr = _layout(slot_model_path)
     eb = EmuBatch(slot_model_path, 1)
-    eb.set_options(8)
+    eb.set_solver("pgs"); eb.set_options(8)
     eb.reset(FP[None])
     dof = eb.nv - 6
     eb.qvel[0, dof + 5] = W_SPIN
@@ -76,7 +76,7 @@ def test_gpu_free_fall_and_spin_closed_form(slot_model_path):
     model = capi.Model(slot_model_path, 0)
     B = 3
     b = capi.Batch(model, B, seed=0)
-    b.set_options(solver_iters=8)
+    b.set_solver("pgs"); b.set_options(solver_iters=8)
     b.reset(free_pos=np.tile(FP[None], (B, 1, 1)))
     dof = model.nv - 6
     qvel = b.get(capi.QVEL)
@@ -104,7 +104,7 @@ REST = np.array([[0.0, 0.12, 0.0], [0.02, -0.05, 0.0]])
 def _settled_oracle(path):
     from oracle.oracle import OracleEnv, OracleModel
     o = OracleEnv(OracleModel(path))
-    o.set_options(max_iter=200, tol=1e-12, warmstart=1)
+    o.set_solver("pgs"); o.set_options(max_iter=200, tol=1e-12, warmstart=1)
     o.reset(free_pos=REST)
     act = HOME.copy(); act[6] = act[13] = 1.0
     for _ in range(25):                                       # 1 s: the soft contacts (solref 0.02 s) have long settled
@@ -129,7 +129,7 @@ def test_kernel_source_resting_bodies_carry_their_weight(slot_model_path):
     from tests.emu.emu import EmuBatch
     o = _settled_oracle(slot_model_path)
     eb = EmuBatch(slot_model_path, 1)
-    eb.set_options(50)
+    eb.set_solver("pgs"); eb.set_options(50)
     eb.reset(REST[None])
     eb.qpos[0, :], eb.qvel[0, :], eb.ctrl[0, :] = o.qpos.astype(np.float32), 0.0, o.ctrl.astype(np.float32)
     eb.forward()
@@ -145,7 +145,7 @@ def test_gpu_resting_bodies_carry_their_weight(slot_model_path):
     o = _settled_oracle(slot_model_path)
     model = capi.Model(slot_model_path, 0)
     b = capi.Batch(model, 2, seed=0)
-    b.set_options(solver_iters=50)
+    b.set_solver("pgs"); b.set_options(solver_iters=50)
     b.reset(free_pos=np.tile(REST[None], (2, 1, 1)))
     b.set(capi.QPOS, np.tile(o.qpos.astype(np.float32), (2, 1)))
     b.set(capi.QVEL, np.zeros((2, model.nv), np.float32))
@@ -359,7 +359,7 @@ def test_oracle_contact_forces_are_cone_feasible(slot_model_path):
     obj = workload.sample_object_positions(5, 11)
     acts = workload.slot_insertion_script(300, obj, 11)
     o = OracleEnv(OracleModel(slot_model_path))
-    o.set_options(max_iter=100, tol=1e-10, warmstart=1)
+    o.set_solver("pgs"); o.set_options(max_iter=100, tol=1e-10, warmstart=1)
     o.reset(free_pos=obj[0])
     for t in range(215):
         o.step(acts[t, 0].astype(np.float64))
@@ -427,7 +427,7 @@ def test_kernel_source_contact_records_match_the_oracle_in_a_grasp_state(slot_mo
     obj = workload.sample_object_positions(5, 11)
     acts = workload.slot_insertion_script(300, obj, 11)
     o = OracleEnv(OracleModel(slot_model_path))
-    o.set_options(max_iter=8, tol=0.0, warmstart=2)
+    o.set_solver("pgs"); o.set_options(max_iter=8, tol=0.0, warmstart=2)
     o.reset(free_pos=obj[0])
     for t in range(215):
         o.step(acts[t, 0].astype(np.float64))
@@ -436,7 +436,7 @@ def test_kernel_source_contact_records_match_the_oracle_in_a_grasp_state(slot_mo
     spheres = [c for c in C if 2 in (avm["geom_type"][int(c[13])], avm["geom_type"][int(c[14])])]
     assert len(C) >= 15 and len(spheres) >= 5
     eb = EmuBatch(slot_model_path, 1)
-    eb.set_options(8)
+    eb.set_solver("pgs"); eb.set_options(8)
     eb.reset(obj[0][None])
     eb.qpos[0, :], eb.qvel[0, :], eb.ctrl[0, :] = o.qpos.astype(np.float32), o.qvel.astype(np.float32), o.ctrl.astype(np.float32)
     eb.forward()
@@ -572,7 +572,7 @@ def test_oracle_friction_loss_is_dry_friction_and_fingers_stay_coupled(slot_mode
     obj = workload.sample_object_positions(5, 11)
     acts = workload.slot_insertion_script(300, obj, 11)
     o = OracleEnv(OracleModel(slot_model_path))
-    o.set_options(max_iter=100, tol=1e-10, warmstart=1)
+    o.set_solver("pgs"); o.set_options(max_iter=100, tol=1e-10, warmstart=1)
     o.reset(free_pos=obj[0])
     for k in range(60):
         o.step(acts[k, 0].astype(np.float64))

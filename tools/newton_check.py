@@ -1,40 +1,40 @@
-"""GPU forward pass with the Newton solver on contact-rich states of the bench workload vs the fp64 oracle's Newton run
-to convergence: |dqacc|inf / max(1, |qacc|inf) per environment (SURVEY.md 8c tolerance: 1e-2)."""
+"""GPU forward pass (Newton) on the fixture's contact-rich states vs the fp64 oracle's Newton (1e-13):
+ (a) oracle on the GPU's contact list (the solve alone), (b) oracle with its own narrowphase (end to end).
+Prints the distribution of |dqacc|inf / max(1, |qacc|inf) and of the energy-norm error sqrt(da' M da) / sqrt(1 + a' M a)."""
 import os
 import sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
-import torch
 
-from av_aloha_b200 import capi, model_io
-from oracle.oracle import OracleEnv, OracleModel
+from oracle.oracle import OracleModel
+from test_solver_newton import TASKS, _gpu_forward, _oracle, _rel
 
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-z = np.load(os.path.join(ROOT, "tools", "_steady", "steady_B4096.npz"))
-path = model_io.model_path("slot_insertion", 3)
-model = capi.Model(path, 0)
-idx = np.random.default_rng(5).choice(4096, N, replace=False)
-b = capi.Batch(model, N)
-b.set_solver("newton")
-for k, f in (("qpos", capi.QPOS), ("qvel", capi.QVEL), ("ctrl", capi.CTRL), ("warm", capi.WARMSTART)):
-    b.set(f, z[k][idx])
-b.forward()
-qacc = b.get(capi.QACC).cpu().numpy()
-ncon = b.get(capi.NCON).cpu().numpy()
-st = b.get(capi.SOLVER_STAT).cpu().numpy()
-om = OracleModel(path)
-errs = []
-for j, e in enumerate(idx):
-    o = OracleEnv(om)
-    o.qpos[:] = z["qpos"][e]; o.qvel[:] = z["qvel"][e]; o.ctrl[:] = z["ctrl"][e]; o.qacc_warmstart[:] = z["warm"][e]
-    o.set_options(max_iter=100, tol=1e-14, warmstart=1); o.set_solver("newton")
-    o.forward()
-    qr = o.qacc.copy()
-    errs.append(np.abs(qacc[j] - qr).max() / max(1, np.abs(qr).max()))
-    if errs[-1] > 1e-2:
-        print("env", e, "ncon", o.ncon, ncon[j], "err %.3e" % errs[-1], "dof", np.abs(qacc[j] - qr).argmax(), "stat", st[j])
-errs = np.array(errs)
-print(f"N={N} rel err median {np.median(errs):.2e} p90 {np.quantile(errs,.9):.2e} p99 {np.quantile(errs,.99):.2e} max {errs.max():.2e} "
-      f"frac>1e-2 {np.mean(errs>1e-2):.4f}; newton iters mean {st[:,0].mean():.2f} max {st[:,0].max():.0f}; grad max {st[:,1].max():.2e}")
+
+def q(x):
+    x = np.asarray(x)
+    return "median %.2e p90 %.2e p99 %.2e max %.2e  frac>1e-2 %.3f" % (np.median(x), np.quantile(x, .9), np.quantile(x, .99), x.max(), np.mean(x > 1e-2))
+
+
+for task in TASKS:
+    path, st, g = _gpu_forward(task)
+    om = OracleModel(path)
+    inj, own, en, worst_dof = [], [], [], []
+    for e in range(len(st["qpos"])):
+        c = g["contacts"][e][: g["ncon"][e]]
+        o = _oracle(om, st, e, contacts=np.concatenate([c[:, 0:7], c[:, 7:9]], axis=1))
+        d = g["qacc"][e] - o.qacc
+        inj.append(_rel(g["qacc"][e], o.qacc))
+        worst_dof.append(int(np.abs(d).argmax()))
+        M = o.M
+        en.append(float(np.sqrt(d @ M @ d) / np.sqrt(1.0 + o.qacc @ M @ o.qacc)))
+        o2 = _oracle(om, st, e)
+        own.append(_rel(g["qacc"][e], o2.qacc))
+    print(task, "N", len(inj), "newton iters mean %.2f max %.0f  scaled grad max %.1e" % (g["stat"][:, 0].mean(), g["stat"][:, 0].max(), g["stat"][:, 1].max()))
+    print("   same contacts, max norm   :", q(inj))
+    print("   same contacts, energy norm:", q(en))
+    print("   own narrowphase, max norm :", q(own))
+    bad = np.nonzero(np.array(inj) > 1e-2)[0]
+    print("   states > 1e-2 (same contacts):", [(int(e), "%.1e" % inj[e], "dof", worst_dof[e]) for e in bad][:12])
