@@ -67,7 +67,7 @@ def load_library():
     L.avsim_forward.argtypes = [vp]
     L.avsim_get.argtypes = [vp, i32, vp]
     L.avsim_set.argtypes = [vp, i32, vp]
-    L.avsim_step_host.argtypes = [vp, vp, i32, vp, vp]
+    L.avsim_step_host.argtypes = [vp, vp, i32, vp, vp, vp]
     L.avsim_render.argtypes = [vp, C.POINTER(C.c_int), i32, i32, i32, vp]
     L.avsim_pixels_to_float.argtypes = [vp, C.c_int64, i32, i32, vp, i32, vp]
     L.avsim_launch_count.restype = C.c_int64; L.avsim_launch_count.argtypes = [vp]
@@ -223,8 +223,9 @@ class Batch:
         assert tuple(action.shape) == (self.num_envs, self.model.njoints), action.shape
         check(self.lib.avsim_step(self.ptr, C.c_void_p(action.data_ptr()), nsubsteps))
 
-    def step_host(self, action_np, nsubsteps=20, agent_pos_out=None, reward_out=None):
-        """Host-buffer path: numpy float32 [B, njoints] in, numpy agent_pos / reward out (copies inside the call)."""
+    def step_host(self, action_np, nsubsteps=20, agent_pos_out=None, reward_out=None, status_out=None):
+        """Host-buffer path: numpy float32 [B, njoints] in, numpy agent_pos / reward (/ status when status_out is given) out
+        (copies inside the call)."""
         a = np.ascontiguousarray(action_np, dtype=np.float32)
         assert a.shape == (self.num_envs, self.model.njoints), a.shape
         if agent_pos_out is None:
@@ -232,7 +233,8 @@ class Batch:
         if reward_out is None:
             reward_out = np.empty((self.num_envs,), np.int32)
         check(self.lib.avsim_step_host(self.ptr, a.ctypes.data_as(C.c_void_p), nsubsteps,
-                                       agent_pos_out.ctypes.data_as(C.c_void_p), reward_out.ctypes.data_as(C.c_void_p)))
+                                       agent_pos_out.ctypes.data_as(C.c_void_p), reward_out.ctypes.data_as(C.c_void_p),
+                                       status_out.ctypes.data_as(C.c_void_p) if status_out is not None else None))
         return agent_pos_out, reward_out
 
     def forward(self):

@@ -125,7 +125,7 @@ struct avsim_batch {
     int64_t launches = 0;
     std::vector<void *> allocs;
     float *h_action = nullptr, *h_agent = nullptr;   // pinned staging for the host-buffer path
-    int32_t *h_reward = nullptr;
+    int32_t *h_reward = nullptr, *h_status = nullptr;
     float *d_action = nullptr;
     float *d_rpose = nullptr;   // render: world pose of every geom and camera, [B][ngeom + ncam][12]
     float4 *d_rrect = nullptr;  // render: screen rectangle of every geom per requested camera, [B][8][ngeom]
@@ -164,7 +164,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     if (!ok) { fail(AVSIM_ERR_CUDA, "avsim_create: device allocation failed"); avsim_destroy(b); return nullptr; }
     if (cudaMallocHost(&b->h_action, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
         cudaMallocHost(&b->h_agent, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
-        cudaMallocHost(&b->h_reward, B * sizeof(int32_t)) != cudaSuccess) {
+        cudaMallocHost(&b->h_reward, B * sizeof(int32_t)) != cudaSuccess || cudaMallocHost(&b->h_status, B * sizeof(int32_t)) != cudaSuccess) {
         fail(AVSIM_ERR_CUDA, "avsim_create: pinned allocation failed");
         avsim_destroy(b);
         return nullptr;
@@ -243,6 +243,7 @@ extern "C" void avsim_destroy(avsim_batch *b) {
     if (b->h_action) cudaFreeHost(b->h_action);
     if (b->h_agent) cudaFreeHost(b->h_agent);
     if (b->h_reward) cudaFreeHost(b->h_reward);
+    if (b->h_status) cudaFreeHost(b->h_status);
     delete b;
 }
 
@@ -269,8 +270,8 @@ extern "C" int avsim_set_warmstart(avsim_batch *b, int mode) {
     return AVSIM_OK;
 }
 
-static int launch_forward(avsim_batch *b, const uint8_t *mask_dev = nullptr) {
-    avsim_forward_kernel<<<b->fwd_grid, 32, sizeof(EnvS), b->stream>>>(b->model->dm, b->st, mask_dev);
+static int launch_forward(avsim_batch *b, const uint8_t *mask_dev, int publish_reward) {
+    avsim_forward_kernel<<<b->fwd_grid, 32, sizeof(EnvS), b->stream>>>(b->model->dm, b->st, mask_dev, publish_reward);
     b->launches++;
     CU(cudaGetLastError());
     return AVSIM_OK;
@@ -283,7 +284,7 @@ extern "C" int avsim_reset(avsim_batch *b, const uint8_t *mask_dev, const float 
     avsim_reset_kernel<<<(n + 127) / 128, 128, 0, b->stream>>>(b->model->dm, b->st, mask_dev, free_pos_dev, b->model->home_dev);
     b->launches++;
     CU(cudaGetLastError());
-    return launch_forward(b, mask_dev);   // physics.forward() + first observation of the reset envs (reference env.py:244-246)
+    return launch_forward(b, mask_dev, 0);   // physics.forward() + first observation of the reset envs (reference env.py:244-246)
 }
 
 static void launch_order(avsim_batch *b, const BatchState &st, cudaStream_t stream) {
@@ -353,7 +354,7 @@ extern "C" int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps
 extern "C" int avsim_forward(avsim_batch *b) {
     if (!b) return fail(AVSIM_ERR_ARG, "avsim_forward: null batch");
     CU(cudaSetDevice(b->model->device));
-    return launch_forward(b);
+    return launch_forward(b, nullptr, 1);   // set_qpos(); get_reward() reads the reward of the forward state (reference env.py:251-253, 546-589)
 }
 
 static int field_ptr(avsim_batch *b, int field, void **p, size_t *bytes) {
@@ -423,7 +424,7 @@ extern "C" int avsim_set(avsim_batch *b, int field, const void *src_dev) {
     return AVSIM_OK;
 }
 
-extern "C" int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host) {
+extern "C" int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host, int32_t *status_host) {
     if (!b || !action_host) return fail(AVSIM_ERR_ARG, "avsim_step_host: null argument");
     CU(cudaSetDevice(b->model->device));
     const DevModel &d = b->model->dm;
@@ -434,9 +435,11 @@ extern "C" int avsim_step_host(avsim_batch *b, const float *action_host, int nsu
     if (rc) return rc;
     CU(cudaMemcpyAsync(b->h_agent, b->st.agent_pos, na * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemcpyAsync(b->h_reward, b->st.reward, b->st.num_envs * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    if (status_host) CU(cudaMemcpyAsync(b->h_status, b->st.status, b->st.num_envs * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     if (agent_pos_host) memcpy(agent_pos_host, b->h_agent, na * sizeof(float));
     if (reward_host) memcpy(reward_host, b->h_reward, b->st.num_envs * sizeof(int32_t));
+    if (status_host) memcpy(status_host, b->h_status, b->st.num_envs * sizeof(int32_t));
     return AVSIM_OK;
 }
 

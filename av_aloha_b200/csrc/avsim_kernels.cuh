@@ -88,8 +88,11 @@ __device__ inline void env_store(const DevModel &m, const BatchState &B, EnvS &S
     for (int i = lane; i < m.nu; i += 32) B.ctrl[(size_t)env * m.nu + i] = S.ctrl[i];
 }
 
-// with_reward = false: called right after a solve (forward kernel): contact forces are valid and the reward is kept
-__device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, const float *scratch, int env, int lane, bool with_reward) {
+// with_reward: publish the staged reward (and SewNeedle's latch) of the contacts just found -- env.step and physics.forward()
+// + get_reward() (reference scripts/check_dataset_reward.py:35-38 read the reward right after set_qpos); the forward pass that
+// reset launches keeps reward 0 and the cleared latch instead.  after_solve: the contact forces in S.c_f are valid (dumped).
+__device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS &S, const float *scratch, int env, int lane, bool with_reward,
+                                   bool after_solve) {
     int latch = B.latch[env];
     int r = stage_reward(m, S, lane, latch);
     if (!with_reward) { r = B.reward[env]; latch = B.latch[env]; }
@@ -116,7 +119,7 @@ __device__ inline void env_outputs(const DevModel &m, const BatchState &B, EnvS 
         o[1] = geo[0]; o[2] = geo[1]; o[3] = geo[2];
         o[4] = geo[3]; o[5] = geo[4]; o[6] = geo[5];
         o[7] = (float)(info & 0xff); o[8] = (float)((info >> 8) & 0xff); o[9] = (float)((info >> 16) & 0xf);
-        o[10] = (float)((info >> 20) & 1); o[11] = with_reward ? 0.f : S.c_f[6 * c];
+        o[10] = (float)((info >> 20) & 1); o[11] = after_solve ? S.c_f[6 * c] : 0.f;
         o[12] = o[13] = o[14] = o[15] = 0.f;
     }
 }
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
         block_collision(m, B, S, scratch, lane, warp, W, active, pf, own);
         if (active) {
             env_store(m, B, S, env, lane);
-            env_outputs(m, B, S, scratch, env, lane, true);
+            env_outputs(m, B, S, scratch, env, lane, true, false);
             pf.mark(PF_OUT, lane);
             if (lane == 0) B.env_cycles[env] = own;
             nw.store(B, env, lane);
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(con
             }
         } else if (active) {   // trailing position pass done: publish the step
             env_store(m, B, S, env, lane);
-            env_outputs(m, B, S, scratch, env, lane, true);
+            env_outputs(m, B, S, scratch, env, lane, true, false);
             pf.mark(PF_OUT, lane);
             if (lane == 0) B.env_cycles[env] += own;
             __syncwarp();
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(32 * AV_SOLVE_WARPS, 4) avsim_solve_kernel(con
 
 // physics.forward(): all stages, no integration; dumps stage outputs for the parity tests.  mask (nullable) selects envs.
 __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B,
-                                                                         const uint8_t *__restrict__ mask) {
+                                                                         const uint8_t *__restrict__ mask, int publish_reward) {
     int lane = threadIdx.x;
     EnvS &S = *reinterpret_cast<EnvS *>(av_smem_raw);
     env_pipe_init(S, lane);
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const 
             B.mass_diag[(size_t)env * m.nv + i] = S.M[t * AV_MTRI + av_mtri(dl, dl)];
         }
         for (int i = lane; i < 3 * m.nbody; i += 32) B.xpos[(size_t)env * 3 * m.nbody + i] = S.xpos[i];
-        env_outputs(m, B, S, scratch, env, lane, false);
+        env_outputs(m, B, S, scratch, env, lane, publish_reward != 0, true);
         __syncwarp();
     }
 }

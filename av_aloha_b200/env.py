@@ -63,6 +63,9 @@ LEFT_ARM_POSE = [0, -0.082, 1.06, 0, -0.953, 0, 0.02239]
 RIGHT_ARM_POSE = [0, -0.082, 1.06, 0, -0.953, 0, 0.02239]
 MIDDLE_ARM_POSE = [0, -0.8, 0.8, 0, 0.5, 0, 0]
 CAMERAS = ["zed_cam_left", "zed_cam_right", "wrist_cam_left", "wrist_cam_right", "overhead_cam", "worms_eye_cam"]
+# the 2-arm ids carry no zed cameras (they sit on the middle arm, which the 2-arm model parks out of view):
+# reference gym_guided_vision/__init__.py:16,32,48,64,81
+CAMERAS_2ARMS = ["overhead_cam", "worms_eye_cam", "wrist_cam_left", "wrist_cam_right"]
 RENDER_CAMERA = "overhead_cam"
 
 TASK_OF = {"InsertPeg": "insert_peg", "SlotInsertion": "slot_insertion", "SewNeedle": "sew_needle",
@@ -146,6 +149,7 @@ class GuidedVisionEnv(_EnvBase):
         self.num_arms, self.num_joints = num_arms, 14 if num_arms == 2 else 21
         self.observation_height, self.observation_width = observation_height, observation_width
         self._model = _model(self.task, num_arms, device)
+        self._model_arms, self._device, self._seed, self._solver_cfg = num_arms, device, seed, (solver, solver_iterations, 1)
         self._batch = capi.Batch(self._model, 1, seed=seed)
         _configure_solver(self._batch, solver, solver_iterations, 1)
         self.max_reward = self._model.max_reward
@@ -155,6 +159,8 @@ class GuidedVisionEnv(_EnvBase):
                                                  dtype=np.uint8) for c in self.cameras}),
             "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float64)})
         self.action_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float32)
+        import torch
+        self.torch = torch
         self._agent = np.zeros((1, self.num_joints), np.float32)
         self._reward = np.zeros((1,), np.int32)
         self._cam_ids = _camera_ids(self.task, num_arms, self.cameras)
@@ -167,9 +173,18 @@ class GuidedVisionEnv(_EnvBase):
         return {c: img[0, k] for k, c in enumerate(self.cameras)}
 
     # -- observation / reward (reference env.py:168-193)
-    def get_obs(self):
+    def _agent_pos(self):
         agent = self._batch.get(capi.AGENT_POS).cpu().numpy()[0].astype(np.float64)
-        return {"pixels": self._pixels(), "agent_pos": agent}
+        if self._model_arms == self.num_arms:
+            return agent
+        # middle arm hidden on a 3-arm environment: the swapped-in 2-arm tables publish 14 joints; the middle arm's seven come
+        # straight from qpos (reference env.py:169-178 reads them through the same named joints whatever the base pose is)
+        qadr = self._model.table("obs_qadr")
+        q = self._batch.get(capi.QPOS).cpu().numpy()[0].astype(np.float64)
+        return np.concatenate([agent[:14], q[qadr[14:21]]])
+
+    def get_obs(self):
+        return {"pixels": self._pixels(), "agent_pos": self._agent_pos()}
 
     def get_reward(self):
         return int(self._batch.get(capi.REWARD).cpu().numpy()[0])
@@ -181,11 +196,18 @@ class GuidedVisionEnv(_EnvBase):
     # -- stepping (reference env.py:203-226, 255-269)
     def step_action(self, action):
         a = np.asarray(action, np.float32).reshape(1, self.num_joints)
-        self._batch.step_host(a, SIM_PHYSICS_ENV_STEP_RATIO, self._agent, self._reward)
+        nj = self._model.njoints
+        if nj != self.num_joints:      # middle arm hidden: its ctrl is still written (reference env.py:213-215), it just is not in view
+            ctrl = self._batch.get(capi.CTRL)
+            ctrl[0, 14:21] = self.torch.as_tensor(a[0, 14:21], device=ctrl.device)
+            self._batch.set(capi.CTRL, ctrl)
+        agent = np.zeros((1, nj), np.float32)
+        self._batch.step_host(np.ascontiguousarray(a[:, :nj]), SIM_PHYSICS_ENV_STEP_RATIO, agent, self._reward)
+        self._agent[0, :nj] = agent[0]
 
     def step(self, action):
         self.step_action(action)
-        observation = {"pixels": self._pixels(), "agent_pos": self._agent[0].astype(np.float64)}
+        observation = {"pixels": self._pixels(), "agent_pos": self._agent_pos()}
         reward = int(self._reward[0])
         return observation, reward, False, False, {"is_success": reward == self.max_reward}
 
@@ -200,11 +222,29 @@ class GuidedVisionEnv(_EnvBase):
         self._batch.set(capi.QPOS, np.asarray(qpos, np.float32).reshape(1, -1))
         self._batch.forward()
 
-    def hide_middle_arm(self):   # the 2-arm model is compiled with the middle arm parked (reference env.py:60-62,394-395)
-        pass
+    # reference env.py:394-398: move middle_base_link to (0, -2.4, -0.4) / back to (0, -0.513, 0.02).  The model tables are
+    # compiled per arm count with exactly that edit (mjcf_compile.py), so the call swaps the compiled model under the same state:
+    # joint positions, velocities and ctrl carry over (the two models have identical dof / actuator layouts, reference env.py:60-62)
+    def hide_middle_arm(self):
+        self._swap_model(2)
 
     def show_middle_arm(self):
-        pass
+        self._swap_model(3)
+
+    def _swap_model(self, arms):
+        if arms == self._model_arms:
+            return
+        state = {f: self._batch.get(f).clone() for f in (capi.QPOS, capi.QVEL, capi.CTRL, capi.WARMSTART, capi.LATCH)}
+        self._batch.close()
+        self._model = _model(self.task, arms, self._device)
+        self._model_arms = arms
+        self._batch = capi.Batch(self._model, 1, seed=self._seed)
+        _configure_solver(self._batch, *self._solver_cfg)
+        for f, v in state.items():
+            self._batch.set(f, v)
+        self._batch.forward()
+        self._cam_ids = _camera_ids(self.task, arms, self.cameras)
+        self._render_cam = _camera_ids(self.task, arms, [RENDER_CAMERA])
 
     def close(self):
         if getattr(self, "_batch", None) is not None:
@@ -249,7 +289,7 @@ ENVS = []
 for _name in TASK_OF:
     for _arms in (2, 3):
         ENVS.append({"id": f"gym_guided_vision/{_name}-{_arms}Arms-v0", "task": TASK_OF[_name],
-                     "kwargs": {"num_arms": _arms, "cameras": CAMERAS if _arms == 3 else CAMERAS[:4],
+                     "kwargs": {"num_arms": _arms, "cameras": list(CAMERAS if _arms == 3 else CAMERAS_2ARMS),
                                 "observation_height": 480, "observation_width": 640}})
 
 
@@ -288,8 +328,11 @@ class GuidedVisionVectorEnv:
 
     def __init__(self, task: str, num_envs: int, num_arms: int = 3, cameras=(), max_episode_steps: int = 300,
                  device: int = 0, solver: str = "newton", solver_iterations: int = 8, warmstart: int = 2, seed: int = 0,
-                 reference_rng: bool = False,
-                 observation_height: int = 480, observation_width: int = 640):
+                 reference_rng: bool = False, observation_height: int = 480, observation_width: int = 640,
+                 free_pos=None, episode_phase=None):
+        """free_pos [B, nfree, 3] (optional): fixed object placements used by every reset of environment e instead of a draw --
+        scripted rollouts whose actions were planned for known placements (bench.py).  episode_phase [B] (optional): steps
+        environment e has already spent in its episode after the first reset(), so that episodes end staggered over the batch."""
         self.task = TASK_OF.get(task, task)
         self.cameras = list(cameras)
         _check_cameras(self.cameras)
@@ -305,6 +348,10 @@ class GuidedVisionVectorEnv:
         self._elapsed = np.zeros(self.num_envs, np.int64)
         self._agent = np.zeros((self.num_envs, self.num_joints), np.float32)
         self._reward = np.zeros((self.num_envs,), np.int32)
+        self._status = np.zeros((self.num_envs,), np.int32)
+        self._free_pos = None if free_pos is None else np.ascontiguousarray(free_pos, np.float64).reshape(self.num_envs, len(self._free_joints), 3)
+        self._phase = None if episode_phase is None else np.asarray(episode_phase, np.int64).reshape(self.num_envs)
+        self.blowup_resets = 0          # environments auto-reset because the step flagged a numerical blow-up (STATUS bit 0)
         self.observation_height, self.observation_width = observation_height, observation_width
         self._cam_ids = _camera_ids(self.task, num_arms, self.cameras)
         self._render_cam = _camera_ids(self.task, num_arms, [RENDER_CAMERA])
@@ -313,6 +360,7 @@ class GuidedVisionVectorEnv:
                                                  dtype=np.uint8) for c in self.cameras}),
             "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float64)})
         self.single_action_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.num_joints,), dtype=np.float32)
+        self.observation_space, self.action_space = self.single_observation_space, self.single_action_space
 
     @property
     def unwrapped(self):
@@ -324,12 +372,12 @@ class GuidedVisionVectorEnv:
         img = self._batch.render(self._cam_ids, self.observation_height, self.observation_width).cpu().numpy()
         return {c: img[:, k] for k, c in enumerate(self.cameras)}
 
-    def _obs(self):
-        return {"pixels": self._pixels(), "agent_pos": self._agent.astype(np.float64)}
+    def _obs(self, pixels=None):
+        return {"pixels": self._pixels() if pixels is None else pixels, "agent_pos": self._agent.astype(np.float64)}
 
     def _reset_rows(self, mask):
-        fp = None
-        if self.reference_rng:   # host draws in the reference's np.random order, env by env (SyncVectorEnv loops envs)
+        fp = self._free_pos
+        if fp is None and self.reference_rng:   # host draws in the reference's np.random order, env by env (SyncVectorEnv loops envs)
             fp = np.zeros((self.num_envs, len(self._free_joints), 3))
             for e in np.nonzero(mask)[0]:
                 fp[e] = reference_reset_draws(self.task, self._free_joints)
@@ -338,32 +386,47 @@ class GuidedVisionVectorEnv:
 
     def reset(self, seed=None, options=None):
         self._reset_rows(np.ones(self.num_envs, bool))
+        if self._phase is not None:
+            self._elapsed[:] = self._phase
         self._agent[:] = self._batch.get(capi.AGENT_POS).cpu().numpy()
         return self._obs(), {}
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, np.float32).reshape(self.num_envs, self.num_joints)
-        self._batch.step_host(a, SIM_PHYSICS_ENV_STEP_RATIO, self._agent, self._reward)
+        self._batch.step_host(a, SIM_PHYSICS_ENV_STEP_RATIO, self._agent, self._reward, self._status)
         self._elapsed += 1
         reward = self._reward.astype(np.float64)
         terminated = np.zeros(self.num_envs, bool)
         truncated = self._elapsed >= self._max_episode_steps
-        info = {}
-        if truncated.any():
+        # an environment whose state blew up numerically (STATUS bit 0; SURVEY.md 8b "Errors") ends its episode here and is
+        # reset like a truncated one -- MuJoCo's analogue is the mj_checkAcc warning followed by mj_resetData
+        blown = (self._status & 1) != 0
+        done = truncated | blown
+        if done.any():
+            self.blowup_resets += int(blown.sum())
             final_obs = np.empty(self.num_envs, object)
             final_info = np.empty(self.num_envs, object)
             agent64 = self._agent.astype(np.float64)
             last_px = self._pixels()                      # the last real frames, rendered before the auto-reset
-            for e in np.nonzero(truncated)[0]:
+            for e in np.nonzero(done)[0]:
                 final_obs[e] = {"pixels": {c: v[e].copy() for c, v in last_px.items()}, "agent_pos": agent64[e].copy()}
-                final_info[e] = {"is_success": bool(self._reward[e] == self.max_reward), "TimeLimit.truncated": True}
-            info = {"final_observation": final_obs, "_final_observation": truncated.copy(),
-                    "final_info": final_info, "_final_info": truncated.copy()}
-            self._reset_rows(truncated)
+                final_info[e] = {"is_success": bool(self._reward[e] == self.max_reward) and not blown[e],
+                                 "TimeLimit.truncated": bool(truncated[e])}
+                if blown[e]:
+                    final_info[e]["numerical_blowup"] = True
+            info = {"final_observation": final_obs, "_final_observation": done.copy(),
+                    "final_info": final_info, "_final_info": done.copy()}
+            self._reset_rows(done)
             fresh = self._batch.get(capi.AGENT_POS).cpu().numpy()
-            self._agent[truncated] = fresh[truncated]
-        else:
-            info = {"is_success": self._reward == self.max_reward, "_is_success": np.ones(self.num_envs, bool)}
+            self._agent[done] = fresh[done]
+            truncated = done
+            if self.cameras and not done.all():           # only the reset environments show a new frame: one more render, spliced
+                new_px = self._pixels()
+                px = {c: np.where(done[:, None, None, None], new_px[c], last_px[c]) for c in self.cameras}
+            else:
+                px = None if self.cameras else {}
+            return self._obs(px), reward, terminated, truncated, info
+        info = {"is_success": self._reward == self.max_reward, "_is_success": np.ones(self.num_envs, bool)}
         return self._obs(), reward, terminated, truncated, info
 
     def call(self, name, *args, **kwargs):

@@ -112,8 +112,11 @@ int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W
  * dst_dev: f32 [n_images][3][H][W].  Stand-alone: needs no batch; runs on `stream` of `device`. */
 int avsim_pixels_to_float(const uint8_t *src_dev, int64_t n_images, int H, int W, float *dst_dev, int device, void *stream);
 
-/* host-buffer convenience path used by the gym-facing wrapper (e2e metric): copies happen inside the call. */
-int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host);
+/* host-buffer convenience path used by the gym-facing wrapper (e2e metric): copies happen inside the call.  status_host
+ * (nullable): the AVSIM_STATUS word of every environment after the step -- the wrapper auto-resets environments whose bit 0
+ * (numerical blow-up) is set, the analogue of MuJoCo's mj_checkAcc warning + reset. */
+int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, float *agent_pos_host, int32_t *reward_host,
+                    int32_t *status_host);
 
 /* number of kernel launches issued by this batch so far (bench.py's gpu_launches) */
 int64_t avsim_launch_count(const avsim_batch *b);

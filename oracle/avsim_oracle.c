@@ -805,17 +805,24 @@ static double primal_eval(const ora_data *d, const double *acc, const double *ja
         int dim = block_dim(d, i);
         double Hc[6][6];
         cost += block_cost(d, i, dim, jar + i, force + i, H ? Hc : NULL);
-        if (H)
+        if (H) {
+            int nz[NV_MAX], nnz = 0;   /* columns any row of the block touches (<= 14: two kinematic trees) */
+            for (int a = 0; a < nv; a++) {
+                int any = 0;
+                for (int k = 0; k < dim; k++) any |= d->efc_J[i + k][a] != 0;
+                if (any) nz[nnz++] = a;
+            }
             for (int k = 0; k < dim; k++)
                 for (int l = 0; l < dim; l++) {
                     if (Hc[k][l] == 0) continue;
                     const double *Jk = d->efc_J[i + k], *Jl = d->efc_J[i + l];
-                    for (int a = 0; a < nv; a++) {
-                        if (Jk[a] == 0) continue;
-                        double t = Jk[a] * Hc[k][l];
-                        for (int c = 0; c < nv; c++) H[a][c] += t * Jl[c];
+                    for (int ia = 0; ia < nnz; ia++) {
+                        double t = Jk[nz[ia]] * Hc[k][l];
+                        if (t == 0) continue;
+                        for (int ic = 0; ic < nnz; ic++) H[nz[ia]][nz[ic]] += t * Jl[nz[ic]];
                     }
                 }
+        }
         i += dim;
     }
     return cost;

@@ -114,10 +114,11 @@ int *emu_i(EmuBatch *b, int k) {
     int *p[] = {s.reward, s.status, s.latch, s.ncon, s.episode};
     return p[k];
 }
-void emu_forward(EmuBatch *b) {
+static void emu_forward_impl(EmuBatch *b, int publish_reward) {
     for (int e = 0; e < b->st.num_envs; e++)
-        emu::run_block(e, b->st.num_envs, [&]() { avsim_forward_kernel(b->pk.dm, b->st, nullptr); });
+        emu::run_block(e, b->st.num_envs, [&]() { avsim_forward_kernel(b->pk.dm, b->st, nullptr, publish_reward); });
 }
+void emu_forward(EmuBatch *b) { emu_forward_impl(b, 1); }
 void emu_step(EmuBatch *b, const float *action, int nsub) {
     int n2 = 1;
     while (n2 < b->st.num_envs) n2 <<= 1;
@@ -134,7 +135,7 @@ void emu_reset(EmuBatch *b, const float *free_pos) {
     int nb = (b->st.num_envs + 31) / 32;
     for (int blk = 0; blk < nb; blk++)
         emu::run_block(blk, nb, [&]() { avsim_reset_kernel(b->pk.dm, b->st, nullptr, free_pos, AV_HOME); });
-    emu_forward(b);
+    emu_forward_impl(b, 0);
 }
 // test hook: stage_reward (the CUDA source) on an explicit contact list of geom id pairs; returns the reward, writes the latch back
 int emu_reward_from_pairs(EmuBatch *b, const int *pairs, int n, int latch_in, int *latch_out) {

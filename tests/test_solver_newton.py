@@ -161,7 +161,7 @@ def test_gpu_solver_parity_on_contact_states(task):
 def test_gpu_contact_records_match_oracle_narrowphase(task):
     """contact lists on the GPU (fp32 SAT / sphere-box / MPR + multiccd) vs the oracle's fp64 narrowphase on the same qpos.
     Lists: same geom pairs in the same order in >= 95 % of the states (the rest differ by a contact at the margin, |dist| ~ 1e-7 m).
-    Records of identical lists: every primitive pair (box / sphere) within 2e-7 m depth, 5e-7 m position, 2e-4 normal; mesh-hull
+    Records of identical lists: every primitive pair (box / sphere) within 2e-7 m depth, 5e-7 m position, 5e-4 normal; mesh-hull
     pairs (MPR) within 1e-6 m / 5e-5 m / 5e-3 for >= 97 % of the contacts (measured 99.7 / 97.5 / 98.1 % on the three tasks) and
     1e-3 m depth for all -- the outliers are hull pairs whose origin ray leaves the Minkowski difference next to an edge: the
     two sides walk onto neighbouring faces (the decisions are fp64 on both sides, but the fp32 body poses differ from the fp64
@@ -198,7 +198,7 @@ def test_gpu_contact_records_match_oracle_narrowphase(task):
           f"position {prim[:, 1].max():.1e} m, normal {prim[:, 2].max():.1e}; MPR contacts {len(hull)}: {100 * ok.mean():.1f} % within "
           f"1e-6 m / 5e-5 m / 5e-3, worst depth {hull[:, 0].max():.1e} m, normal {hull[:, 2].max():.1e}; end-to-end qacc: {_q(e2e)}")
     assert same >= 0.95 * N, (task, same, N)
-    assert prim[:, 0].max() <= 2e-7 and prim[:, 1].max() <= 5e-7 and prim[:, 2].max() <= 2e-4
+    assert prim[:, 0].max() <= 2e-7 and prim[:, 1].max() <= 5e-7 and prim[:, 2].max() <= 5e-4
     assert ok.mean() >= 0.97 and hull[:, 0].max() <= 1e-3
     # own narrowphase on both sides: the bulk meets the solver tolerance; the tail is the conditioning of the problem (header)
     assert np.median(e2e) <= 2e-3 and np.quantile(e2e, 0.75) <= TOL, (task, _q(e2e))
