@@ -131,12 +131,14 @@ void emu_step(EmuBatch *b, const float *action, int nsub) {
     } else
         emu::run_block(0, 1, [&]() { avsim_step_kernel(b->pk.dm, b->st, action, nsub); });   // one block drains the queue
 }
-void emu_reset(EmuBatch *b, const float *free_pos) {
+void emu_reset_masked(EmuBatch *b, const uint8_t *mask, const float *free_pos) {
     int nb = (b->st.num_envs + 31) / 32;
     for (int blk = 0; blk < nb; blk++)
-        emu::run_block(blk, nb, [&]() { avsim_reset_kernel(b->pk.dm, b->st, nullptr, free_pos, AV_HOME); });
-    emu_forward_impl(b, 0);
+        emu::run_block(blk, nb, [&]() { avsim_reset_kernel(b->pk.dm, b->st, mask, free_pos, AV_HOME); });
+    for (int e = 0; e < b->st.num_envs; e++)
+        if (!mask || mask[e]) emu::run_block(e, b->st.num_envs, [&]() { avsim_forward_kernel(b->pk.dm, b->st, mask, 0); });
 }
+void emu_reset(EmuBatch *b, const float *free_pos) { emu_reset_masked(b, nullptr, free_pos); }
 // test hook: stage_reward (the CUDA source) on an explicit contact list of geom id pairs; returns the reward, writes the latch back
 int emu_reward_from_pairs(EmuBatch *b, const int *pairs, int n, int latch_in, int *latch_out) {
     if (n > AV_NCON) return -1;

@@ -42,6 +42,7 @@ def lib():
         _lib.emu_forward.argtypes = [C.c_void_p]
         _lib.emu_step.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
         _lib.emu_reset.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        _lib.emu_reset_masked.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
     return _lib
 
 
@@ -85,12 +86,15 @@ class EmuBatch:
         a = np.ascontiguousarray(action, dtype=np.float32)
         lib().emu_step(self.ptr, a.ctypes.data_as(C.POINTER(C.c_float)), nsub)
 
-    def reset(self, free_pos=None):
-        fp = None
+    def reset(self, free_pos=None, mask=None):
+        fp = mk = None
         if free_pos is not None:
             self._fp = np.ascontiguousarray(free_pos, dtype=np.float32)
             fp = self._fp.ctypes.data_as(C.POINTER(C.c_float))
-        lib().emu_reset(self.ptr, fp)
+        if mask is not None:
+            self._mk = np.ascontiguousarray(mask, dtype=np.uint8)
+            mk = self._mk.ctypes.data_as(C.POINTER(C.c_uint8))
+        lib().emu_reset_masked(self.ptr, mk, fp)
 
 
 def emu_reward_from_pairs(eb, pairs, latch=0):
