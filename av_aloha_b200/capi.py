@@ -23,7 +23,7 @@ SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
     "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render", "avsim_set_warmstart",
-    "avsim_pixels_to_float", "avsim_jac", "avsim_set_solver",
+    "avsim_pixels_to_float", "avsim_jac", "avsim_set_solver", "avsim_transform",
 ]
 SOLVER_PGS, SOLVER_NEWTON = 0, 1
 
@@ -75,6 +75,7 @@ def load_library():
     L.avsim_gradik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(GradIKParams), vp, vp]
     L.avsim_fk.argtypes = [vp, i32, vp, i32, vp, vp]
     L.avsim_jac.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.avsim_transform.argtypes = [i32, vp, vp, i32, C.c_double, C.c_double, vp, i32, vp]
     L.avsim_last_error.restype = cp
     L.avsim_stage_cycles.argtypes = [vp, i32, i32]
     _lib = L

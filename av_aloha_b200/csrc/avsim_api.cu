@@ -536,6 +536,16 @@ extern "C" int avsim_gradik(const avsim_model *m, int arm, const float *q, const
     CU(cudaGetLastError());
     return AVSIM_OK;
 }
+extern "C" int avsim_transform(int op, const double *a_dev, const double *b_dev, int n, double p0, double p1, double *out_dev, int device, void *stream) {
+    if (op < 0 || op >= XF_NOPS || n < 0) return fail(AVSIM_ERR_ARG, "avsim_transform: unknown operator or negative count");
+    if (n == 0) return AVSIM_OK;
+    bool two = op == XF_ANGULAR_ERROR || op == XF_LIMIT_POSE || op == XF_WITHIN_POSE;
+    if (!a_dev || !out_dev || (two && !b_dev)) return fail(AVSIM_ERR_ARG, "avsim_transform: null buffer");
+    CU(cudaSetDevice(device));
+    avsim_transform_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(op, a_dev, b_dev, n, p0, p1, out_dev);
+    CU(cudaGetLastError());
+    return AVSIM_OK;
+}
 extern "C" int avsim_fk(const avsim_model *m, int arm, const float *q, int n, float *T_out, void *stream) {
     if (!m || !q || !T_out || arm < 0 || arm > 2 || n < 0) return fail(AVSIM_ERR_ARG, "avsim_fk: bad arguments");
     CU(cudaSetDevice(m->device));

@@ -128,6 +128,58 @@ __device__ inline void spd_solve(double A[7][7], int n, double *b) {
     for (int i = n - 1; i >= 0; i--) { double s = b[i]; for (int k = i + 1; k < n; k++) s -= A[k][i] * b[k]; b[i] = s / A[i][i]; }
 }
 
+// x = pinv(G) b for a symmetric positive SEMI-definite 6x6 G (= J J'), the way np.linalg.pinv treats a rank-deficient
+// Jacobian (reference diff_ik.py:72: directions whose singular value is below the cutoff are dropped, not divided by):
+// cyclic Jacobi eigen-decomposition, eigenvalues below 1e-14 of the largest -- the resolution of the squared spectrum in fp64 --
+// count as zero.  Only taken when the Cholesky path meets a vanishing pivot (at / next to a kinematic singularity).
+__device__ inline void psd6_pinv_apply(double G[7][7], double *b) {
+    double V[6][6];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) V[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; sweep++) {
+        double off = 0;
+        for (int p = 0; p < 6; p++) for (int q = p + 1; q < 6; q++) off += G[p][q] * G[p][q];
+        if (off < 1e-40) break;
+        for (int p = 0; p < 6; p++)
+            for (int q = p + 1; q < 6; q++) {
+                if (fabs(G[p][q]) < 1e-300) continue;
+                double th = (G[q][q] - G[p][p]) / (2.0 * G[p][q]);
+                double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0)), c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 6; k++) { double a = G[k][p], bb = G[k][q]; G[k][p] = c * a - sn * bb; G[k][q] = sn * a + c * bb; }
+                for (int k = 0; k < 6; k++) { double a = G[p][k], bb = G[q][k]; G[p][k] = c * a - sn * bb; G[q][k] = sn * a + c * bb; }
+                for (int k = 0; k < 6; k++) { double a = V[k][p], bb = V[k][q]; V[k][p] = c * a - sn * bb; V[k][q] = sn * a + c * bb; }
+            }
+    }
+    double lmax = 0;
+    for (int i = 0; i < 6; i++) lmax = fmax(lmax, G[i][i]);
+    double x[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 6; i++) {
+        if (!(G[i][i] > 1e-14 * lmax)) continue;
+        double s = 0;
+        for (int k = 0; k < 6; k++) s += V[k][i] * b[k];
+        s /= G[i][i];
+        for (int k = 0; k < 6; k++) x[k] += V[k][i] * s;
+    }
+    for (int k = 0; k < 6; k++) b[k] = x[k];
+}
+// Cholesky solve of the 6x6 system; false (A, b untouched by the caller's copy) when a pivot vanishes
+__device__ inline bool spd6_solve_checked(double A[7][7], double *b) {
+    double dmax = 0;
+    for (int i = 0; i < 6; i++) dmax = fmax(dmax, A[i][i]);
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = A[i][j];
+            for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k];
+            if (i == j) {
+                if (!(s > 1e-12 * dmax)) return false;
+                A[i][j] = sqrt(s);
+            } else
+                A[i][j] = s / A[j][j];
+        }
+    for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= A[i][k] * b[k]; b[i] = s / A[i][i]; }
+    for (int i = 5; i >= 0; i--) { double s = b[i]; for (int k = i + 1; k < 6; k++) s -= A[k][i] * b[k]; b[i] = s / A[i][i]; }
+    return true;
+}
+
 __global__ void avsim_fk_kernel(DevModel m, int arm, const float *__restrict__ q, int n, float *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -201,7 +253,12 @@ __global__ void avsim_diffik_kernel(DevModel m, int arm, const float *__restrict
             Jz[i] = s;
             for (int j = 0; j < 6; j++) { double g = 0; for (int k = 0; k < nd; k++) g += J[i][k] * J[j][k]; G[i][j] = g; }
         }
-        spd_solve(G, 6, Jz);
+        {
+            double G2[7][7], Jz2[7];
+            for (int i = 0; i < 6; i++) { Jz2[i] = Jz[i]; for (int j = 0; j < 6; j++) G2[i][j] = G[i][j]; }
+            if (spd6_solve_checked(G2, Jz2)) { for (int i = 0; i < 6; i++) Jz[i] = Jz2[i]; }
+            else psd6_pinv_apply(G, Jz);     // rank-deficient Jacobian: thresholded pseudo-inverse, finite like np.linalg.pinv
+        }
         for (int k = 0; k < nd; k++) {
             double s = 0;
             for (int i = 0; i < 6; i++) s += J[i][k] * Jz[i];
@@ -226,6 +283,40 @@ __device__ inline void ik_mat2quat_xyzw(const double *R, double *q) {
     if (w < 0) { w = -w; x = -x; y = -y; z = -z; }
     double nn = sqrt(w * w + x * x + y * y + z * z);
     q[0] = x / nn; q[1] = y / nn; q[2] = z / nn; q[3] = w / nn;
+}
+// quat2axisangle / axisangle2quat (transform_utils.py:82-133) on (x,y,z,w); np.isclose(x, 0) = |x| <= 1e-8
+__device__ inline void ik_quat2axisangle(const double *q, double *rv) {
+    double wq = fmin(fmax(q[3], -1.0), 1.0), den = sqrt(1.0 - wq * wq);
+    rv[0] = rv[1] = rv[2] = 0;
+    if (den > 1e-8) { double sc = 2.0 * acos(wq) / den; rv[0] = q[0] * sc; rv[1] = q[1] * sc; rv[2] = q[2] * sc; }
+}
+__device__ inline void ik_axisangle2quat(const double *v, double *q) {
+    double a = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    q[0] = q[1] = q[2] = 0; q[3] = 1;
+    if (a > 1e-8) { double s = sin(a / 2) / a; q[0] = v[0] * s; q[1] = v[1] * s; q[2] = v[2] * s; q[3] = cos(a / 2); }
+}
+// limit_pose (transform_utils.py:263-287): the target (tp, tR) is pulled to within max_pos / max_rot of the current pose, in place
+__device__ inline void ik_limit_pose(const double *cp, const double *cR, double *tp, double *tR, double max_pos, double max_rot) {
+    double d[3] = {tp[0] - cp[0], tp[1] - cp[1], tp[2] - cp[2]};
+    double dn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (dn > max_pos) for (int k = 0; k < 3; k++) d[k] = d[k] / dn * max_pos;
+    for (int k = 0; k < 3; k++) tp[k] = cp[k] + d[k];
+    double Rrel[9];
+    for (int i = 0; i < 3; i++)   // target @ inv(current) = target @ current^T
+        for (int j = 0; j < 3; j++) Rrel[3 * i + j] = tR[3 * i] * cR[3 * j] + tR[3 * i + 1] * cR[3 * j + 1] + tR[3 * i + 2] * cR[3 * j + 2];
+    double qr[4], rv[3];
+    ik_mat2quat_xyzw(Rrel, qr);
+    ik_quat2axisangle(qr, rv);
+    double ang = sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+    if (ang > max_rot) {
+        double sc = max_rot / ang, v[3] = {rv[0] * sc, rv[1] * sc, rv[2] * sc}, ql[4];
+        ik_axisangle2quat(v, ql);
+        double Rl[9], Rn[9];
+        ik_quat2mat_xyzw(ql, Rl);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rl[3 * i] * cR[j] + Rl[3 * i + 1] * cR[3 + j] + Rl[3 * i + 2] * cR[6 + j];
+        for (int i = 0; i < 9; i++) tR[i] = Rn[i];
+    }
 }
 __device__ inline double gradik_cost(const ArmTab &A, const GradIKParams &P, const double *q, const double *q_start,
                                      const double *tp, const double *tR, const double *cw, const double *centers) {
@@ -264,30 +355,7 @@ __global__ void avsim_gradik_kernel(DevModel m, int arm, const float *__restrict
     // limit_pose (transform_utils.py:263-287)
     T44 T;
     ik_fk(A, q0, T);
-    {
-        double d[3] = {tp[0] - T.p[0], tp[1] - T.p[1], tp[2] - T.p[2]};
-        double dn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        if (dn > (double)P.max_pos_diff) for (int k = 0; k < 3; k++) d[k] = d[k] / dn * (double)P.max_pos_diff;
-        for (int k = 0; k < 3; k++) tp[k] = T.p[k] + d[k];
-        double Rrel[9];
-        for (int i = 0; i < 3; i++)   // target @ inv(current) = target @ current^T
-            for (int j = 0; j < 3; j++) Rrel[3 * i + j] = tR[3 * i] * T.R[3 * j] + tR[3 * i + 1] * T.R[3 * j + 1] + tR[3 * i + 2] * T.R[3 * j + 2];
-        double qr[4], rv[3] = {0, 0, 0};
-        ik_mat2quat_xyzw(Rrel, qr);
-        double wq = fmin(fmax(qr[3], -1.0), 1.0), den = sqrt(1.0 - wq * wq);
-        if (den > 1e-8) { double sc = 2.0 * acos(wq) / den; rv[0] = qr[0] * sc; rv[1] = qr[1] * sc; rv[2] = qr[2] * sc; }
-        double ang = sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
-        if (ang > (double)P.max_rot_diff) {
-            double sc = (double)P.max_rot_diff / ang, v[3] = {rv[0] * sc, rv[1] * sc, rv[2] * sc};
-            double a = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), ql[4] = {0, 0, 0, 1};
-            if (a > 1e-8) { double s = sin(a / 2) / a; ql[0] = v[0] * s; ql[1] = v[1] * s; ql[2] = v[2] * s; ql[3] = cos(a / 2); }
-            double Rl[9], Rn[9];
-            ik_quat2mat_xyzw(ql, Rl);
-            for (int i = 0; i < 3; i++)
-                for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rl[3 * i] * T.R[j] + Rl[3 * i + 1] * T.R[3 + j] + Rl[3 * i + 2] * T.R[6 + j];
-            for (int i = 0; i < 9; i++) tR[i] = Rn[i];
-        }
-    }
+    ik_limit_pose(T.p, T.R, tp, tR, (double)P.max_pos_diff, (double)P.max_rot_diff);
     double step = (double)P.step_size;
     double init_cost = gradik_cost(A, P, q0, q0, tp, tR, cw, centers);
     double grad[7], working[7], local[7], best[7];
@@ -329,4 +397,67 @@ __global__ void avsim_gradik_kernel(DevModel m, int arm, const float *__restrict
         previous_cost = local_cost;
     }
     for (int k = 0; k < nd; k++) q_out[(size_t)idx * nd + k] = (float)(q0[k] + (double)P.joint_p * (best[k] - q0[k]));
+}
+
+// ---- transform_utils.py primitives as a batched operator (fp64 in / out, one thread per item): the callable mirror of the
+// helpers the two controllers use internally, so that each can be checked on its own against the reference's numba functions
+// (tests/test_transform_utils.py) and used by host code on whole batches of poses (av_aloha_b200/transform_utils.py).
+enum { XF_MAT2QUAT = 0, XF_QUAT2MAT, XF_QUAT2AXISANGLE, XF_AXISANGLE2QUAT, XF_ANGULAR_ERROR, XF_LIMIT_POSE, XF_EXP2MAT, XF_ADJOINT,
+       XF_WITHIN_POSE, XF_NOPS };
+__global__ void avsim_transform_kernel(int op, const double *__restrict__ a, const double *__restrict__ b, int n, double p0, double p1,
+                                       double *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (op) {
+    case XF_MAT2QUAT: ik_mat2quat_xyzw(a + 9 * (size_t)i, out + 4 * (size_t)i); break;
+    case XF_QUAT2MAT: ik_quat2mat_xyzw(a + 4 * (size_t)i, out + 9 * (size_t)i); break;
+    case XF_QUAT2AXISANGLE: ik_quat2axisangle(a + 4 * (size_t)i, out + 3 * (size_t)i); break;
+    case XF_AXISANGLE2QUAT: ik_axisangle2quat(a + 3 * (size_t)i, out + 4 * (size_t)i); break;
+    case XF_ANGULAR_ERROR: ik_ang_err(a + 9 * (size_t)i, b + 9 * (size_t)i, out + 3 * (size_t)i); break;
+    case XF_LIMIT_POSE: {   // a = current [pos 3 | mat 9], b = target [pos 3 | mat 9], p0 = max_pos_diff, p1 = max_rot_diff
+        double tp[3], tR[9];
+        for (int k = 0; k < 3; k++) tp[k] = b[12 * (size_t)i + k];
+        for (int k = 0; k < 9; k++) tR[k] = b[12 * (size_t)i + 3 + k];
+        ik_limit_pose(a + 12 * (size_t)i, a + 12 * (size_t)i + 3, tp, tR, p0, p1);
+        for (int k = 0; k < 3; k++) out[12 * (size_t)i + k] = tp[k];
+        for (int k = 0; k < 9; k++) out[12 * (size_t)i + 3 + k] = tR[k];
+        break;
+    }
+    case XF_EXP2MAT: {      // a = [w 3 | v 3 | theta]; |w| = 1, or w = 0 and |v| = 1 (pure translation)
+        const double *x = a + 7 * (size_t)i;
+        T44 T;
+        if (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] <= 1e-16) {
+            for (int k = 0; k < 9; k++) T.R[k] = (k % 4) == 0;
+            for (int k = 0; k < 3; k++) T.p[k] = x[3 + k] * x[6];
+        } else
+            exp2mat(x, x + 3, x[6], T);
+        double *o = out + 16 * (size_t)i;
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) o[4 * r + c] = T.R[3 * r + c]; o[4 * r + 3] = T.p[r]; }
+        o[12] = o[13] = o[14] = 0; o[15] = 1;
+        break;
+    }
+    case XF_ADJOINT: {      // a = 4x4 T -> 6x6 [[R 0] [skew(p) R, R]]
+        const double *T = a + 16 * (size_t)i;
+        double *o = out + 36 * (size_t)i;
+        double R[9], p[3] = {T[3], T[7], T[11]};
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = T[4 * r + c];
+        double S[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0};
+        for (int k = 0; k < 36; k++) o[k] = 0;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                o[6 * r + c] = R[3 * r + c];
+                o[6 * (r + 3) + c + 3] = R[3 * r + c];
+                o[6 * (r + 3) + c] = S[3 * r] * R[c] + S[3 * r + 1] * R[3 + c] + S[3 * r + 2] * R[6 + c];
+            }
+        break;
+    }
+    case XF_WITHIN_POSE: {  // a = current [pos | mat], b = target [pos | mat], p0 / p1 = position / rotation threshold
+        const double *c = a + 12 * (size_t)i, *t = b + 12 * (size_t)i;
+        double d[3] = {t[0] - c[0], t[1] - c[1], t[2] - c[2]}, e[3];
+        ik_ang_err(t + 3, c + 3, e);
+        out[i] = (sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) < p0 && sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) < p1) ? 1.0 : 0.0;
+        break;
+    }
+    default: break;
+    }
 }

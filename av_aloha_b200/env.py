@@ -466,10 +466,51 @@ class GuidedVisionVectorEnv:
         self._agent[:] = self._batch.get(capi.AGENT_POS).cpu().numpy()
         self._reward[:] = self._batch.get(capi.REWARD).cpu().numpy()
         self._elapsed += 1
-        obs = self._obs()
-        obs["qvel"] = self._batch.get(capi.QVEL).cpu().numpy().astype(np.float64)
-        obs["ctrl"] = self._batch.get(capi.CTRL).cpu().numpy().astype(np.float64)
-        return obs, self._reward.astype(np.float64), np.zeros(self.num_envs, bool), np.zeros(self.num_envs, bool), {}
+        # the teleop env reports reward 0 / terminated False / truncated False on every step (sim_env.py:306-311)
+        return self.get_teleop_obs(), np.zeros(self.num_envs), np.zeros(self.num_envs, bool), np.zeros(self.num_envs, bool), {}
+
+    # the teleop environment's observation (reference data_collection_scripts/sim_env.py:160-218), batched over the leading axis
+    TELEOP_CAMERAS = {"zed_cam": ("zed_cam_left", "zed_cam_right"), "cam_left_wrist": ("wrist_cam_left",),
+                      "cam_right_wrist": ("wrist_cam_right",), "cam_high": ("overhead_cam",), "cam_low": ("worms_eye_cam",)}
+
+    def get_teleop_obs(self, cameras=()):
+        """{'joints': {'position' [B,21], 'velocity' [B,21]}, 'qpos' [B,nq], 'control' [B,21], 'poses': {'left','right','middle'
+        [B,7] = position + wxyz quaternion of FK(ctrl)}, 'images': {...}} -- gripper position / ctrl normalised to [0, 1], gripper
+        velocity divided by the ctrl range, the commanded (ctrl) end-effector poses rather than the measured ones, 'zed_cam' = the
+        two 720 x 720 eye views side by side, the other cameras 480 x 640 (sim_env.py:160-218)."""
+        from . import kinematics, transform_utils
+
+        if self.num_arms != 3:
+            raise ValueError("the teleop observation covers all three arms")
+        m = self._model
+        qpos = self._batch.get(capi.QPOS).cpu().numpy().astype(np.float64)
+        qvel = self._batch.get(capi.QVEL).cpu().numpy().astype(np.float64)
+        ctrl = self._batch.get(capi.CTRL).cpu().numpy().astype(np.float64)
+        qadr, dadr = m.table("obs_qadr"), m.table("act_dof")
+        lo, hi = m.table("act_ctrl_lo").astype(np.float64), m.table("act_ctrl_hi").astype(np.float64)
+        pos, vel, con = qpos[:, qadr[:21]], qvel[:, dadr[:21]], ctrl[:, :21].copy()
+        for g in (6, 13):
+            pos[:, g] = (pos[:, g] - lo[g]) / (hi[g] - lo[g])
+            vel[:, g] = vel[:, g] / (hi[g] - lo[g])
+            con[:, g] = (con[:, g] - lo[g]) / (hi[g] - lo[g])
+        poses = {}
+        for arm, sl in (("left", slice(0, 6)), ("right", slice(7, 13)), ("middle", slice(14, 21))):
+            if not hasattr(self, "_fk"):
+                self._fk = {}
+            fk = self._fk.setdefault(arm, kinematics.create_fk_fn(m, arm))
+            T = np.asarray(fk(ctrl[:, sl])).reshape(-1, 4, 4)
+            quat = np.asarray(transform_utils.mat2quat(np.ascontiguousarray(T[:, :3, :3]))).reshape(-1, 4)
+            poses[arm] = np.concatenate([T[:, :3, 3], transform_utils.xyzw_to_wxyz(quat)], axis=1)
+        images = {}
+        for cam in cameras:
+            key = next((k for k in self.TELEOP_CAMERAS if k in cam), None)
+            if key is None:
+                raise NotImplementedError(f"Camera {cam} not implemented")
+            ids = _camera_ids(self.task, self.num_arms, list(self.TELEOP_CAMERAS[key]))
+            h, w = (720, 720) if key == "zed_cam" else (480, 640)
+            img = self._batch.render(ids, h, w).cpu().numpy()
+            images[key] = np.concatenate([img[:, 0], img[:, 1]], axis=2) if key == "zed_cam" else img[:, 0]
+        return {"joints": {"position": pos, "velocity": vel}, "qpos": qpos, "control": con, "poses": poses, "images": images}
 
     # -- device-resident variants (SURVEY.md 8 f1): nothing below copies to the host.  The unchanged lerobot loop pays, per
     # step, a D2H of every frame plus a CPU uint8 -> fp32 cast (eval.py:150, utils.py:37-50); a policy that lives on the same

@@ -30,6 +30,48 @@ def _arm(arm):
     return ARM_INDEX[arm] if isinstance(arm, str) else int(arm)
 
 
+EEF_SITE = {"left": "left_gripper_control", "right": "right_gripper_control", "middle": "middle_zed_camera_center"}   # aloha_sim.xml:160,249,350
+
+
+def _name(x):
+    """name of an MJCF element the way the reference passes it (a dm_control mjcf element has .name / .full_identifier)"""
+    return x if isinstance(x, str) else (getattr(x, "name", None) or getattr(x, "full_identifier", None) or str(x))
+
+
+def _resolve(physics, joints, eef_site=None):
+    """(capi.Model, arm index) from the reference's constructor arguments.
+
+    The reference builds its controllers from a dm_control ``physics``, the list of MJCF joint elements of one arm and that
+    arm's end-effector site (data_collection_scripts/sim_env.py:89-138: ``DiffIK(physics=..., joints=self._middle_joints,
+    actuators=..., eef_site=self._middle_eef_site, ...)``).  Here ``physics`` is whatever owns the compiled model -- a
+    ``capi.Model``, a ``capi.Batch``, or one of this package's environments -- and ``joints`` are the same joint elements or
+    their names; the arm is read off the names ("left_waist" ... / "right_..." / "middle_...").  The kernels carry
+    product-of-exponentials tables for exactly the three arm chains (first 6, 6, 7 joints), which is what every call site of the
+    reference asks for; anything else raises.  For this repo's own callers ``joints`` may also be an arm name / index.
+    """
+    model = physics if isinstance(physics, capi.Model) else (getattr(physics, "_model", None) or getattr(physics, "model", None))
+    if not isinstance(model, capi.Model):
+        raise TypeError("physics must be a capi.Model, a capi.Batch or an environment of this package")
+    if isinstance(joints, (str, int, np.integer)):
+        return model, _arm(joints)
+    names = [_name(j) for j in joints]
+    if not names:
+        raise ValueError("empty joint list")
+    arm_name = names[0].split("_")[0]
+    if arm_name not in ARM_INDEX:
+        raise ValueError(f"cannot tell the arm from joint {names[0]!r}")
+    arm = ARM_INDEX[arm_name]
+    from . import model_io
+    task = {0: "insert_peg", 1: "slot_insertion", 2: "sew_needle", 3: "tube_transfer", 4: "hook_package"}[model.task_id]
+    all_j = [n for n in model_io.load_names(task, model.num_arms)["joint"] if n.startswith(arm_name + "_")]
+    ndof = (6, 6, 7)[arm]
+    if names != all_j[:ndof]:
+        raise ValueError(f"IK tables exist for the {arm_name} arm chain {all_j[:ndof]}, got {names}")
+    if eef_site is not None and _name(eef_site) != EEF_SITE[arm_name]:
+        raise ValueError(f"end-effector site of the {arm_name} arm is {EEF_SITE[arm_name]!r}, got {_name(eef_site)!r}")
+    return model, arm
+
+
 class _Controller:
     def __init__(self, model: capi.Model, arm):
         self.model, self.arm = model, _arm(arm)
@@ -60,9 +102,13 @@ class _Controller:
 class DiffIK(_Controller):
     """Damped-least-squares differential IK with a null-space posture term (reference diff_ik.py:51-85)."""
 
-    def __init__(self, model, arm="middle", k_pos=0.9, k_ori=0.9, damping=1.0e-4, k_null=DIFFIK_SIM["k_null"],
-                 q0=DIFFIK_SIM["q0"], max_angvel=3.14, integration_dt=0.04, iterations=10):
+    def __init__(self, physics, joints="middle", actuators=None, eef_site=None, k_pos=0.9, k_ori=0.9, damping=1.0e-4,
+                 k_null=DIFFIK_SIM["k_null"], q0=DIFFIK_SIM["q0"], max_angvel=3.14, integration_dt=0.04, iterations=10):
+        """Reference signature (diff_ik.py:8-22): ``DiffIK(physics, joints, actuators, eef_site, k_pos, k_ori, damping, k_null,
+        q0, max_angvel, integration_dt, iterations)``; see `_resolve` for what physics / joints may be."""
+        model, arm = _resolve(physics, joints, eef_site)
         super().__init__(model, arm)
+        self.physics, self.joints, self.actuators, self.eef_site = physics, joints, actuators, eef_site
         p = capi.DiffIKParams()
         p.k_pos, p.k_ori, p.damping, p.max_angvel, p.integration_dt = k_pos, k_ori, damping, max_angvel, integration_dt
         p.iterations = int(iterations)
@@ -82,11 +128,16 @@ class DiffIK(_Controller):
 class GradIK(_Controller):
     """Finite-difference gradient-descent IK with a secant line step (reference grad_ik.py:8-99)."""
 
-    def __init__(self, model, arm="left", step_size=0.0001, min_cost_delta=1.0e-12, max_iterations=50,
-                 position_weight=500.0, rotation_weight=100.0, joint_center_weight=GRADIK_SIM["joint_center_weight"],
+    def __init__(self, physics, joints="left", actuators=None, eef_site=None, step_size=0.0001, min_cost_delta=1.0e-12,
+                 max_iterations=50, position_weight=500.0, rotation_weight=100.0,
+                 joint_center_weight=GRADIK_SIM["joint_center_weight"],
                  joint_displacement_weight=GRADIK_SIM["joint_displacement_weight"], position_threshold=0.001,
-                 rotation_threshold=0.001, max_pos_diff=0.1, max_rot_diff=0.1, joint_p=0.1):
+                 rotation_threshold=0.001, max_pos_diff=0.1, max_rot_diff=0.3, joint_p=0.1):
+        """Reference signature and defaults (grad_ik.py:101-121): ``GradIK(physics, joints, actuators, eef_site, step_size=1e-4,
+        ..., max_pos_diff=0.1, max_rot_diff=0.3, joint_p=0.1)``."""
+        model, arm = _resolve(physics, joints, eef_site)
         super().__init__(model, arm)
+        self.physics, self.joints, self.actuators, self.eef_site = physics, joints, actuators, eef_site
         from . import model_io  # joint ranges of the arm (reference grad_ik.py:134-137 divides by the half range)
 
         p = capi.GradIKParams()
@@ -110,9 +161,10 @@ class GradIK(_Controller):
         return self._ret(out, single, as_np)
 
 
-def create_fk_fn(model, arm):
-    """``fk(theta) -> 4x4`` (or [n,4,4]) end-effector site pose by product of exponentials (reference kinematics.py:7-26)."""
-    a = _arm(arm)
+def create_fk_fn(physics, joints, eef_site=None):
+    """``fk(theta) -> 4x4`` (or [n,4,4]) end-effector site pose by product of exponentials.  Reference signature
+    (kinematics.py:7): ``create_fk_fn(physics, joints, eef_site)``; `joints` may also be an arm name / index."""
+    model, a = _resolve(physics, joints, eef_site)
     ndof = (6, 6, 7)[a]
 
     def forward_kinematics(theta):
@@ -133,10 +185,10 @@ def create_fk_fn(model, arm):
     return forward_kinematics
 
 
-def create_jac_fn(model, arm):
-    """``jacobian(theta) -> 6 x n`` (or [N, 6, n]) space Jacobian of the end-effector site, rows [v; w] (reference
-    kinematics.py:28-52; what DiffIK iterates on)."""
-    a = _arm(arm)
+def create_jac_fn(physics, joints):
+    """``jacobian(theta) -> 6 x n`` (or [N, 6, n]) space Jacobian of the end-effector site, rows [v; w].  Reference signature
+    (kinematics.py:28): ``create_jac_fn(physics, joints)``; what DiffIK iterates on."""
+    model, a = _resolve(physics, joints)
     ndof = (6, 6, 7)[a]
 
     def jacobian(theta):
@@ -168,13 +220,25 @@ def _angular_error(desired, current):
     return 0.5 * sum(np.cross(current[..., :3, k], desired[..., :3, k]) for k in range(3))
 
 
-def create_safety_fn(model, arm, xyz_bounds, joint_limit_safety_margin=0.01, joint_tracking_safety_margin=1.0,
-                     eef_pos_tracking_safety_margin=0.2, eef_rot_tracking_safety_margin=3.0):
+def create_safety_fn(physics, joints, *args, **kwargs):
     """``safety_fn(qpos, ctrl, Taction=None) -> (ok, message)`` for one arm, or -- with a leading batch axis on qpos / ctrl
-    (/ Taction) -- ``(ok bool[n], code int[n])`` with ``SAFETY_MESSAGES[code]`` the reference's message."""
-    a = _arm(arm)
-    return _make_safety_fn(create_fk_fn(model, a), model.ik_range(a), xyz_bounds, joint_limit_safety_margin,
-                           joint_tracking_safety_margin, eef_pos_tracking_safety_margin, eef_rot_tracking_safety_margin)
+    (/ Taction) -- ``(ok bool[n], code int[n])`` with ``SAFETY_MESSAGES[code]`` the reference's message.  Reference signature
+    (kinematics.py:104): ``create_safety_fn(physics, joints, eef_site, xyz_bounds, joint_limit_safety_margin=0.01,
+    joint_tracking_safety_margin=1.0, eef_pos_tracking_safety_margin=0.2, eef_rot_tracking_safety_margin=3.0)``; this repo's
+    own form drops eef_site: ``create_safety_fn(model, arm, xyz_bounds, ...)``."""
+    names = ("xyz_bounds", "joint_limit_safety_margin", "joint_tracking_safety_margin", "eef_pos_tracking_safety_margin",
+             "eef_rot_tracking_safety_margin")
+    eef_site = kwargs.pop("eef_site", None)
+    args = list(args)
+    if args and not isinstance(joints, (str, int, np.integer)) and np.ndim(args[0]) == 0:
+        eef_site = args.pop(0)                     # reference order: the site comes before the bounds
+    kw = dict(joint_limit_safety_margin=0.01, joint_tracking_safety_margin=1.0, eef_pos_tracking_safety_margin=0.2,
+              eef_rot_tracking_safety_margin=3.0)
+    kw.update(dict(zip(names, args)))
+    kw.update(kwargs)
+    model, a = _resolve(physics, joints, eef_site)
+    return _make_safety_fn(create_fk_fn(model, a), model.ik_range(a), kw["xyz_bounds"], kw["joint_limit_safety_margin"],
+                           kw["joint_tracking_safety_margin"], kw["eef_pos_tracking_safety_margin"], kw["eef_rot_tracking_safety_margin"])
 
 
 def _make_safety_fn(fk_fn, joint_range, xyz_bounds, joint_limit_safety_margin, joint_tracking_safety_margin,

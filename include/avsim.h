@@ -148,6 +148,22 @@ int avsim_fk(const avsim_model *m, int arm, const float *q_dev, int n, float *T_
 /* space Jacobian of the same site, rows re-ordered to [v; w] (kinematics.py:28-52): out f32[n][6][ndof] (ndof = 6, 6, 7) */
 int avsim_jac(const avsim_model *m, int arm, const float *q_dev, int n, float *J_out_dev, void *stream);
 
+/* ---- SO(3) / SE(3) helpers of the reference's transform_utils.py (data_collection_scripts/transform_utils.py), batched:
+ * n items, fp64 in and out (the reference computes in float64), quaternions (x, y, z, w) like the reference's internals.
+ *   AVSIM_XF_MAT2QUAT          a[9]            -> out[4]    mat2quat 9-49 (w >= 0)
+ *   AVSIM_XF_QUAT2MAT          a[4]            -> out[9]    quat2mat 52-79, including its float32 round trip
+ *   AVSIM_XF_QUAT2AXISANGLE    a[4]            -> out[3]    quat2axisangle 82-106
+ *   AVSIM_XF_AXISANGLE2QUAT    a[3]            -> out[4]    axisangle2quat 108-133
+ *   AVSIM_XF_ANGULAR_ERROR     a[9] desired, b[9] current -> out[3]   angular_error 183-194
+ *   AVSIM_XF_LIMIT_POSE        a[12] current (pos | mat), b[12] target, p0 = max_pos_diff, p1 = max_rot_diff -> out[12]   limit_pose 263-287
+ *   AVSIM_XF_EXP2MAT           a[7] (w | v | theta)        -> out[16]  exp2mat 239-261
+ *   AVSIM_XF_ADJOINT           a[16]           -> out[36]   adjoint 289-301
+ *   AVSIM_XF_WITHIN_POSE       a[12], b[12], p0 / p1 = position / rotation threshold -> out[1] (1.0 / 0.0)   within_pose_threshold 196-201 */
+enum avsim_xf_op { AVSIM_XF_MAT2QUAT = 0, AVSIM_XF_QUAT2MAT, AVSIM_XF_QUAT2AXISANGLE, AVSIM_XF_AXISANGLE2QUAT, AVSIM_XF_ANGULAR_ERROR,
+                   AVSIM_XF_LIMIT_POSE, AVSIM_XF_EXP2MAT, AVSIM_XF_ADJOINT, AVSIM_XF_WITHIN_POSE };
+int avsim_transform(int op, const double *a_dev, const double *b_dev, int n, double p0, double p1, double *out_dev, int device,
+                    void *stream);
+
 const char *avsim_last_error(void);
 
 #ifdef __cplusplus

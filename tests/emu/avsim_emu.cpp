@@ -171,6 +171,10 @@ void emu_diffik(EmuBatch *b, int arm, const float *q, const float *pos, const fl
     int nb = (n + 31) / 32;
     for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_diffik_kernel(b->pk.dm, arm, q, pos, quat, n, *p, out); });
 }
+void emu_transform(int op, const double *a, const double *b, int n, double p0, double p1, double *out) {
+    int nb = (n + 31) / 32;
+    for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_transform_kernel(op, a, b, n, p0, p1, out); });
+}
 void emu_gradik(EmuBatch *b, int arm, const float *q, const float *pos, const float *quat, int n, const GradIKParams *p, float *out) {
     int nb = (n + 31) / 32;
     for (int blk = 0; blk < nb; blk++) emu::run_block(blk, nb, [&]() { avsim_gradik_kernel(b->pk.dm, arm, q, pos, quat, n, *p, out); });

@@ -153,3 +153,18 @@ def emu_gradik(eb, arm, q, pos, quat, params):
     out = np.zeros_like(q)
     L.emu_gradik(eb.ptr, arm, _fp(q), _fp(pos), _fp(quat), len(q), C.byref(params), _fp(out))
     return out
+
+
+def emu_transform(op, a, wa, wout, b=None, p0=0.0, p1=0.0):
+    """avsim_transform_kernel (the CUDA source, emulated) on n items: a [n, wa] (b [n, wb]) -> [n, wout] float64"""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.emu_transform.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double, C.c_double, dp]
+    a = np.ascontiguousarray(a, np.float64).reshape(-1, wa)
+    out = np.zeros((len(a), wout))
+    bp = None
+    if b is not None:
+        b = np.ascontiguousarray(b, np.float64).reshape(len(a), -1)
+        bp = b.ctypes.data_as(dp)
+    L.emu_transform(op, a.ctypes.data_as(dp), bp, len(a), p0, p1, out.ctypes.data_as(dp))
+    return out

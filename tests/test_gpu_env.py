@@ -120,7 +120,7 @@ def test_device_reset_stays_in_reference_ranges_and_masks():
 def test_teleop_pose_action_step_tracks_targets():
     """sim_env.py:277-312: pose actions -> GradIK / DiffIK -> joint targets -> 20 substeps; holding the home poses keeps
     the arms at home, and moving the left target 3 cm moves the left end effector towards it"""
-    from av_aloha_b200 import env, kinematics, model_io
+    from av_aloha_b200 import capi, env, kinematics, model_io
 
     B = 4
     v = env.GuidedVisionVectorEnv("slot_insertion", B, num_arms=3, cameras=[], seed=1)
@@ -136,19 +136,39 @@ def test_teleop_pose_action_step_tracks_targets():
     act = np.concatenate([poses["left"][0], poses["left"][1], [0.0], poses["right"][0], poses["right"][1], [0.0],
                           poses["middle"][0], poses["middle"][1]])
     acts = np.tile(act, (B, 1))
-    for _ in range(3):
-        obs, rew, term, trunc, info = v.step_pose(acts)
-    assert obs["agent_pos"].shape == (B, 21) and obs["qvel"].shape[0] == B and obs["ctrl"].shape == (B, 21)
-    assert np.abs(obs["agent_pos"][:, :6] - np.array(home["left"])).max() < 0.02
-    assert np.abs(obs["agent_pos"][:, 14:21] - np.array(home["middle"])).max() < 0.05
-    assert np.abs(obs["agent_pos"][:, [6, 13]] - 1.0).max() < 0.05        # g = 0 -> ctrl = unnorm(1): open
+    q_before = v._batch.get(capi.QPOS).cpu().numpy()
+    obs, rew, term, trunc, info = v.step_pose(acts)
+    # observation contract of the teleop env (reference sim_env.py:206-218)
+    assert set(obs) == {"joints", "qpos", "control", "poses", "images"} and set(obs["joints"]) == {"position", "velocity"}
+    assert obs["joints"]["position"].shape == (B, 21) and obs["joints"]["velocity"].shape == (B, 21)
+    assert obs["qpos"].shape == (B, v._model.nq) and obs["control"].shape == (B, 21)
+    assert all(obs["poses"][k].shape == (B, 7) for k in ("left", "right", "middle")) and obs["images"] == {}
+    assert (rew == 0).all() and not term.any() and not trunc.any()
+    # wiring of the controllers: ctrl = GradIK(qpos[:6]) / DiffIK(qpos_middle), grippers ctrl = unnorm(1 - g) reported normalised
+    qadr = v._model.table("obs_qadr")
+    for arm, sl, ctl in (("left", slice(0, 6), v._ik[0]), ("right", slice(7, 13), v._ik[1]), ("middle", slice(14, 21), v._ik[2])):
+        want = ctl.run(q_before[:, qadr[sl]].astype(np.float64), np.tile(poses[arm][0], (B, 1)), np.tile(poses[arm][1], (B, 1)))
+        assert np.abs(obs["control"][:, sl] - want).max() <= 1e-6, arm
+        # 'poses' = FK of the COMMANDED joints as position + wxyz quaternion
+        T = kinematics.create_fk_fn(v._model, arm)(obs["control"][:, sl])
+        assert np.abs(obs["poses"][arm][:, :3] - T[:, :3, 3]).max() <= 1e-6
+        assert np.abs(np.abs(obs["poses"][arm][:, 3:] @ poses[arm][1]) - 1.0).max() <= 1e-3       # same orientation as the target
+    assert np.abs(obs["control"][:, [6, 13]] - 1.0).max() <= 1e-6               # g = 0 -> ctrl = unnorm(1): open
+    for _ in range(2):
+        obs, *_ = v.step_pose(acts)
+    pos = obs["joints"]["position"]
+    assert np.abs(pos[:, :6] - np.array(home["left"])).max() < 0.02
+    assert np.abs(pos[:, 14:21] - np.array(home["middle"])).max() < 0.05
+    assert np.abs(pos[:, [6, 13]] - 1.0).max() < 0.05
     acts2 = acts.copy()
     acts2[:, 2] += 0.03                                                     # raise the left target by 3 cm
     for _ in range(15):
         obs, *_ = v.step_pose(acts2)
-    T = kinematics.create_fk_fn(v._model, "left")(obs["agent_pos"][:, :6])
+    T = kinematics.create_fk_fn(v._model, "left")(obs["joints"]["position"][:, :6])
     dz = T[:, 2, 3] - poses["left"][0][2]            # GradIK trades pose error against joint displacement: it gets part way
     assert (dz > 0.008).all() and (dz < 0.035).all(), dz
+    img = v.get_teleop_obs(cameras=["zed_cam", "cam_high"])["images"]
+    assert img["zed_cam"].shape == (B, 720, 1440, 3) and img["cam_high"].shape == (B, 480, 640, 3) and img["zed_cam"].dtype == np.uint8
     v.close()
 
 
@@ -195,4 +215,54 @@ def test_config1_insert_peg_two_arms_plumbing():
     assert np.abs(obs["agent_pos"] - o.agent_pos()[:14]).max() <= 1e-4          # 400 steps = 8000 substeps next to the oracle
     assert np.abs(obs["agent_pos"] - at300).max() <= 1e-5                        # settled: holds the pose
     assert worst < 5e-2, worst                                                   # PD sag, not drift
+    e.close()
+
+
+def test_set_qpos_then_get_reward_reads_the_forward_state():
+    """reference scripts/check_dataset_reward.py:35-38 / test_sim_reward.py:30-33: set_qpos(q); get_reward() -- the reward of the
+    contacts of the state just set (physics.forward), not the one of the last step"""
+    import os
+    from av_aloha_b200 import env, model_io
+    from oracle.oracle import OracleEnv, OracleModel
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "contact_states.npz"))
+    om = OracleModel(model_io.model_path("slot_insertion", 3))
+    e = env.SlotInsertionEnv(num_arms=3, cameras=[])
+    e.reset()
+    assert e.get_reward() == 0
+    seen = set()
+    for k in (0, 3, 50, 120, 200, 250):
+        q = z["slot_insertion_qpos"][k]
+        e.set_qpos(q)
+        o = OracleEnv(om)
+        o.qpos[:] = q
+        o.forward()
+        c = o.contacts()
+        want, _ = o.reward_from_pairs([(int(r[13]), int(r[14])) for r in c])
+        assert e.get_reward() == want, k
+        seen.add(want)
+    assert len(seen) >= 2 and max(seen) >= 2          # the fixture spans resting objects and grasps
+    e.reset()
+    assert e.get_reward() == 0                         # reset's own forward pass leaves the reward at 0
+    e.close()
+
+
+def test_hide_and_show_middle_arm():
+    """reference env.py:394-398 (used by data_collection_scripts/replay_sim_episode.py:59 on a 3-arm env): the middle arm leaves
+    the picture, the joint state stays, stepping still takes 21-dim actions; show_middle_arm restores the view"""
+    from av_aloha_b200 import env
+    e = env.SlotInsertionEnv(num_arms=3, cameras=["overhead_cam"], observation_height=120, observation_width=160)
+    np.random.seed(3)
+    obs0, _ = e.reset()
+    e.hide_middle_arm()
+    obs1 = e.get_obs()
+    assert obs1["agent_pos"].shape == (21,) and np.abs(obs1["agent_pos"] - obs0["agent_pos"]).max() <= 1e-6
+    d = np.abs(obs1["pixels"]["overhead_cam"].astype(int) - obs0["pixels"]["overhead_cam"].astype(int))
+    assert (d.max(axis=2) > 20).mean() > 0.005          # the arm's pixels changed ...
+    obs2, reward, *_ = e.step(_hold(21))
+    assert obs2["agent_pos"].shape == (21,) and np.abs(obs2["agent_pos"][14:] - obs0["agent_pos"][14:]).max() < 0.05
+    e.show_middle_arm()
+    e.set_qpos(e._batch.get(env.capi.QPOS).cpu().numpy()[0])
+    back = e.get_obs()["pixels"]["overhead_cam"]
+    d2 = np.abs(back.astype(int) - obs0["pixels"]["overhead_cam"].astype(int))
+    assert (d2.max(axis=2) > 20).mean() < 0.004         # ... and are back (up to the 0.03 rad the arms sagged in one step)
     e.close()

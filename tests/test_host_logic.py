@@ -55,6 +55,16 @@ def test_registry_matches_reference_ids():
             assert (e["kwargs"]["observation_height"], e["kwargs"]["observation_width"]) == (480, 640)
     assert env.SIM_PHYSICS_ENV_STEP_RATIO == 20
     assert env.GuidedVisionEnv.metadata["render_fps"] == pytest.approx(25.0)
+    # ... and entry by entry against what the reference's own __init__.py registers (recorded by executing it:
+    # tools/gen_registry_golden.py): ids, class names, camera LISTS IN ORDER (the 2-arm ids carry no zed cameras)
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "registry_golden.json")))
+    assert len(gold) == 10
+    for g in gold:
+        e = next(x for x in env.ENVS if x["id"] == g["id"])
+        assert e["kwargs"] == g["kwargs"], g["id"]
+        assert env._TASK_CLASSES[e["task"]].__name__ == g["entry_point"].split(":")[1]
+        assert g["nondeterministic"] is True
 
 
 def test_cabi_exports_every_declared_symbol():
