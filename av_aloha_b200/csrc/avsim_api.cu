@@ -119,7 +119,7 @@ struct avsim_batch {
     // split pipeline: the environments are cut into `ngroups` contiguous groups, each stepped by its own launch chain on its own
     // stream, so that the tail of one group's solver kernel (a few environments that need many Newton iterations) overlaps with
     // the other groups' kernels instead of idling the GPU
-    int ngroups = 1, per_sm = 1, sms = 1, solve_per_sm = 1;
+    int ngroups = 1, per_sm = 1, sms = 1, solve_per_sm = 1, solve_warps = AV_MAX_WARPS;
     cudaStream_t gstream[AV_MAX_GROUPS] = {};
     cudaEvent_t ev_start = nullptr, ev_done[AV_MAX_GROUPS] = {};
     int64_t launches = 0;
@@ -160,7 +160,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
               dalloc(b, &s.contacts, B * AV_NCON * 16) && dalloc(b, &s.qacc, B * d.nv) && dalloc(b, &s.xpos, B * 3 * d.nbody) &&
               dalloc(b, &s.qfrc_bias, B * d.nv) && dalloc(b, &s.qacc_smooth, B * d.nv) && dalloc(b, &s.mass_diag, B * d.nv) &&
               dalloc(b, &s.scratch, B * AV_SCRATCH_FLOATS) && dalloc(b, &s.env_cycles, B) && dalloc(b, &s.fc_key, B * (AV_NCON + AV_NSC)) && dalloc(b, &s.fc_n, B * 2) &&
-              dalloc(b, &s.fc_val, B * (AV_NCON * 6 + AV_NSC)) && dalloc(b, &s.nw_stat, B * 4) && dalloc(b, &s.heads, B * AV_HEAD_FLOATS) && dalloc(b, &s.order_b, B) && dalloc(b, &s.queue_b, AV_MAX_GROUPS) && dalloc(b, &s.env_cycles_b, B) && dalloc(b, &s.order, B) && dalloc(b, &s.queue, AV_MAX_GROUPS) && dalloc(b, &b->d_action, B * d.nj_obs);
+              dalloc(b, &s.fc_val, B * (AV_NCON * 6 + AV_NSC)) && dalloc(b, &s.nw_stat, B * 4) && dalloc(b, &s.heads, B * AV_HEADX_FLOATS) && dalloc(b, &s.order_b, B) && dalloc(b, &s.queue_b, AV_MAX_GROUPS) && dalloc(b, &s.env_cycles_b, B) && dalloc(b, &s.order, B) && dalloc(b, &s.queue, AV_MAX_GROUPS) && dalloc(b, &b->d_action, B * d.nj_obs);
     if (!ok) { fail(AVSIM_ERR_CUDA, "avsim_create: device allocation failed"); avsim_destroy(b); return nullptr; }
     if (cudaMallocHost(&b->h_action, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
         cudaMallocHost(&b->h_agent, B * d.nj_obs * sizeof(float)) != cudaSuccess ||
@@ -193,17 +193,17 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
-    CUP(cudaFuncSetAttribute(avsim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SOLVE_WARPS * (int)AV_SOLVER_SLICE_BYTES));
-    {   // solver kernel: AV_SOLVE_WARPS free-running warps per block, as many blocks per SM as shared memory and registers allow
-        const char *esb = getenv("AVSIM_SOLVE_BLOCKS"), *esp = getenv("AVSIM_SPLIT");
-        int per = smem_sm / (AV_SOLVE_WARPS * (int)AV_SOLVER_SLICE_BYTES + 1024);
-        per = std::max(1, std::min(per, 16 / AV_SOLVE_WARPS));          // 128 registers per thread: 16 warps per SM
-        if (esb) per = std::max(1, std::min(per, atoi(esb)));
-        b->solve_grid = std::min((num_envs + AV_SOLVE_WARPS - 1) / AV_SOLVE_WARPS, per * sms);
-        b->solve_per_sm = per;
+    {   // solver kernel: one block per SM of `solve_warps` phase-locked warps, one environment slice each
+        const char *esw = getenv("AVSIM_SOLVE_WARPS"), *esp = getenv("AVSIM_SPLIT");
+        int sw = esw ? atoi(esw) : 8;   // 8 slices leave the SM ~170 KB of L1 for the contact blocks; 6..16 measure within 2 % (profiles/r2_sweeps.txt)
+        sw = std::max(1, std::min(sw, std::min(AV_MAX_WARPS, (smem_blk - 1024) / (int)AV_SOLVER_SLICE_BYTES)));
+        b->solve_warps = sw;
+        CUP(cudaFuncSetAttribute(avsim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sw * (int)AV_SOLVER_SLICE_BYTES));
+        b->solve_grid = std::min((num_envs + sw - 1) / sw, sms);
+        b->solve_per_sm = 1;
         b->split = esp ? atoi(esp) : 1;
         const char *eg = getenv("AVSIM_GROUPS");
-        int ng = eg ? atoi(eg) : 4;
+        int ng = eg ? atoi(eg) : 3;
         ng = std::max(1, std::min(ng, AV_MAX_GROUPS));
         while (ng > 1 && num_envs / ng < b->envw * sms / 2) ng--;   // a group should still be a good fraction of a wave
         b->ngroups = ng;
@@ -309,7 +309,7 @@ static BatchState group_view(const avsim_batch *b, int e0, int n, int g) {
     v.scratch += o * AV_SCRATCH_FLOATS;
     v.order += o; v.queue += g; v.order_b += o; v.queue_b += g;
     v.fc_key += o * (AV_NCON + AV_NSC); v.fc_n += o * 2; v.fc_val += o * (AV_NCON * 6 + AV_NSC);
-    v.env_cycles += o; v.env_cycles_b += o; v.heads += o * AV_HEAD_FLOATS; v.nw_stat += o * 4;
+    v.env_cycles += o; v.env_cycles_b += o; v.heads += o * AV_HEADX_FLOATS; v.nw_stat += o * 4;
     return v;
 }
 
@@ -330,11 +330,11 @@ extern "C" int avsim_step(avsim_batch *b, const float *action_dev, int nsubsteps
             launch_order(b, v, st);
             launch_order(b, vb, st);
             int tasks = (ng + b->envw - 1) / b->envw;
-            int grid = std::min(tasks, b->per_sm * b->sms), sgrid = std::min((ng + AV_SOLVE_WARPS - 1) / AV_SOLVE_WARPS, b->solve_per_sm * b->sms);
+            int grid = std::min(tasks, b->per_sm * b->sms), sgrid = std::min((ng + b->solve_warps - 1) / b->solve_warps, b->sms);
             const float *act = action_dev ? action_dev + (size_t)e0 * d.nj_obs : nullptr;
             for (int s = 0; s <= nsubsteps; s++) {
                 avsim_substep_kernel<<<grid, dim3(32, b->warps), sizeof(EnvS) * b->envw, st>>>(d, v, act, s, nsubsteps);
-                if (s < nsubsteps) avsim_solve_kernel<<<sgrid, dim3(32, AV_SOLVE_WARPS), AV_SOLVE_WARPS * AV_SOLVER_SLICE_BYTES, st>>>(d, v);
+                if (s < nsubsteps) avsim_solve_kernel<<<sgrid, dim3(32, b->solve_warps), b->solve_warps * AV_SOLVER_SLICE_BYTES, st>>>(d, v);
             }
             b->launches += 2 * nsubsteps + 1;
             if (G > 1) {

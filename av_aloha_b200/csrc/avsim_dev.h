@@ -27,9 +27,6 @@
 #ifndef AV_MAX_WARPS
 #define AV_MAX_WARPS 16  // warps per block of the step kernel (16 x 32 x 128 registers = the register file); AV_MAX_ENVW of them own a slice
 #endif
-#ifndef AV_SOLVE_WARPS
-#define AV_SOLVE_WARPS 4   // warps (= environments) per block of the solver kernel
-#endif
 #define AV_MIN_BLOCKS 14 // resident single-warp blocks per SM the register allocation of the forward kernel must allow
 #ifndef AV_BULK_PREFETCH
 #define AV_BULK_PREFETCH 0 // 1: TMA bulk prefetch of contact blocks in the solver sweep (measured slower, see avsim_solve.cuh)

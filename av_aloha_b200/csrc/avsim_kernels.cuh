@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(con
         const bool active = warp < nenv && base + warp < B.num_envs;
         const int env = active ? B.order[base + warp] : 0;
         float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
-        float *img = B.heads + (size_t)env * AV_HEAD_FLOATS;
+        float *img = B.heads + (size_t)env * AV_HEADX_FLOATS;
         const FCache fc = env_fcache(B, env);
         pf.start();
         long long own = 0;
@@ -370,13 +370,18 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(con
                 }
                 if (lane == 0) { float *o = B.nw_stat + 4 * (size_t)env; o[0] = o[1] = o[2] = o[3] = 0.f; B.env_cycles_b[env] = 0; }
             } else {
-                head_load(S, img, AV_HEAD_FLOATS, &s_hbar[warp], hphase, lane);   // state + the solver's acc
+                head_load(S, img, AV_HEADX_FLOATS, &s_hbar[warp], hphase, lane);   // state + the solver's acc and forces
                 env_consts(m, S, lane);
             }
             pf.mark(PF_LOAD, lane);
             __syncwarp();
         }
-        if (s > 0) AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
+        if (s > 0) {   // the noslip sweeps on the solver's forces (same work for every environment: lockstep), then the integrator
+            AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, 3));
+            for (int it = 0; it < B.noslip_iters; it++) AV_STAGE_SYNC(solve_sweep(m, S, scratch, lane, true, true));
+            pf.mark(PF_SOLVE, lane);
+            AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
+        }
         AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); if (s < nsub) { stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane); });
         block_collision(m, B, S, scratch, lane, warp, W, active, pf, own);
         if (s < nsub) {
@@ -396,51 +401,65 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(con
     }
 }
 
-// The constraint solve of one substep for every environment: free-running warps, one environment each, pulled from a queue
-// sorted by the solver cycles of the previous step.  Slices hold only the head record and the solver scratch.
-__global__ void __launch_bounds__(32 * AV_SOLVE_WARPS, 4) avsim_solve_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B) {
+// The Newton solve of one substep for every environment.  One block per SM, its warps PHASE-LOCKED: every trip of the loop runs
+// the phases fetch / gradient / Hessian / direction / line search once, with a block barrier after each, and a warp takes part in
+// a phase when its environment needs it.  A warp whose environment has converged publishes the forces, stores the record and
+// fetches the next environment from the queue at the top of the next trip -- so an environment that needs 17 iterations holds
+// one warp for 17 trips and nobody else.  Why phase-locked: free-running warps (the first version of this kernel) spread over
+// 100 KB of solver code and ncu showed 'no_instruction' as 6.4 of the 12.4 stall cycles per issued instruction, at any
+// occupancy (profiles/r2_solve_kernel_ncu.txt) -- instruction fetch, not arithmetic, bounded it; in lockstep one fetched line
+// serves all the warps of the SM.  The noslip sweeps that follow the solve cost the same for every environment, so they run in
+// the substep kernel's lockstep blocks (start of the next launch), not here.
+__global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_solve_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B) {
     const int lane = threadIdx.x, warp = threadIdx.y;
     EnvS &S = *reinterpret_cast<EnvS *>(reinterpret_cast<char *>(av_smem_raw) + (size_t)warp * AV_SOLVER_SLICE_BYTES);
-    AV_SHARED unsigned long long s_hbar[AV_SOLVE_WARPS];
+    AV_SHARED unsigned long long s_hbar[AV_MAX_WARPS];
     unsigned hphase = 0;
-    Prof pf;
     if (lane == 0) mbar_init(&s_hbar[warp], 1);
     if (blockIdx.x == 0 && warp == 0 && lane == 0) *B.queue = 0;   // rewind the substep kernel's queue
-    __syncwarp();
+    __syncthreads();
+    Newton nw;
+    bool run = false, drained = false;
+    int env = 0;
+    float *scratch = nullptr, *img = nullptr;
+    long long t0 = 0;
     for (;;) {
-        int idx = 0;
-        if (lane == 0) idx = atomicAdd(B.queue_b, 1);
-        idx = __shfl_sync(AV_FULL, idx, 0);
-        if (idx >= B.num_envs) break;
-        const int env = B.order_b[idx];
-        float *scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
-        float *img = B.heads + (size_t)env * AV_HEAD_FLOATS;
-        const FCache fc = env_fcache(B, env);
-        pf.start();
-        long long t0 = clock64();
-        head_load(S, img, AV_HEAD_FLOATS, &s_hbar[warp], hphase, lane);
-        pf.mark(PF_LOAD, lane);
-        int sweeps = B.solver_iters;
-        if (B.solver == 1) {
+        if (!run && !drained) {   // ---- fetch: next environment of the cost-sorted queue, record in, start point
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(B.queue_b, 1);
+            idx = __shfl_sync(AV_FULL, idx, 0);
+            if (idx < B.num_envs) {
+                env = B.order_b[idx];
+                scratch = B.scratch + (size_t)env * AV_SCRATCH_FLOATS;
+                img = B.heads + (size_t)env * AV_HEADX_FLOATS;
+                t0 = clock64();
+                head_load(S, img, AV_HEAD_FLOATS, &s_hbar[warp], hphase, lane);
+                nw.init(m, S, scratch, lane);
+                run = true;
+            } else
+                drained = true;
+        }
+        if (!__syncthreads_or(run ? 1 : 0)) break;
+        bool stop = false;
+        if (run) stop = nw.grad(m, S, scratch, lane, B.newton_iters, B.newton_tol);
+        __syncthreads();
+        if (run && !stop) nw.hess(m, S, scratch, lane);
+        __syncthreads();
+        if (run && !stop) stop = nw.dir(m, S, lane, B.newton_tol);
+        __syncthreads();
+        if (run && !stop) stop = nw.search(m, S, scratch, lane, B.newton_ls);
+        if (run && stop) {   // converged (or out of descent in fp32, or at the cap): forces out, record back to the image
             float gr = 0.f;
-            int ni = stage_newton(m, S, scratch, lane, B.newton_iters, B.newton_ls, B.newton_tol, gr, pf);
+            nw.publish(S, lane, gr);
             if (lane == 0) {
                 float *o = B.nw_stat + 4 * (size_t)env;
-                o[0] += (float)ni; o[1] = fmaxf(o[1], gr); o[2] = fmaxf(o[2], (float)ni); o[3] += ni >= B.newton_iters ? 1.f : 0.f;
+                o[0] += (float)nw.it; o[1] = fmaxf(o[1], gr); o[2] = fmaxf(o[2], (float)nw.it); o[3] += nw.it >= B.newton_iters ? 1.f : 0.f;
             }
-            sweeps = 0;
+            head_store(S, img, AV_HEADX_FLOATS, lane);   // head (acc, scalar-row forces, status) + contact forces / multipliers
+            if (lane == 0) B.env_cycles_b[env] += clock64() - t0;
+            run = false;
         }
-        stage_solve_begin(m, S, scratch, lane, B.solver == 1 ? 3 : B.warm_mode);
-        for (int it = 0; it < sweeps + B.noslip_iters; it++) solve_sweep(m, S, scratch, lane, it >= sweeps, B.solver == 1);
-        if (B.solver != 1) stage_cache_store(m, S, lane, fc);
-        pf.mark(PF_SOLVE, lane);
-        // back to the image: the constraint acceleration and the status word are all the integrator needs from here
-        for (int i = lane; i < AV_NVP; i += 32) img[offsetof(EnvS, acc) / 4 + i] = S.acc[i];
-        if (lane == 0) {
-            reinterpret_cast<int *>(img)[offsetof(EnvS, status) / 4] = S.status;
-            B.env_cycles_b[env] += clock64() - t0;
-        }
-        __syncwarp();
+        __syncthreads();
     }
 }
 

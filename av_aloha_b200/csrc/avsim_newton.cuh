@@ -289,46 +289,54 @@ __device__ __forceinline__ void nw_solve(const float *H, int n, const float *g, 
     x0 = s0; x1 = s1;
 }
 
-// The solve.  In: scalar rows (S.sc_*), contact blocks (scratch), S.warm = previous qacc, S.qacc_smooth.  Out: S.acc (S.warm and
-// S.qfrc_bias are clobbered), the
-// constraint forces S.sc_f / S.c_f of the final iterate (the noslip sweeps and the outputs read them); returns the iterations.
-__device__ AV_STAGE int stage_newton(const DevModel &m, EnvS &S, float *scratch, int lane, int max_iter, int ls_iter, float tol, float &grad_out, Prof &pf) {
-    const int nv = m.nv, nsc = S.nsc, ncon = S.ncon;
-    const int i0 = lane, i1 = lane + 32;
-    // gradient and search direction reuse two joint-space vectors that are dead during the solve: qfrc_bias (read by the smooth
-    // stage, rewritten by the integrator) and warm (the previous qacc: consumed by the start below, rewritten by the integrator)
-    float *g = S.qfrc_bias, *p = S.warm, *H = S.H;
-    // scale of the stopping tests: 1 / trace(M) (MuJoCo: 1 / (meaninertia * nv))
-    float trm = 0.f;
-    for (int i = lane; i < nv; i += 32) {
-        int t = m.dof_tree[i], dl = i - m.tree_dofadr[t];
-        trm += S.M[t * AV_MTRI + av_mtri(dl, dl)];
-    }
-    const float scale = 1.0f / warp_sum(trm);
-    const int mycls = lane < nsc ? (S.sc_key[lane] >> 24) : -1;
-    // ---- start: the better of qacc_smooth (acc = 0) and the warm start (previous qacc), like mj_fwdConstraint
-    for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = i < nv ? S.warm[i] - S.qacc_smooth[i] : 0.f;
-    __syncwarp();
-    nw_jar_all(S, scratch, S.acc, lane);
-    {
-        float ga = 0.f;
-        if (i0 < nv) ga += 0.5f * S.acc[i0] * nw_mrow(m, S, S.acc, i0);
-        if (i1 < nv) ga += 0.5f * S.acc[i1] * nw_mrow(m, S, S.acc, i1);
-        float cw = warp_sum(ga) + nw_cost(S, scratch, S.acc, false, lane), c0 = nw_cost(S, scratch, S.acc, true, lane);
-        if (!(cw < c0)) {
-            __syncwarp();
-            for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
-            for (int c = 0; c < ncon; c++)
-                if (lane < 6) scratch[c * AV_CBLK + AV_CB_JAR + lane] = ldblk1(scratch + c * AV_CBLK + AV_CB_B + lane);
-            __syncwarp();
+// The solve, as a state machine so that a kernel can run its phases in lockstep across warps (avsim_solve_kernel: one fetched
+// instruction line then serves all the warps of the SM, like the stages of the substep kernel) -- or back to back for one warp
+// (stage_newton below: forward kernel, fused step kernel, emulation harness).  In: scalar rows (S.sc_*), contact blocks
+// (scratch), S.warm = previous qacc, S.qacc_smooth.  Out: S.acc (S.warm and S.qfrc_bias are clobbered) and the constraint forces
+// S.sc_f / S.c_f of the final iterate (the noslip sweeps and the outputs read them).
+//   init -> loop { grad (stop?) -> hess -> dir (stop?) -> search (stop?) } -> publish
+struct Newton {
+    float scale, fs, fa[6], fb[6], p0, p1, gn;   // registers that live across the phases of one solve
+    int mycls, it;
+    bool sfree;
+
+    __device__ __forceinline__ void init(const DevModel &m, EnvS &S, float *scratch, int lane) {
+        const int nv = m.nv, nsc = S.nsc, ncon = S.ncon;
+        const int i0 = lane, i1 = lane + 32;
+        it = 0; p0 = p1 = gn = 0.f;
+        // scale of the stopping tests: 1 / trace(M) (MuJoCo: 1 / (meaninertia * nv))
+        float trm = 0.f;
+        for (int i = lane; i < nv; i += 32) {
+            int t = m.dof_tree[i], dl = i - m.tree_dofadr[t];
+            trm += S.M[t * AV_MTRI + av_mtri(dl, dl)];
+        }
+        scale = 1.0f / warp_sum(trm);
+        mycls = lane < nsc ? (S.sc_key[lane] >> 24) : -1;
+        // ---- start: the better of qacc_smooth (acc = 0) and the warm start (previous qacc), like mj_fwdConstraint
+        for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = i < nv ? S.warm[i] - S.qacc_smooth[i] : 0.f;
+        __syncwarp();
+        nw_jar_all(S, scratch, S.acc, lane);
+        {
+            float ga = 0.f;
+            if (i0 < nv) ga += 0.5f * S.acc[i0] * nw_mrow(m, S, S.acc, i0);
+            if (i1 < nv) ga += 0.5f * S.acc[i1] * nw_mrow(m, S, S.acc, i1);
+            float cw = warp_sum(ga) + nw_cost(S, scratch, S.acc, false, lane), c0 = nw_cost(S, scratch, S.acc, true, lane);
+            if (!(cw < c0)) {
+                __syncwarp();
+                for (int i = lane; i < AV_NVP; i += 32) S.acc[i] = 0.f;
+                for (int c = 0; c < ncon; c++)
+                    if (lane < 6) scratch[c * AV_CBLK + AV_CB_JAR + lane] = ldblk1(scratch + c * AV_CBLK + AV_CB_B + lane);
+                __syncwarp();
+            }
         }
     }
-    pf.mark(PF_NW_INIT, lane);
-    int it = 0;
-    for (;; it++) {
-        // ---- forces of the current iterate (lane = constraint block), gradient g = M acc - J' f
-        float fs = 0.f, fa[6], fb[6];
-        bool sfree = false;
+
+    // forces of the current iterate (lane = constraint block) and gradient g = M acc - J' f; true = stop here
+    __device__ __forceinline__ bool grad(const DevModel &m, EnvS &S, float *scratch, int lane, int max_iter, float tol) {
+        const int nv = m.nv, nsc = S.nsc, ncon = S.ncon;
+        const int i0 = lane, i1 = lane + 32;
+        float *g = S.qfrc_bias;
+        fs = 0.f; sfree = false;
 #pragma unroll
         for (int k = 0; k < 6; k++) fa[k] = fb[k] = 0.f;
         if (lane < nsc) fs = sc_force(S, lane, sc_jx(S, lane, S.acc) + S.sc_b[lane], sfree);
@@ -368,174 +376,211 @@ __device__ AV_STAGE int stage_newton(const DevModel &m, EnvS &S, float *scratch,
             if (half == 0 && dof >= 0) g[dof] -= t;
             __syncwarp();
         }
-        float gn = 0.f;
+        gn = 0.f;
         if (i0 < nv) gn += g[i0] * g[i0];
         if (i1 < nv) gn += g[i1] * g[i1];
         gn = warp_sum(gn);
-        pf.mark(PF_NW_GRAD, lane);
-        // final iterate: publish its forces (the noslip sweeps and the contact dump read them)
-        bool stop = it >= max_iter || scale * sqrtf(gn) < tol;
-        if (!stop) {
-            // ---- Hessian H = M + J' Hc J
-            const int nh = nv * (nv + 1) / 2;
-            for (int i = lane; i < nh; i += 32) H[i] = 0.f;
-            __syncwarp();
-            for (int i = lane; i < nv; i += 32) {
-                int t = m.dof_tree[i], d0 = m.tree_dofadr[t], dl = i - d0;
-                for (int j = 0; j <= dl; j++) H[i * (i + 1) / 2 + d0 + j] = S.M[t * AV_MTRI + av_mtri(dl, j)];
-            }
-            __syncwarp();
-            for (int cls = 0; cls < 3; cls++) {
-                if (mycls == cls && sfree) {
-                    float D = __fdividef(1.0f, S.sc_R[lane]), c1 = S.sc_c1[lane], c2 = S.sc_c2[lane];
-                    int d1 = S.sc_dof1[lane], d2 = S.sc_dof2[lane];
-                    H[d1 * (d1 + 1) / 2 + d1] += D * c1 * c1;
-                    if (d2 >= 0) {
-                        H[d2 * (d2 + 1) / 2 + d2] += D * c2 * c2;
-                        H[nw_tri(d1, d2)] += D * c1 * c2;
-                    }
-                }
-                __syncwarp();
-            }
-            for (int c = 0; c < ncon; c++) {
-                if ((S.c_info[c] >> 20) & 1) continue;
-                const float *blk = scratch + c * AV_CBLK, *J = blk + AV_CB_J;
-                ConeP cp;
-                cone_load(blk, cp);
-                float y[6], U[6], T_, e_;
-#pragma unroll
-                for (int k = 0; k < 6; k++) y[k] = ldblk1(nw_jar(scratch, c) + k);
-                const int zone = cone_zone(y, cp, U, T_, e_);   // uniform: every lane evaluates the same contact
-                if (zone == 0) continue;
-                const int col = lane & 15, half = lane >> 4, tr = c_tr(S, c);
-                float jc[6];
-#pragma unroll
-                for (int k = 0; k < 6; k++) jc[k] = ldblk1(J + k * AV_JW + col);
-                if (zone == 1) {   // inside the cone: Hc = diag(1 / R), T = Hc J is a row scaling
-#pragma unroll
-                    for (int r = 0; r < 3; r++) {
-                        float t0 = __fdividef(jc[r], cp.R[r]), t1 = __fdividef(jc[r + 3], cp.R[r + 3]);
-                        S.stage[(3 * half + r) * AV_JW + col] = half ? t1 : t0;
-                    }
-                } else {
-                    float Hc[21];
-                    cone_hess(y, cp, Hc);
-#pragma unroll
-                    for (int r = 0; r < 3; r++) {   // T = Hc J: this lane's rows 3 half .. 3 half + 2 at its column
-                        float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-                        for (int l = 0; l < 6; l++) { t0 += Hc[TRI(r, l)] * jc[l]; t1 += Hc[TRI(r + 3, l)] * jc[l]; }
-                        S.stage[(3 * half + r) * AV_JW + col] = half ? t1 : t0;
-                    }
-                }
-                __syncwarp();
-                const int b1 = tr & 63, n1 = (tr >> 6) & 15, b2 = (tr >> 10) & 63, n2 = (tr >> 16) & 15, nl = n1 + n2, np = nl * (nl + 1) / 2;
-                for (int e = lane; e < np; e += 32) {
-                    int ij = av_tri_ij[e], ii = ij >> 4, jj = ij & 15;
-                    int ci = ii < n1 ? ii : 8 + ii - n1, cj = jj < n1 ? jj : 8 + jj - n1;
-                    int di = ii < n1 ? b1 + ii : b2 + ii - n1, dj = jj < n1 ? b1 + jj : b2 + jj - n1;
-                    float s = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) s += ldblk1(J + k * AV_JW + ci) * S.stage[k * AV_JW + cj];
-                    H[nw_tri(di, dj)] += s;
-                }
-                __syncwarp();
-            }
-            pf.mark(PF_NW_HESS, lane);
-            if (!nw_chol(H, nv, lane)) S.status |= 16;
-            float p0, p1;
-            nw_solve(H, nv, g, lane, p0, p1);
-            if (i0 < nv) p[i0] = p0;
-            if (i1 < nv) p[i1] = p1;
-            float dec = -((i0 < nv ? g[i0] * p0 : 0.f) + (i1 < nv ? g[i1] * p1 : 0.f));
-            dec = warp_sum(dec);   // Newton decrement: the decrease the quadratic model predicts is dec / 2
-            __syncwarp();
-            stop = !(0.5f * scale * dec >= 1e-6f * tol);   // also catches NaN / a non-descent direction
-            pf.mark(PF_NW_CHOL, lane);
-            if (!stop) {
-                // ---- line search along p
-                float pMp = 0.f, pMa = 0.f;
-                if (i0 < nv) { float mp = nw_mrow(m, S, p, i0); pMp += p0 * mp; pMa += S.acc[i0] * mp; }
-                if (i1 < nv) { float mp = nw_mrow(m, S, p, i1); pMp += p1 * mp; pMa += S.acc[i1] * mp; }
-                pMp = warp_sum(pMp); pMa = warp_sum(pMa);
-                float va[6], vb[6];
-#pragma unroll
-                for (int k = 0; k < 6; k++) va[k] = vb[k] = 0.f;
-                for (int c = 0; c < ncon; c++) {
-                    if ((S.c_info[c] >> 20) & 1) continue;
-                    float res[6];
-                    nw_rows(scratch + c * AV_CBLK, c_tr(S, c), p, lane, res);
-                    if (lane == (c & 31)) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) { if (c < 32) va[k] = res[k]; else vb[k] = res[k]; }
-                    }
-                }
-                LsCon La, Lb;
-                ls_con_init(La, S, scratch, lane, va);
-                ls_con_init(Lb, S, scratch, lane + 32, vb);
-                float ys = 0.f, vs = 0.f, Rs = 1.f, los = 0.f, his = 0.f;
-                if (lane < nsc) {
-                    ys = sc_jx(S, lane, S.acc) + S.sc_b[lane]; vs = sc_jx(S, lane, p);
-                    Rs = S.sc_R[lane]; los = S.sc_lo[lane]; his = S.sc_hi[lane];
-                }
-                float lo = 0.f, hi = -1.f, alpha = 0.f, d10 = 0.f;
-                bool accepted = false;
-                for (int k = 0; k <= ls_iter; k++) {
-                    float d1 = 0.f, d2 = 0.f;
-                    ls_con_eval(La, alpha, d1, d2);
-                    ls_con_eval(Lb, alpha, d1, d2);
-                    if (lane < nsc) {
-                        float y = ys + alpha * vs, f = -__fdividef(y, Rs);
-                        bool fr = f > los && f < his;
-                        f = fminf(fmaxf(f, los), his);
-                        d1 -= f * vs;
-                        if (fr) d2 += __fdividef(vs * vs, Rs);
-                    }
-                    d1 = warp_sum(d1) + pMa + alpha * pMp;
-                    d2 = warp_sum(d2) + pMp;
-                    if (k == 0) d10 = d1;
-                    else if (fabsf(d1) <= 1e-3f * fabsf(d10)) { accepted = true; break; }
-                    if (k == ls_iter) break;
-                    if (d1 < 0.f) lo = alpha; else hi = alpha;
-                    float next = alpha - __fdividef(d1, fmaxf(d2, 1e-30f));
-                    if (!(next > lo) || (hi >= 0.f && !(next < hi))) next = hi >= 0.f ? 0.5f * (lo + hi) : 2.f * alpha + 1e-6f;
-                    alpha = next;
-                }
-                if (!accepted) alpha = lo;   // the descending side of the bracket: the cost cannot increase
-                if (!(d10 < 0.f) || !(alpha > 0.f)) stop = true;
-                else {
-                    if (i0 < nv) S.acc[i0] += alpha * p0;
-                    if (i1 < nv) S.acc[i1] += alpha * p1;
-                    if (La.live) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) nw_jar(scratch, lane)[k] += alpha * La.v[k];
-                    }
-                    if (Lb.live) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) nw_jar(scratch, lane + 32)[k] += alpha * Lb.v[k];
-                    }
-                    __syncwarp();
-                }
-            }
+        return it >= max_iter || scale * sqrtf(gn) < tol;
+    }
+
+    // Hessian H = M + J' Hc J into the packed lower triangle S.H
+    __device__ __forceinline__ void hess(const DevModel &m, EnvS &S, float *scratch, int lane) {
+        const int nv = m.nv, ncon = S.ncon;
+        float *H = S.H;
+        // ---- Hessian H = M + J' Hc J
+        const int nh = nv * (nv + 1) / 2;
+        for (int i = lane; i < nh; i += 32) H[i] = 0.f;
+        __syncwarp();
+        for (int i = lane; i < nv; i += 32) {
+            int t = m.dof_tree[i], d0 = m.tree_dofadr[t], dl = i - d0;
+            for (int j = 0; j <= dl; j++) H[i * (i + 1) / 2 + d0 + j] = S.M[t * AV_MTRI + av_mtri(dl, j)];
         }
-        pf.mark(PF_NW_LS, lane);
-        if (stop) {
-            grad_out = scale * sqrtf(gn);
-            if (lane < nsc) S.sc_f[lane] = fs;
-            __syncwarp();
-            if (lane < ncon) {   // the Hessian (which overlays c_f / c_lam) is dead from here on
-#pragma unroll
-                for (int k = 0; k < 6; k++) S.c_f[6 * lane + k] = fa[k];
-                S.c_lam[lane] = 0.f;
-            }
-            if (lane + 32 < ncon) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) S.c_f[6 * (lane + 32) + k] = fb[k];
-                S.c_lam[lane + 32] = 0.f;
+        __syncwarp();
+        for (int cls = 0; cls < 3; cls++) {
+            if (mycls == cls && sfree) {
+                float D = __fdividef(1.0f, S.sc_R[lane]), c1 = S.sc_c1[lane], c2 = S.sc_c2[lane];
+                int d1 = S.sc_dof1[lane], d2 = S.sc_dof2[lane];
+                H[d1 * (d1 + 1) / 2 + d1] += D * c1 * c1;
+                if (d2 >= 0) {
+                    H[d2 * (d2 + 1) / 2 + d2] += D * c2 * c2;
+                    H[nw_tri(d1, d2)] += D * c1 * c2;
+                }
             }
             __syncwarp();
-            break;
+        }
+        for (int c = 0; c < ncon; c++) {
+            if ((S.c_info[c] >> 20) & 1) continue;
+            const float *blk = scratch + c * AV_CBLK, *J = blk + AV_CB_J;
+            ConeP cp;
+            cone_load(blk, cp);
+            float y[6], U[6], T_, e_;
+#pragma unroll
+            for (int k = 0; k < 6; k++) y[k] = ldblk1(nw_jar(scratch, c) + k);
+            const int zone = cone_zone(y, cp, U, T_, e_);   // uniform: every lane evaluates the same contact
+            if (zone == 0) continue;
+            const int col = lane & 15, half = lane >> 4, tr = c_tr(S, c);
+            float jc[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) jc[k] = ldblk1(J + k * AV_JW + col);
+            if (zone == 1) {   // inside the cone: Hc = diag(1 / R), T = Hc J is a row scaling
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    float t0 = __fdividef(jc[r], cp.R[r]), t1 = __fdividef(jc[r + 3], cp.R[r + 3]);
+                    S.stage[(3 * half + r) * AV_JW + col] = half ? t1 : t0;
+                }
+            } else {
+                float Hc[21];
+                cone_hess(y, cp, Hc);
+#pragma unroll
+                for (int r = 0; r < 3; r++) {   // T = Hc J: this lane's rows 3 half .. 3 half + 2 at its column
+                    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                    for (int l = 0; l < 6; l++) { t0 += Hc[TRI(r, l)] * jc[l]; t1 += Hc[TRI(r + 3, l)] * jc[l]; }
+                    S.stage[(3 * half + r) * AV_JW + col] = half ? t1 : t0;
+                }
+            }
+            __syncwarp();
+            const int b1 = tr & 63, n1 = (tr >> 6) & 15, b2 = (tr >> 10) & 63, n2 = (tr >> 16) & 15, nl = n1 + n2, np = nl * (nl + 1) / 2;
+            for (int e = lane; e < np; e += 32) {
+                int ij = av_tri_ij[e], ii = ij >> 4, jj = ij & 15;
+                int ci = ii < n1 ? ii : 8 + ii - n1, cj = jj < n1 ? jj : 8 + jj - n1;
+                int di = ii < n1 ? b1 + ii : b2 + ii - n1, dj = jj < n1 ? b1 + jj : b2 + jj - n1;
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; k++) s += ldblk1(J + k * AV_JW + ci) * S.stage[k * AV_JW + cj];
+                H[nw_tri(di, dj)] += s;
+            }
+            __syncwarp();
         }
     }
-    return it;
+
+    // Cholesky, search direction p = -H^-1 g, Newton decrement; true = stop (the model predicts no further decrease)
+    __device__ __forceinline__ bool dir(const DevModel &m, EnvS &S, int lane, float tol) {
+        const int nv = m.nv;
+        const int i0 = lane, i1 = lane + 32;
+        float *g = S.qfrc_bias, *p = S.warm, *H = S.H;
+        bool stop;
+        if (!nw_chol(H, nv, lane)) S.status |= 16;
+        nw_solve(H, nv, g, lane, p0, p1);
+        if (i0 < nv) p[i0] = p0;
+        if (i1 < nv) p[i1] = p1;
+        float dec = -((i0 < nv ? g[i0] * p0 : 0.f) + (i1 < nv ? g[i1] * p1 : 0.f));
+        dec = warp_sum(dec);   // Newton decrement: the decrease the quadratic model predicts is dec / 2
+        __syncwarp();
+        stop = !(0.5f * scale * dec >= 1e-6f * tol);   // also catches NaN / a non-descent direction
+        return stop;
+    }
+
+    // exact line search along p and the update of acc / jar; true = stop (no descent left in fp32)
+    __device__ __forceinline__ bool search(const DevModel &m, EnvS &S, float *scratch, int lane, int ls_iter) {
+        const int nv = m.nv, nsc = S.nsc, ncon = S.ncon;
+        const int i0 = lane, i1 = lane + 32;
+        float *p = S.warm;
+        bool stop = false;
+        // ---- line search along p
+        float pMp = 0.f, pMa = 0.f;
+        if (i0 < nv) { float mp = nw_mrow(m, S, p, i0); pMp += p0 * mp; pMa += S.acc[i0] * mp; }
+        if (i1 < nv) { float mp = nw_mrow(m, S, p, i1); pMp += p1 * mp; pMa += S.acc[i1] * mp; }
+        pMp = warp_sum(pMp); pMa = warp_sum(pMa);
+        float va[6], vb[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) va[k] = vb[k] = 0.f;
+        for (int c = 0; c < ncon; c++) {
+            if ((S.c_info[c] >> 20) & 1) continue;
+            float res[6];
+            nw_rows(scratch + c * AV_CBLK, c_tr(S, c), p, lane, res);
+            if (lane == (c & 31)) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) { if (c < 32) va[k] = res[k]; else vb[k] = res[k]; }
+            }
+        }
+        LsCon La, Lb;
+        ls_con_init(La, S, scratch, lane, va);
+        ls_con_init(Lb, S, scratch, lane + 32, vb);
+        float ys = 0.f, vs = 0.f, Rs = 1.f, los = 0.f, his = 0.f;
+        if (lane < nsc) {
+            ys = sc_jx(S, lane, S.acc) + S.sc_b[lane]; vs = sc_jx(S, lane, p);
+            Rs = S.sc_R[lane]; los = S.sc_lo[lane]; his = S.sc_hi[lane];
+        }
+        float lo = 0.f, hi = -1.f, alpha = 0.f, d10 = 0.f;
+        bool accepted = false;
+        for (int k = 0; k <= ls_iter; k++) {
+            float d1 = 0.f, d2 = 0.f;
+            ls_con_eval(La, alpha, d1, d2);
+            ls_con_eval(Lb, alpha, d1, d2);
+            if (lane < nsc) {
+                float y = ys + alpha * vs, f = -__fdividef(y, Rs);
+                bool fr = f > los && f < his;
+                f = fminf(fmaxf(f, los), his);
+                d1 -= f * vs;
+                if (fr) d2 += __fdividef(vs * vs, Rs);
+            }
+            d1 = warp_sum(d1) + pMa + alpha * pMp;
+            d2 = warp_sum(d2) + pMp;
+            if (k == 0) d10 = d1;
+            else if (fabsf(d1) <= 1e-3f * fabsf(d10)) { accepted = true; break; }
+            if (k == ls_iter) break;
+            if (d1 < 0.f) lo = alpha; else hi = alpha;
+            float next = alpha - __fdividef(d1, fmaxf(d2, 1e-30f));
+            if (!(next > lo) || (hi >= 0.f && !(next < hi))) next = hi >= 0.f ? 0.5f * (lo + hi) : 2.f * alpha + 1e-6f;
+            alpha = next;
+        }
+        if (!accepted) alpha = lo;   // the descending side of the bracket: the cost cannot increase
+        if (!(d10 < 0.f) || !(alpha > 0.f)) stop = true;
+        else {
+            if (i0 < nv) S.acc[i0] += alpha * p0;
+            if (i1 < nv) S.acc[i1] += alpha * p1;
+            if (La.live) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) nw_jar(scratch, lane)[k] += alpha * La.v[k];
+            }
+            if (Lb.live) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) nw_jar(scratch, lane + 32)[k] += alpha * Lb.v[k];
+            }
+            __syncwarp();
+            it++;
+        }
+        return stop;
+    }
+
+    // the forces of the last evaluated iterate become the solver's output; the Hessian (which overlays c_f / c_lam) is dead
+    __device__ __forceinline__ void publish(EnvS &S, int lane, float &grad_out) {
+        const int nsc = S.nsc, ncon = S.ncon;
+        grad_out = scale * sqrtf(gn);
+        if (lane < nsc) S.sc_f[lane] = fs;
+        __syncwarp();
+        if (lane < ncon) {   // the Hessian (which overlays c_f / c_lam) is dead from here on
+#pragma unroll
+            for (int k = 0; k < 6; k++) S.c_f[6 * lane + k] = fa[k];
+            S.c_lam[lane] = 0.f;
+        }
+        if (lane + 32 < ncon) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) S.c_f[6 * (lane + 32) + k] = fb[k];
+            S.c_lam[lane + 32] = 0.f;
+        }
+        __syncwarp();
+    }
+};
+
+__device__ AV_STAGE int stage_newton(const DevModel &m, EnvS &S, float *scratch, int lane, int max_iter, int ls_iter, float tol, float &grad_out, Prof &pf) {
+    Newton nw;
+    nw.init(m, S, scratch, lane);
+    pf.mark(PF_NW_INIT, lane);
+    for (;;) {
+        bool stop = nw.grad(m, S, scratch, lane, max_iter, tol);
+        pf.mark(PF_NW_GRAD, lane);
+        if (stop) break;
+        nw.hess(m, S, scratch, lane);
+        pf.mark(PF_NW_HESS, lane);
+        stop = nw.dir(m, S, lane, tol);
+        pf.mark(PF_NW_CHOL, lane);
+        if (stop) break;
+        stop = nw.search(m, S, scratch, lane, ls_iter);
+        pf.mark(PF_NW_LS, lane);
+        if (stop) break;
+    }
+    nw.publish(S, lane, grad_out);
+    return nw.it;
 }

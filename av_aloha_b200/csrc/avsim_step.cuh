@@ -105,8 +105,10 @@ struct EnvS {
 #endif
 };
 #define AV_HEAD_FLOATS ((int)(offsetof(EnvS, H) / 4))
+// what the solver kernel stores back: the head + the contact forces / cone multipliers (c_f, c_lam: the first part of the solver scratch)
+#define AV_HEADX_FLOATS (AV_HEAD_FLOATS + AV_NCON * 7)
 #define AV_SOLVER_SLICE_BYTES (offsetof(EnvS, xpos))
-static_assert((AV_HEAD_FLOATS * 4) % 16 == 0 && AV_SOLVER_SLICE_BYTES % 16 == 0, "bulk copies move 16-byte multiples");
+static_assert((AV_HEAD_FLOATS * 4) % 16 == 0 && (AV_HEADX_FLOATS * 4) % 16 == 0 && AV_SOLVER_SLICE_BYTES % 16 == 0, "bulk copies move 16-byte multiples");
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[AV_MBLK]), "L must fit inside crb");
 static_assert(sizeof(float[AV_NB * 12]) >= sizeof(float[2 * 6 * AV_JW + AV_NSC * AV_TD]), "row staging must fit inside crb");
 static_assert(AV_NHP <= AV_NG * 3 + 2 * AV_NCAND + AV_NKEEP + AV_NB * 13, "the Hessian must fit inside the two unions it overlays");

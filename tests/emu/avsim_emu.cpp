@@ -81,7 +81,7 @@ EmuBatch *emu_create(const char *path, int num_envs) {
     s.fc_key = b->fckey.data(); s.fc_n = b->fcn.data(); s.fc_val = b->fcval.data(); s.warm_mode = 1;
     s.solver = 1; s.newton_iters = 30; s.newton_ls = 20; s.newton_tol = 3e-7f;   // the library's defaults (avsim_create)
     b->order.resize(B); b->queue.assign(1, 0); s.order = b->order.data(); s.queue = b->queue.data();
-    b->heads.assign(B * AV_HEAD_FLOATS, 0.f); s.heads = b->heads.data();
+    b->heads.assign(B * AV_HEADX_FLOATS, 0.f); s.heads = b->heads.data();
     b->order_b.resize(B); for (size_t i = 0; i < B; i++) b->order_b[i] = (int)i;
     b->queue_b.assign(1, 0); b->cyc_b.assign(B, 0);
     s.order_b = b->order_b.data(); s.queue_b = b->queue_b.data(); s.env_cycles_b = b->cyc_b.data();

@@ -74,6 +74,12 @@ static inline unsigned __float_as_uint(float f) { return f2u(f); }
 static inline float __uint_as_float(unsigned u) { return u2f(u); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::exchange(0); }
 static inline void __syncthreads() { emu::exchange(0); }   // one warp per emulated block
+static inline int __syncthreads_or(int pred) {
+    const uint32_t *x = emu::exchange(pred ? 1u : 0u);
+    int r = 0;
+    for (int i = 0; i < 32; i++) r |= x[i] != 0;
+    return r;
+}
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::exchange((uint32_t)v)[src & 31]; }
 static inline float __shfl_sync(unsigned, float v, int src) { return u2f(emu::exchange(f2u(v))[src & 31]); }
 static inline float __shfl_sync(unsigned, float v, int src, int width) {
