@@ -42,7 +42,7 @@ def test_gather_episode_stats_world2(num_envs):
     procs = [ctx.Process(target=_worker, args=(r, world, port, num_envs, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in range(world))
+    res = sorted(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
