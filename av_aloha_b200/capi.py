@@ -23,7 +23,7 @@ SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
     "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render", "avsim_set_warmstart",
-    "avsim_pixels_to_float", "avsim_jac", "avsim_set_solver", "avsim_transform",
+    "avsim_pixels_to_float", "avsim_jac", "avsim_set_solver", "avsim_transform", "avsim_render_ids",
 ]
 SOLVER_PGS, SOLVER_NEWTON = 0, 1
 
@@ -69,6 +69,7 @@ def load_library():
     L.avsim_set.argtypes = [vp, i32, vp]
     L.avsim_step_host.argtypes = [vp, vp, i32, vp, vp, vp]
     L.avsim_render.argtypes = [vp, C.POINTER(C.c_int), i32, i32, i32, vp]
+    L.avsim_render_ids.argtypes = [vp, C.POINTER(C.c_int), i32, i32, i32, vp]
     L.avsim_pixels_to_float.argtypes = [vp, C.c_int64, i32, i32, vp, i32, vp]
     L.avsim_launch_count.restype = C.c_int64; L.avsim_launch_count.argtypes = [vp]
     L.avsim_diffik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(DiffIKParams), vp, vp]
@@ -241,13 +242,15 @@ class Batch:
     def forward(self):
         check(self.lib.avsim_forward(self.ptr))
 
-    def render(self, cam_ids, height=480, width=640, out=None):
-        """uint8 CUDA tensor [B, ncam, H, W, 3] of the current state (cam_ids: indices into the model's camera list)."""
+    def render(self, cam_ids, height=480, width=640, out=None, ids=False):
+        """uint8 CUDA tensor [B, ncam, H, W, 3] of the current state (cam_ids: indices into the model's camera list).  ids=True:
+        the geom index each pixel sees instead of a colour (255 = background; test hook)."""
         t = self.torch
-        ids = (C.c_int * len(cam_ids))(*[int(c) for c in cam_ids])
+        cids = (C.c_int * len(cam_ids))(*[int(c) for c in cam_ids])
         if out is None:
             out = t.empty((self.num_envs, len(cam_ids), height, width, 3), dtype=t.uint8, device=self.dev)
-        check(self.lib.avsim_render(self.ptr, ids, len(cam_ids), height, width, C.c_void_p(out.data_ptr())))
+        fn = self.lib.avsim_render_ids if ids else self.lib.avsim_render
+        check(fn(self.ptr, cids, len(cam_ids), height, width, C.c_void_p(out.data_ptr())))
         return out
 
     def get(self, field, out=None):

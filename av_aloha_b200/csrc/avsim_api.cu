@@ -128,7 +128,7 @@ struct avsim_batch {
     int32_t *h_reward = nullptr, *h_status = nullptr;
     float *d_action = nullptr;
     float *d_rpose = nullptr;   // render: world pose of every geom and camera, [B][ngeom + ncam][12]
-    float4 *d_rrect = nullptr;  // render: screen rectangle of every geom per requested camera, [B][8][ngeom]
+    float4 *d_rrect = nullptr;  // render: screen 8-DOP + nearest depth of every geom per requested camera, [B][8][ngeom][3]
     int *d_camids = nullptr;
 };
 
@@ -444,7 +444,15 @@ extern "C" int avsim_step_host(avsim_batch *b, const float *action_host, int nsu
 }
 
 // render: replaces physics.render(h, w, camera_id) per configured camera (reference env.py:180-188, 195-200)
+static int render_impl(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev, int id_mode);
 extern "C" int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev) {
+    return render_impl(b, cam_ids_host, ncam, H, W, dst_dev, 0);
+}
+// test hook: same rays, but every pixel carries the index of the geom it sees in all three channels (255 = background)
+extern "C" int avsim_render_ids(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev) {
+    return render_impl(b, cam_ids_host, ncam, H, W, dst_dev, 1);
+}
+static int render_impl(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev, int id_mode) {
     if (!b || !cam_ids_host || !dst_dev || ncam < 1 || ncam > 8 || H < 1 || W < 4 || (W % 4))
         return fail(AVSIM_ERR_ARG, "avsim_render: bad arguments (1..8 cameras, width a multiple of 4)");
     const DevModel &d = b->model->dm;
@@ -454,7 +462,7 @@ extern "C" int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, i
     size_t n = (size_t)b->st.num_envs;
     if (!b->d_rpose) {
         if (!dalloc(b, &b->d_rpose, n * (d.ngeom + d.ncam) * 12) || !dalloc(b, &b->d_camids, 8) ||
-            !dalloc(b, &b->d_rrect, n * 8 * d.ngeom))
+            !dalloc(b, &b->d_rrect, n * 8 * d.ngeom * 3))
             return fail(AVSIM_ERR_CUDA, "avsim_render: device allocation failed");
     }
     CU(cudaMemcpyAsync(b->d_camids, cam_ids_host, ncam * sizeof(int), cudaMemcpyHostToDevice, b->stream));
@@ -462,8 +470,8 @@ extern "C" int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, i
                                                                             d.cam_quat, d.cam_fovy, b->d_camids, ncam, H, W);
     CU(cudaGetLastError());
     dim3 grid(((W + AV_RT_W - 1) / AV_RT_W) * ((H + AV_RT_H - 1) / AV_RT_H), ncam, (unsigned)n);
-    avsim_render_kernel<<<grid, AV_RT_W * AV_RT_H, 0, b->stream>>>(d, b->d_rpose, b->d_rrect, d.geom_rgba, d.geom_visible, d.cam_fovy, b->d_camids, ncam,
-                                                               d.ncam, H, W, dst_dev);
+    avsim_render_kernel<<<grid, AV_RT_THREADS, 0, b->stream>>>(d, b->d_rpose, b->d_rrect, d.geom_rgba, d.geom_visible, d.cam_fovy, b->d_camids, ncam,
+                                                               d.ncam, H, W, dst_dev, id_mode);
     b->launches += 2;
     CU(cudaGetLastError());
     return AVSIM_OK;

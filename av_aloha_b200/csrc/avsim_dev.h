@@ -75,8 +75,11 @@ struct DevModel {
     const int *reset_draw;                   // Philox stream layout (which draw feeds which coordinate)
     // cameras / render colours (K9)
     int ncam;
-    const int *cam_body, *geom_visible;
+    const int *cam_body, *geom_visible, *geom_tex;
     const float *cam_pos, *cam_quat, *cam_fovy, *geom_rgba;
+    const float *hull_kdop;   // [nhull][13][2] slab intervals of the 26-DOP around every hull (render stand-in for mesh geoms)
+    const float *light;       // directional light: dir 3 | diffuse | headlight ambient | headlight diffuse
+    const float *table_tex;   // [128][128][3] diffuse texture of the table top
     // IK tables
     const int *ik_ndof;
     const float *ik_w0, *ik_p0, *ik_site0, *ik_range;

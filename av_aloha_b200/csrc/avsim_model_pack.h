@@ -245,6 +245,7 @@ inline bool pack_model(const char *avm_path, PackedModel &out) {
     d.ncam = a.len("cam_body");
     PI(cam_body, "cam_body"); PI(geom_visible, "geom_visible");
     PF(cam_pos, "cam_pos"); PF(cam_quat, "cam_quat"); PF(cam_fovy, "cam_fovy"); PF(geom_rgba, "geom_rgba");
+    PI(geom_tex, "geom_tex"); PF(hull_kdop, "hull_kdop"); PF(light, "light"); PF(table_tex, "table_tex");
     PI(ik_ndof, "ik_ndof"); PF(ik_w0, "ik_w0"); PF(ik_p0, "ik_p0"); PF(ik_site0, "ik_site0"); PF(ik_range, "ik_range");
 #undef PF
 #undef PI

@@ -200,6 +200,13 @@ def _read_obj(path):
     return np.array(verts, dtype=np.float64)
 
 
+# the 13 slab directions of a 26-DOP (3 axes, 6 face diagonals, 4 body diagonals): what the renderer intersects a ray with for a
+# mesh geom -- a convex polytope around the hull with 26 faces instead of the 6 of its bounding box
+KDOP_DIRS = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, -1, 0], [1, 0, 1], [1, 0, -1], [0, 1, 1], [0, 1, -1],
+                      [1, 1, 1], [1, 1, -1], [1, -1, 1], [1, -1, -1]], np.float64)
+KDOP_DIRS = KDOP_DIRS / np.linalg.norm(KDOP_DIRS, axis=1, keepdims=True)
+
+
 def _hull_of(verts):
     """Convex hull vertices + interior reference point (volume centroid of the hull)."""
     from scipy.spatial import ConvexHull
@@ -524,6 +531,8 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
         hull_adr.append(sum(hull_num))
         hull_num.append(len(hv))
         hull_verts.append(hv - cen)
+    hull_kdop = np.array([np.stack([(hv @ KDOP_DIRS.T).min(0), (hv @ KDOP_DIRS.T).max(0)], axis=1) for hv in hull_verts]) \
+        if hull_verts else np.zeros((0, len(KDOP_DIRS), 2))          # [nhull, 13, 2]: the renderer's stand-in for the hull (K9)
     hull_verts = np.concatenate(hull_verts, axis=0) if hull_verts else np.zeros((0, 3))
 
     # ---- contact excludes + candidate pair list (static filters) [upstream collision filtering, SURVEY App. A]
@@ -606,6 +615,7 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
         geom_margin=np.array(G["margin"]), geom_hull=np.array(G["hull"], np.int32),
         geom_rgba=np.array(G["rgba"]), geom_visible=np.array(G["visible"], np.int32),
         hull_adr=np.array(hull_adr, np.int32), hull_num=np.array(hull_num, np.int32), hull_vert=hull_verts,
+        hull_kdop=hull_kdop,
         pair_geom=pairs,
         eq_dof1=np.array(eq_dof1, np.int32), eq_dof2=np.array(eq_dof2, np.int32),
         eq_qadr1=np.array(eq_q1, np.int32), eq_qadr2=np.array(eq_q2, np.int32),
@@ -625,6 +635,24 @@ def compile_task(asset_dir, task, num_arms=3, timestep=0.002):
     m["cam_pos"] = np.array([_f(c.get("pos", "0 0 0"), 3) for c in cams])
     m["cam_quat"] = np.array([_orientation(c) for c in cams])
     m["cam_fovy"] = np.array([float(c["fovy"]) for c in cams])
+
+    # ---- render-only constants (K9): the scene's directional light (scene.xml:50; MuJoCo's default light diffuse 0.7 [upstream]),
+    # the headlight (scene.xml:9) and the table's diffuse texture (scene.xml:30,32: material "table" on the tabletop mesh), box
+    # filtered down to 128 x 128 texels and drawn on the top face of the table box that stands in for it
+    light = next(iter(root.iter("light")), None)
+    ldir = _f(light.attrib.get("dir", "0 0 -1"), 3) if light is not None else np.array([0.0, 0.0, -1.0])
+    head = next(iter(root.iter("headlight")), None)
+    amb = float(_f(head.attrib.get("ambient", "0.1 0.1 0.1"))[0]) if head is not None else 0.1
+    dif = float(_f(head.attrib.get("diffuse", "0.4 0.4 0.4"))[0]) if head is not None else 0.4
+    m["light"] = np.array(list(ldir / np.linalg.norm(ldir)) + [0.7 if light is not None else 0.0, amb, dif])
+    tex = np.full((128, 128, 3), 0.5)
+    tex_path = os.path.join(asset_dir, "meshes", "small_meta_table_diffuse.png")
+    if os.path.exists(tex_path):
+        import cv2
+        img = cv2.imread(tex_path, cv2.IMREAD_COLOR)
+        tex = cv2.resize(img, (128, 128), interpolation=cv2.INTER_AREA)[:, :, ::-1].astype(np.float64) / 255.0
+    m["table_tex"] = tex.reshape(-1)
+    m["geom_tex"] = np.array([1 if n == "table" else 0 for n in G["name"]], np.int32)
 
     _finish(m, names)
     return m, names

@@ -103,8 +103,10 @@ int avsim_set(avsim_batch *b, int field, const void *src_dev);
 
 /* render: replaces physics.render(height, width, camera_id) for each configured camera (reference env.py:180-188, 195-200).
  * cam_ids_host: indices into the model's camera list (names in the model's .json sidecar), dst_dev: u8 [B][ncam][H][W][3].
- * Ray-cast of the physics geoms (mesh geoms as oriented bounding boxes of their hulls); W must be a multiple of 4. */
+ * Ray-cast of the physics geoms (mesh geoms as the 26-DOP of their hulls, scene lights, table texture); W must be a multiple of 4. */
 int avsim_render(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev);
+/* test hook: the same primary rays, every pixel = index of the geom it hits (all three channels; 255 = background) */
+int avsim_render_ids(avsim_batch *b, const int *cam_ids_host, int ncam, int H, int W, uint8_t *dst_dev);
 
 /* device-resident observation path: replaces the image half of lerobot's preprocess_observation (reference
  * lerobot/lerobot/common/envs/utils.py:37-50: channel-last u8 -> channel-first f32 in [0,1], fp32 division by 255,
