@@ -229,7 +229,7 @@ def install():
     import huggingface_hub.errors as hf_errors
     _module("huggingface_hub.utils._errors", RepositoryNotFoundError=hf_errors.RepositoryNotFoundError)
     if REFERENCE_LEROBOT not in sys.path:
-        sys.path.insert(0, REFERENCE_LEROBOT)
+        sys.path.append(REFERENCE_LEROBOT)   # appended: it has its own top-level `tests` package that must not shadow ours
     unused = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("not on the rollout path"))   # noqa: E731
     _module("lerobot.common.datasets.factory", make_dataset=unused)
     _module("lerobot.common.logger", log_output_dir=unused)
