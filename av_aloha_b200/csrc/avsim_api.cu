@@ -17,6 +17,7 @@
 #include "avsim_render.cuh"
 
 #define AV_SORT_MAX 8192
+#define AV_GRADIK_GROUP_MAX 4096   // crossover measured between 4096 and 16384 problems (profiles/r2_ik_bench.txt)
 #define AV_MAX_GROUPS 8
 #ifndef AV_DEFAULT_HEAVY_TASKS
 #define AV_DEFAULT_HEAVY_TASKS 0
@@ -288,11 +289,10 @@ extern "C" int avsim_reset(avsim_batch *b, const uint8_t *mask_dev, const float 
 }
 
 static void launch_order(avsim_batch *b, const BatchState &st, cudaStream_t stream) {
-    // queue order: costliest environment of the previous step first (single-block sort up to 8192 environments)
-    int n = st.num_envs, n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    if (n2 <= AV_SORT_MAX) avsim_order_kernel<<<1, 1024, n2 * sizeof(unsigned long long), stream>>>(st, n2);
-    else avsim_identity_order_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st);
+    // queue order: costliest environment of the previous step first; one sorting block per 8192 environments, chunks interleaved
+    int n = st.num_envs, n2 = 1, nch = (n + AV_SORT_MAX - 1) / AV_SORT_MAX;
+    while (n2 < std::min(n, AV_SORT_MAX)) n2 <<= 1;
+    avsim_order_kernel<<<nch, 1024, n2 * sizeof(unsigned long long), stream>>>(st, n2, AV_SORT_MAX);
     b->launches++;
 }
 
@@ -540,7 +540,14 @@ extern "C" int avsim_gradik(const avsim_model *m, int arm, const float *q, const
     gp.rotation_threshold = p->rotation_threshold; gp.max_pos_diff = p->max_pos_diff; gp.max_rot_diff = p->max_rot_diff;
     gp.joint_p = p->joint_p; gp.max_iterations = p->max_iterations;
     for (int k = 0; k < 7; k++) { gp.center_w[k] = p->joint_center_weight[k]; gp.disp_w[k] = p->joint_displacement_weight[k]; }
-    avsim_gradik_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(m->dm, arm, q, pos, quat, n, gp, q_out);
+    // up to AV_GRADIK_GROUP_MAX problems: 16 lanes per problem (latency: 3 FK chains per iteration instead of 16); above, one
+    // thread per problem (throughput: every lane busy).  AVSIM_GRADIK_GROUP=0/1 forces one form (tests compare the two).
+    const char *fe = getenv("AVSIM_GRADIK_GROUP");
+    const int force = fe ? atoi(fe) : -1;
+    if (force == 1 || (force < 0 && n <= AV_GRADIK_GROUP_MAX))
+        avsim_gradik_group_kernel<<<(n + 7) / 8, 128, 0, (cudaStream_t)stream>>>(m->dm, arm, q, pos, quat, n, gp, q_out);
+    else
+        avsim_gradik_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(m->dm, arm, q, pos, quat, n, gp, q_out);
     CU(cudaGetLastError());
     return AVSIM_OK;
 }

@@ -399,6 +399,88 @@ __global__ void avsim_gradik_kernel(DevModel m, int arm, const float *__restrict
     for (int k = 0; k < nd; k++) q_out[(size_t)idx * nd + k] = (float)(q0[k] + (double)P.joint_p * (best[k] - q0[k]));
 }
 
+// GradIK.run, low-latency form: 16 lanes per problem.  One iteration of the descent is 2 ndof + 2 + 1 cost evaluations and one
+// FK that a single thread walks one after the other (16 forward-kinematics chains per iteration, 50 iterations); here lane
+// 2i / 2i+1 of the group evaluate the -/+ finite difference of joint i at the same time, lanes 0 / 1 the two probes, lane 0 the
+// cost of the new iterate while lane 1 does the pose-threshold FK: 3 chains per iteration instead of 16.  Every evaluation is done
+// entirely by one lane with the arithmetic of the thread-per-problem kernel and only finished doubles are exchanged
+// (__shfl_sync, width 16), so the two kernels return the same iterates.  Two problems share a warp and may leave the loop at
+// different iterations: all shuffles are masked to the problem's own half-warp.
+#if defined(__CUDACC__)   // device build only: the host emulation harness (tests/emu) runs the thread-per-problem form
+__global__ void avsim_gradik_group_kernel(DevModel m, int arm, const float *__restrict__ q_in, const float *__restrict__ pos,
+                                          const float *__restrict__ quat_wxyz, int n, GradIKParams P, float *__restrict__ q_out) {
+    const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, sub = threadIdx.x & 15;
+    const unsigned gm = 0xffffu << (threadIdx.x & 16);
+    const bool valid = gidx < n;
+    const int idx = valid ? gidx : n - 1;   // surplus groups recompute the last problem and do not store
+    ArmTab A;
+    load_arm(m, arm, A);
+    int nd = A.n;
+    double q0[7], tp[3], tq[4], tR[9], cw[7], centers[7];
+    for (int k = 0; k < nd; k++) {
+        q0[k] = q_in[(size_t)idx * nd + k];
+        centers[k] = 0.5 * (A.lo[k] + A.hi[k]);
+        cw[k] = (double)P.center_w[k];
+    }
+    for (int k = 0; k < 3; k++) tp[k] = pos[(size_t)idx * 3 + k];
+    tq[0] = quat_wxyz[(size_t)idx * 4 + 1]; tq[1] = quat_wxyz[(size_t)idx * 4 + 2]; tq[2] = quat_wxyz[(size_t)idx * 4 + 3];
+    tq[3] = quat_wxyz[(size_t)idx * 4];
+    ik_quat2mat_xyzw(tq, tR);
+    T44 T;
+    ik_fk(A, q0, T);
+    ik_limit_pose(T.p, T.R, tp, tR, (double)P.max_pos_diff, (double)P.max_rot_diff);
+    double step = (double)P.step_size;
+    double init_cost = gradik_cost(A, P, q0, q0, tp, tR, cw, centers);
+    double grad[7], working[7], local[7], best[7];
+    for (int k = 0; k < nd; k++) working[k] = local[k] = best[k] = q0[k];
+    double local_cost = init_cost, best_cost = init_cost, previous_cost = 0.0;
+    for (int it = 0; it < P.max_iterations; it++) {
+        double mine = 0.0;
+        if (sub < 2 * nd) {
+            const int i = sub >> 1;
+            working[i] = (sub & 1) ? local[i] + step : local[i] - step;
+            mine = gradik_cost(A, P, working, q0, tp, tR, cw, centers);
+            working[i] = local[i];
+        }
+        for (int i = 0; i < nd; i++) {
+            double p1 = __shfl_sync(gm, mine, 2 * i, 16), p3 = __shfl_sync(gm, mine, 2 * i + 1, 16);
+            grad[i] = p3 - p1;
+        }
+        double sum = step;
+        for (int i = 0; i < nd; i++) sum += fabs(grad[i]);
+        double f = step / sum;
+        for (int i = 0; i < nd; i++) grad[i] *= f;
+        if (sub < 2) {
+            for (int i = 0; i < nd; i++) working[i] = sub ? local[i] + grad[i] : local[i] - grad[i];
+            mine = gradik_cost(A, P, working, q0, tp, tR, cw, centers);
+        }
+        double p1 = __shfl_sync(gm, mine, 0, 16), p3 = __shfl_sync(gm, mine, 1, 16);
+        double p2 = 0.5 * (p1 + p3), cost_diff = 0.5 * (p3 - p1);
+        double joint_diff = (isfinite(cost_diff) && cost_diff != 0.0) ? p2 / cost_diff : 0.0;
+        for (int i = 0; i < nd; i++) {
+            working[i] = fmin(fmax(local[i] - grad[i] * joint_diff, A.lo[i]), A.hi[i]);
+            local[i] = working[i];
+        }
+        int within = 0;
+        if (sub == 0) mine = gradik_cost(A, P, local, q0, tp, tR, cw, centers);
+        if (sub == 1) {   // solution_fn (grad_ik.py:205-218): within_pose_threshold
+            ik_fk(A, local, T);
+            double d[3] = {tp[0] - T.p[0], tp[1] - T.p[1], tp[2] - T.p[2]}, e[3];
+            ik_ang_err(tR, T.R, e);
+            within = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) < (double)P.position_threshold &&
+                     sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) < (double)P.rotation_threshold;
+        }
+        local_cost = __shfl_sync(gm, mine, 0, 16);
+        within = __shfl_sync(gm, within, 1, 16);
+        if (local_cost < best_cost) { for (int i = 0; i < nd; i++) best[i] = local[i]; best_cost = local_cost; }
+        if (within) break;
+        if (fabs(local_cost - previous_cost) <= (double)P.min_cost_delta) break;
+        previous_cost = local_cost;
+    }
+    if (valid && sub < nd) q_out[(size_t)idx * nd + sub] = (float)(q0[sub] + (double)P.joint_p * (best[sub] - q0[sub]));
+}
+#endif
+
 // ---- transform_utils.py primitives as a batched operator (fp64 in / out, one thread per item): the callable mirror of the
 // helpers the two controllers use internally, so that each can be checked on its own against the reference's numba functions
 // (tests/test_transform_utils.py) and used by host code on whole batches of poses (av_aloha_b200/transform_utils.py).

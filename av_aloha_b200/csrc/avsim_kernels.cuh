@@ -491,15 +491,19 @@ __global__ void __launch_bounds__(32, AV_MIN_BLOCKS) avsim_forward_kernel(const 
 }
 
 // Sorts environments by the cycles they took in the previous step (descending) into B.order and rewinds the queue.
-// One block, bitonic sort of (cycles, env) keys in shared memory; n2 = num_envs rounded up to a power of two.
-__global__ void avsim_order_kernel(BatchState B, int n2) {
+// Bitonic sort of (cycles, env) keys in shared memory.  Up to `chunk` (<= 8192, a power of two) environments one block does
+// it all (n2 = num_envs rounded up to a power of two).  Larger batches: block c sorts environments [c chunk, (c+1) chunk) and
+// the sorted chunks are interleaved -- order = rank 0 of every chunk, rank 1 of every chunk, ... -- which is heaviest-first
+// to within one chunk's spread; that is all the queue needs (blocks of similar cost, the long environments early).
+__global__ void avsim_order_kernel(BatchState B, int n2, int chunk) {
     extern __shared__ unsigned long long av_keys[];
-    int n = B.num_envs;
+    const int c = blockIdx.x, nch = gridDim.x, e0 = c * chunk;
+    const int n = min(chunk, B.num_envs - e0);
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-        unsigned long long c = i < n ? (unsigned long long)B.env_cycles[i] : 0ull;
-        if (c > 0xffffffffffull) c = 0xffffffffffull;
+        unsigned long long cy = i < n ? (unsigned long long)B.env_cycles[e0 + i] : 0ull;
+        if (cy > 0xffffffffffull) cy = 0xffffffffffull;
         // key = cycles << 20 | (0xfffff - env): descending sort keeps ties in ascending env order; padding sorts last
-        av_keys[i] = i < n ? ((c << 20) | (unsigned long long)(0xfffff - i)) : 0ull;
+        av_keys[i] = i < n ? ((cy << 20) | (unsigned long long)(0xfffff - i)) : 0ull;
     }
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1)
@@ -514,8 +518,13 @@ __global__ void avsim_order_kernel(BatchState B, int n2) {
             }
             __syncthreads();
         }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) B.order[i] = 0xfffff - (int)(av_keys[i] & 0xfffff);
-    if (threadIdx.x == 0) *B.queue = 0;
+    // only the last chunk can be short (L environments): ranks below L interleave over all chunks, the rest over nch - 1
+    const int L = B.num_envs - (nch - 1) * chunk;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        int pos = r < L ? r * nch + c : L * nch + (r - L) * (nch - 1) + c;
+        B.order[pos] = e0 + 0xfffff - (int)(av_keys[r] & 0xfffff);
+    }
+    if (c == 0 && threadIdx.x == 0) *B.queue = 0;
 }
 __global__ void avsim_identity_order_kernel(BatchState B) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

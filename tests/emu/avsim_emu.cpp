@@ -122,7 +122,7 @@ void emu_forward(EmuBatch *b) { emu_forward_impl(b, 1); }
 void emu_step(EmuBatch *b, const float *action, int nsub) {
     int n2 = 1;
     while (n2 < b->st.num_envs) n2 <<= 1;
-    emu::run_block(0, 1, [&]() { avsim_order_kernel(b->st, n2); });   // same queue order as the device
+    emu::run_block(0, 1, [&]() { avsim_order_kernel(b->st, n2, 8192); });   // same queue order as the device
     if (b->st.solver == 1) {   // split pipeline, as avsim_step launches it
         for (int s = 0; s <= nsub; s++) {
             emu::run_block(0, 1, [&]() { avsim_substep_kernel(b->pk.dm, b->st, action, s, nsub); });

@@ -136,3 +136,34 @@ def test_force_cache_warm_start_parity(setup):
             assert ncon[e] == envs[e].ncon and rew[e] == r, (step, e)
             assert np.abs(qpos[e] - envs[e].qpos).max() <= 3e-4, (step, e)
     batch.close()
+
+
+def test_batches_above_one_sort_block_keep_the_cost_sorted_queue(setup, monkeypatch):
+    """More than 8192 environments in one queue: the order kernel sorts 8192-environment chunks in separate blocks and
+    interleaves them (round 1 fell back to the unsorted order).  Results must not depend on where an environment sits in the
+    queue: the first and last environments of a 9 000-environment batch step exactly like the same environments in a batch of 48."""
+    torch, capi, model, om, OracleEnv = setup
+    monkeypatch.setenv("AVSIM_GROUPS", "1")          # one queue for the whole batch (default: 3 groups of 3 000)
+    B, K = 9000, 24
+    rng = np.random.default_rng(5)
+    fp = np.zeros((B, 2, 3))
+    fp[:, 0] = [0.0, 0.12, 0.0]
+    fp[:, 1, 0] = rng.uniform(-0.1, 0.1, B)
+    fp[:, 1, 1] = -0.05
+    act = np.tile(_hold_action(model.njoints), (B, 1)).astype(np.float32)
+    act[:, 0] += rng.uniform(-0.2, 0.2, B).astype(np.float32)      # different arm motion per environment: different costs
+    big = capi.Batch(model, B, seed=1)
+    big.reset(free_pos=fp)
+    sel = np.r_[0:K, B - K:B]
+    small = capi.Batch(model, 2 * K, seed=1)
+    small.reset(free_pos=fp[sel])
+    for _ in range(3):                                # step 1 sorts on zero costs, steps 2-3 on the measured ones
+        big.step(torch.as_tensor(act, device="cuda"))
+        small.step(torch.as_tensor(act[sel], device="cuda"))
+    assert int(big.get(capi.STATUS).max().item()) == 0
+    qb, qs = big.get(capi.QPOS).cpu().numpy()[sel], small.get(capi.QPOS).cpu().numpy()
+    assert np.isfinite(qb).all() and np.array_equal(qb, qs)
+    cyc = big.get(capi.ENV_CYCLES).cpu().numpy()
+    assert (cyc > 0).all()                            # every environment was visited exactly once per step (a permutation)
+    big.close()
+    small.close()

@@ -182,6 +182,26 @@ def test_gpu_gradik(gold, gpu_model, arm):
     _check_gradik(ctl.run(*args), ctl8.run(*args), gold, arm, model_io.load_avm(gpu_model.avm_path))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("arm", [0, 2])
+def test_gpu_gradik_group_and_thread_kernels_agree(gold, gpu_model, arm, monkeypatch):
+    """The 16-lanes-per-problem kernel (small batches, low latency) and the thread-per-problem kernel (large batches) do the same
+    evaluations with the same arithmetic: both forms against the golden vectors, and against each other."""
+    from av_aloha_b200 import kinematics, model_io
+    n = (6, 6, 7)[arm]
+    kw = dict(kinematics.GRADIK_SIM, joint_center_weight=(10.0, 10.0, 1.0, 50.0, 1.0, 1.0, 1.0)[:n],
+              joint_displacement_weight=(50.0,) * n)
+    args = (gold[f"gradik_q_{arm}"], gold[f"gradik_pos_{arm}"], gold[f"gradik_quat_{arm}"])
+    out = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("AVSIM_GRADIK_GROUP", form)
+        ctl, ctl8 = kinematics.GradIK(gpu_model, arm, **kw), kinematics.GradIK(gpu_model, arm, **dict(kw, max_iterations=8))
+        out[form] = (ctl.run(*args), ctl8.run(*args))
+        _check_gradik(out[form][0], out[form][1], gold, arm, model_io.load_avm(gpu_model.avm_path))
+    assert np.abs(out["0"][1] - out["1"][1]).max() <= 1e-6       # 8 iterations: same iterates (fp32 output)
+    assert np.median(np.abs(out["0"][0] - out["1"][0])) <= 1e-6
+
+
 # ------------------------------------------------------------------ create_safety_fn (reference kinematics.py:54-135)
 SAFETY_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "safety_golden.npz")
 
