@@ -196,7 +196,7 @@ __device__ inline void collide_box_box(const Shape &A, const Shape &B, PrimOut &
 // the exact difference of the two fp32 support points.  In fp32 those triple products (three 5 cm vectors that differ by
 // millimetres) keep 2-4 significant digits, and whenever the origin ray leaves the Minkowski difference within ~1e-3 of an
 // edge the portal walked onto the neighbouring face: 5 % of the hull contacts of the bench workload came out with another
-// normal (up to 60 degrees off) and up to 0.9 mm another depth than the fp64 oracle (profiles/r2_mpr_fp64.txt).  The decisions
+// normal (up to 60 degrees off) and up to 0.9 mm another depth than the fp64 oracle (profiles/r2_newton_parity.txt, the MPR lines).  The decisions
 // are a few dozen scalar operations per iteration next to a scan over hundreds of vertices: B200's fp64 pipe makes them free.
 struct D3 {
     double x, y, z;

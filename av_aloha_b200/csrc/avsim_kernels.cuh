@@ -327,9 +327,9 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_step_kernel(const 
 // the lockstep blocks of the fused kernel every solve costs its block the iterations of the block's SLOWEST environment
 // (measured: 11 ms per step per mean Newton iteration; profiles/r2_summary.md), and letting the warps free-run through the
 // whole pipeline instead thrashes the instruction cache (AVSIM_SYNC=0: 73 vs 46 ms).  The solver kernel holds only the solver's
-// code, so its warps can free-run: one warp = one environment pulled from a cost-sorted queue, no barrier anywhere, an
-// environment that needs 17 iterations delays nobody.  The substep kernel keeps the lockstep blocks + pooled narrowphase for
-// everything else (whose cost per environment is far more uniform).
+// code and its own block shape (phase-locked warps, see avsim_solve_kernel): one warp = one environment pulled from a
+// cost-sorted queue, an environment that needs 17 iterations holds one warp for 17 trips and delays nobody else.  The substep
+// kernel keeps the lockstep blocks + pooled narrowphase for everything else (whose cost per environment is far more uniform).
 // What crosses the kernel boundary is the slice's head record (AV_HEAD_FLOATS floats, 6.7 KB: state, mass matrix and its
 // block inverse, smooth forces, scalar rows, contact ids) -- one bulk copy per direction through an L2-resident image -- and
 // the contact blocks, which already live in the global scratch.  Per env.step that is 2 x 20 x 6.7 KB x 2 = 0.5 MB per
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(con
 // fetches the next environment from the queue at the top of the next trip -- so an environment that needs 17 iterations holds
 // one warp for 17 trips and nobody else.  Why phase-locked: free-running warps (the first version of this kernel) spread over
 // 100 KB of solver code and ncu showed 'no_instruction' as 6.4 of the 12.4 stall cycles per issued instruction, at any
-// occupancy (profiles/r2_solve_kernel_ncu.txt) -- instruction fetch, not arithmetic, bounded it; in lockstep one fetched line
+// occupancy (profiles/r2_summary.md row 2; the final kernel: profiles/r2_step_kernels_ncu.txt) -- instruction fetch, not arithmetic, bounded it; in lockstep one fetched line
 // serves all the warps of the SM.  The noslip sweeps that follow the solve cost the same for every environment, so they run in
 // the substep kernel's lockstep blocks (start of the next launch), not here.
 __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_solve_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B) {
