@@ -410,6 +410,9 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(con
 // occupancy (profiles/r2_summary.md row 2; the final kernel: profiles/r2_step_kernels_ncu.txt) -- instruction fetch, not arithmetic, bounded it; in lockstep one fetched line
 // serves all the warps of the SM.  The noslip sweeps that follow the solve cost the same for every environment, so they run in
 // the substep kernel's lockstep blocks (start of the next launch), not here.
+#ifndef AV_NW_SYNC
+#define AV_NW_SYNC 4   // phase barriers per Newton trip besides the one at the top (sweep: profiles/r2_sweeps.txt)
+#endif
 __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_solve_kernel(const __grid_constant__ DevModel m, const __grid_constant__ BatchState B) {
     const int lane = threadIdx.x, warp = threadIdx.y;
     EnvS &S = *reinterpret_cast<EnvS *>(reinterpret_cast<char *>(av_smem_raw) + (size_t)warp * AV_SOLVER_SLICE_BYTES);
@@ -423,6 +426,8 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_solve_kernel(const
     int env = 0;
     float *scratch = nullptr, *img = nullptr;
     long long t0 = 0;
+    Prof pf;   // -DAVSIM_PROFILE: own cycles per phase + cycles spent waiting at the phase barriers
+    pf.start();
     for (;;) {
         if (!run && !drained) {   // ---- fetch: next environment of the cost-sorted queue, record in, start point
             int idx = 0;
@@ -439,14 +444,28 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_solve_kernel(const
             } else
                 drained = true;
         }
+        pf.mark(PF_NW_INIT, lane);
         if (!__syncthreads_or(run ? 1 : 0)) break;
+        pf.mark(PF_NW_WAIT, lane);
         bool stop = false;
         if (run) stop = nw.grad(m, S, scratch, lane, B.newton_iters, B.newton_tol);
+        pf.mark(PF_NW_GRAD, lane);
+#if AV_NW_SYNC >= 4
         __syncthreads();
+        pf.mark(PF_NW_WAIT, lane);
+#endif
         if (run && !stop) nw.hess(m, S, scratch, lane);
+        pf.mark(PF_NW_HESS, lane);
+#if AV_NW_SYNC >= 2
         __syncthreads();
+        pf.mark(PF_NW_WAIT, lane);
+#endif
         if (run && !stop) stop = nw.dir(m, S, lane, B.newton_tol);
+        pf.mark(PF_NW_CHOL, lane);
+#if AV_NW_SYNC >= 3
         __syncthreads();
+        pf.mark(PF_NW_WAIT, lane);
+#endif
         if (run && !stop) stop = nw.search(m, S, scratch, lane, B.newton_ls);
         if (run && stop) {   // converged (or out of descent in fp32, or at the cap): forces out, record back to the image
             float gr = 0.f;
@@ -459,7 +478,9 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_solve_kernel(const
             if (lane == 0) B.env_cycles_b[env] += clock64() - t0;
             run = false;
         }
+        pf.mark(PF_NW_LS, lane);
         __syncthreads();
+        pf.mark(PF_NW_WAIT, lane);
     }
 }
 

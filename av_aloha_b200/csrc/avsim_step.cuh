@@ -18,7 +18,7 @@ static_assert((AV_CB_GEO * 4) % 16 == 0 && (AV_CBLK * 4) % 16 == 0, "bulk copies
 
 // ---- optional per-stage cycle counters (-DAVSIM_PROFILE; read back with avsim_stage_cycles)
 enum { PF_LOAD = 0, PF_KIN, PF_INERTIA, PF_BROAD, PF_PRIM, PF_CONVEX, PF_SMOOTH, PF_ROWS_S, PF_ROWS_C, PF_SOLVE, PF_INTEGRATE,
-       PF_OUT, PF_NW_INIT, PF_NW_GRAD, PF_NW_HESS, PF_NW_CHOL, PF_NW_LS, PF_N };
+       PF_OUT, PF_NW_INIT, PF_NW_GRAD, PF_NW_HESS, PF_NW_CHOL, PF_NW_LS, PF_NW_WAIT, PF_N };
 #ifdef AVSIM_PROFILE
 __device__ unsigned long long g_prof[PF_N];
 struct Prof {

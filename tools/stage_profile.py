@@ -18,7 +18,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 nsteps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 NAMES = ["load", "kinematics", "inertia", "broadphase", "prim_narrow", "convex_narrow", "smooth", "rows_scalar",
-         "rows_contact", "solve", "integrate", "outputs", "newton_init", "newton_grad", "newton_hess", "newton_chol", "newton_ls"]
+         "rows_contact", "solve", "integrate", "outputs", "newton_init", "newton_grad", "newton_hess", "newton_chol", "newton_ls", "newton_wait"]
 model, batch, acts, masks, mask_any, fp, t0 = steady.restore(B, iters)
 batch.set_solver(os.environ.get('SOLVER', 'newton'))
 lib = capi.load_library()
