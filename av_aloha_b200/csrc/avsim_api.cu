@@ -183,7 +183,17 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     const char *ee = getenv("AVSIM_ENVW");
     b->warps = ew ? atoi(ew) : AV_DEFAULT_WARPS;
     b->warps = std::max(1, std::min(b->warps, AV_MAX_WARPS));
-    b->envw = ee ? atoi(ee) : std::min(b->warps, AV_DEFAULT_ENVW);
+    // environment groups of the split pipeline (decided first: the block shapes below follow the size of a group)
+    const char *eg = getenv("AVSIM_GROUPS");
+    int ng = eg ? atoi(eg) : 3;
+    ng = std::max(1, std::min(ng, AV_MAX_GROUPS));
+    while (ng > 1 && num_envs / ng < AV_DEFAULT_ENVW * sms / 2) ng--;   // a group should still be a good fraction of a wave
+    // Small batches: spread a group over ALL SMs instead of filling 11-slice blocks on a few of them -- the step is bound by the
+    // serial latency of an environment, and an environment alone on an SM (all helper warps on its hull pairs, no lockstep
+    // partners, the whole L1) runs a substep in 0.85 ms instead of 1.25 ms (profiles/r2_sweeps.txt: B = 128: 25.1 -> 17.1 ms,
+    // B = 512: 27.0 -> 20.5 ms).  From 11 x 148 environments per group on, the shapes are the large-batch optimum (11 slices, 8 solve warps).
+    const int per_sm_envs = std::max(1, ((num_envs + ng - 1) / ng + sms - 1) / sms);
+    b->envw = ee ? atoi(ee) : std::min(b->warps, per_sm_envs >= 9 ? AV_DEFAULT_ENVW : per_sm_envs);   // 9, 10 measured slower than 11 at B = 4096
     b->envw = std::max(1, std::min(b->envw, std::min(b->warps, std::min(AV_MAX_ENVW, (smem_blk - 64) / esz))));
     s.env_warps = b->envw;
     const char *ek = getenv("AVSIM_KEY");
@@ -196,17 +206,13 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     CUP(cudaFuncSetAttribute(avsim_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
     {   // solver kernel: one block per SM of `solve_warps` phase-locked warps, one environment slice each
         const char *esw = getenv("AVSIM_SOLVE_WARPS"), *esp = getenv("AVSIM_SPLIT");
-        int sw = esw ? atoi(esw) : 8;   // 8 slices leave the SM ~170 KB of L1 for the contact blocks; 6..16 measure within 2 % (profiles/r2_sweeps.txt)
+        int sw = esw ? atoi(esw) : std::min(8, per_sm_envs);   // 8 slices leave the SM ~170 KB of L1 for the contact blocks; 6..16 measure within 2 % (profiles/r2_sweeps.txt)
         sw = std::max(1, std::min(sw, std::min(AV_MAX_WARPS, (smem_blk - 1024) / (int)AV_SOLVER_SLICE_BYTES)));
         b->solve_warps = sw;
         CUP(cudaFuncSetAttribute(avsim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sw * (int)AV_SOLVER_SLICE_BYTES));
         b->solve_grid = std::min((num_envs + sw - 1) / sw, sms);
         b->solve_per_sm = 1;
         b->split = esp ? atoi(esp) : 1;
-        const char *eg = getenv("AVSIM_GROUPS");
-        int ng = eg ? atoi(eg) : 3;
-        ng = std::max(1, std::min(ng, AV_MAX_GROUPS));
-        while (ng > 1 && num_envs / ng < b->envw * sms / 2) ng--;   // a group should still be a good fraction of a wave
         b->ngroups = ng;
         for (int g = 0; g < ng && ng > 1; g++) {
             CUP(cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking));
