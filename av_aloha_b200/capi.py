@@ -23,7 +23,7 @@ SYMBOLS = [
     "avsim_model_load", "avsim_model_free", "avsim_model_dim", "avsim_create", "avsim_destroy", "avsim_set_options",
     "avsim_reset", "avsim_step", "avsim_forward", "avsim_get", "avsim_set", "avsim_step_host", "avsim_launch_count",
     "avsim_diffik", "avsim_gradik", "avsim_fk", "avsim_last_error", "avsim_stage_cycles", "avsim_render", "avsim_set_warmstart",
-    "avsim_pixels_to_float", "avsim_jac", "avsim_set_solver", "avsim_transform", "avsim_render_ids",
+    "avsim_pixels_to_float", "avsim_jac", "avsim_set_solver", "avsim_transform", "avsim_render_ids", "avsim_launch_shape",
 ]
 SOLVER_PGS, SOLVER_NEWTON = 0, 1
 
@@ -72,6 +72,7 @@ def load_library():
     L.avsim_render_ids.argtypes = [vp, C.POINTER(C.c_int), i32, i32, i32, vp]
     L.avsim_pixels_to_float.argtypes = [vp, C.c_int64, i32, i32, vp, i32, vp]
     L.avsim_launch_count.restype = C.c_int64; L.avsim_launch_count.argtypes = [vp]
+    L.avsim_launch_shape.argtypes = [vp, C.POINTER(C.c_int)]
     L.avsim_diffik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(DiffIKParams), vp, vp]
     L.avsim_gradik.argtypes = [vp, i32, vp, vp, vp, i32, C.POINTER(GradIKParams), vp, vp]
     L.avsim_fk.argtypes = [vp, i32, vp, i32, vp, vp]
@@ -274,3 +275,10 @@ class Batch:
     @property
     def launch_count(self):
         return int(self.lib.avsim_launch_count(self.ptr))
+
+    @property
+    def launch_shape(self):
+        """{'split', 'groups', 'warps', 'env_warps', 'solve_warps', 'sms'}: how avsim_create laid this batch out on the GPU"""
+        out = (C.c_int * 6)()
+        check(self.lib.avsim_launch_shape(self.ptr, out))
+        return dict(zip(("split", "groups", "warps", "env_warps", "solve_warps", "sms"), (int(v) for v in out)))

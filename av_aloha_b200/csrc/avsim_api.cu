@@ -17,6 +17,7 @@
 #include "avsim_render.cuh"
 
 #define AV_SORT_MAX 8192
+#define AV_SPLIT_MIN_ENVS_PER_SM 17
 #define AV_GRADIK_GROUP_MAX 4096   // crossover measured between 4096 and 16384 problems (profiles/r2_ik_bench.txt)
 #define AV_MAX_GROUPS 8
 #ifndef AV_DEFAULT_HEAVY_TASKS
@@ -201,18 +202,25 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     int per_sm = eb ? atoi(eb) : std::max(1, smem_sm / (b->envw * esz + 1024));
     per_sm = std::max(1, std::min(per_sm, smem_sm / (b->envw * esz + 1024)));
     per_sm = std::max(1, std::min(per_sm, 64 / b->warps));                    // 64 resident warps per SM
-    CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
+    // the attribute belongs to the function, not to the batch: batches of different shapes coexist in one process, so it is
+    // always set to the largest block any of them may launch
+    const int max_slices = std::min(AV_MAX_ENVW, (smem_blk - 64) / esz);
+    CUP(cudaFuncSetAttribute(avsim_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_slices * esz));
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
-    CUP(cudaFuncSetAttribute(avsim_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->envw * esz));
+    CUP(cudaFuncSetAttribute(avsim_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_slices * esz));
     {   // solver kernel: one block per SM of `solve_warps` phase-locked warps, one environment slice each
         const char *esw = getenv("AVSIM_SOLVE_WARPS"), *esp = getenv("AVSIM_SPLIT");
         int sw = esw ? atoi(esw) : std::min(8, per_sm_envs);   // 8 slices leave the SM ~170 KB of L1 for the contact blocks; 6..16 measure within 2 % (profiles/r2_sweeps.txt)
         sw = std::max(1, std::min(sw, std::min(AV_MAX_WARPS, (smem_blk - 1024) / (int)AV_SOLVER_SLICE_BYTES)));
         b->solve_warps = sw;
-        CUP(cudaFuncSetAttribute(avsim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sw * (int)AV_SOLVER_SLICE_BYTES));
+        CUP(cudaFuncSetAttribute(avsim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 std::min(AV_MAX_WARPS, (smem_blk - 1024) / (int)AV_SOLVER_SLICE_BYTES) * (int)AV_SOLVER_SLICE_BYTES));
         b->solve_grid = std::min((num_envs + sw - 1) / sw, sms);
         b->solve_per_sm = 1;
-        b->split = esp ? atoi(esp) : 1;
+        // split pipeline from ~17 environments per SM on; below, the fused kernel (one launch per env.step: no launch gaps, no record
+        // round trips) is faster: B = 128 / 512 / 1024 / 2048: 16.0 / 19.1 / 24.2 / 27.1 ms fused vs 17.1 / 20.5 / 25.8 / 29.2 split;
+        // B = 4096: 47.5 fused vs 40.0 split (profiles/r2_sweeps.txt)
+        b->split = esp ? atoi(esp) : (num_envs > AV_SPLIT_MIN_ENVS_PER_SM * sms ? 1 : 0);
         b->ngroups = ng;
         for (int g = 0; g < ng && ng > 1; g++) {
             CUP(cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking));
@@ -520,6 +528,12 @@ extern "C" int avsim_stage_cycles(uint64_t *out_host, int n, int reset) {
 }
 
 extern "C" int64_t avsim_launch_count(const avsim_batch *b) { return b ? b->launches : 0; }
+extern "C" int avsim_launch_shape(const avsim_batch *b, int out[6]) {
+    if (!b || !out) return fail(AVSIM_ERR_ARG, "avsim_launch_shape: null argument");
+    out[0] = (b->split && b->st.solver == AVSIM_SOLVER_NEWTON) ? 1 : 0;
+    out[1] = out[0] ? b->ngroups : 1; out[2] = b->warps; out[3] = b->envw; out[4] = b->solve_warps; out[5] = b->sms;
+    return AVSIM_OK;
+}
 
 // ------------------------------------------------------------------ IK entry points
 extern "C" int avsim_diffik(const avsim_model *m, int arm, const float *q, const float *pos, const float *quat, int n,

@@ -432,7 +432,8 @@ def run_gpu(args):
         peak, how = peaks()
         kern_avg_ms = total_ms / args.steps
         achieved = ALGO_BYTES_PER_ENV_STEP * B / (kern_avg_ms * 1e-3) / 1e9
-        split = args.solver == "newton" and os.environ.get("AVSIM_SPLIT", "1") != "0"
+        shape = batch.launch_shape
+        split = bool(shape["split"])
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kern_avg_ms, "higher_is_better": True, "scaling": args.scaling,
@@ -444,9 +445,10 @@ def run_gpu(args):
                                  else f"PGS {args.solver_iters} sweeps + 3 noslip, warm start {args.warmstart}",
                        "parallelism": f"env-sharded x{world}",
                        "kernel_shape": ("split pipeline per substep: avsim_substep_kernel (1 block/SM of 16 lockstep warps: 11 environment "
-                                        "slices + 5 narrowphase helpers) -> avsim_solve_kernel (free-running warps, 1 environment each); "
-                                        "4 environment groups on 4 streams; head records moved by cp.async.bulk") if split else
-                                       "fused step kernel, 1 block/SM of 16 lockstep warps",
+                                        "slices + 5 narrowphase helpers) -> avsim_solve_kernel (8 phase-locked warps per block, 1 environment each); "
+                                        f"{shape['groups']} environment groups on separate streams; head records moved by cp.async.bulk") if split else
+                                       f"fused step kernel, 1 block/SM of {shape['warps']} lockstep warps ({shape['env_warps']} environment slices)",
+                       "launch_shape": shape,
                        "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
                        "timing": "sum of per-step CUDA event pairs on the launching stream, max over ranks"},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(B * model.njoints * 4),

@@ -122,6 +122,11 @@ int avsim_step_host(avsim_batch *b, const float *action_host, int nsubsteps, flo
 
 /* number of kernel launches issued by this batch so far (bench.py's gpu_launches) */
 int64_t avsim_launch_count(const avsim_batch *b);
+/* how this batch is launched (chosen by avsim_create from the batch size, or by the AVSIM_* diagnostic variables):
+ * out[0] = 1 split pipeline (substep + solve kernels) / 0 fused step kernel, out[1] = environment groups (streams),
+ * out[2] = warps per block, out[3] = of which own an environment slice, out[4] = warps per solve block, out[5] = SMs.
+ * Diagnostics only: no reference call corresponds (the reference steps one environment per process). */
+int avsim_launch_shape(const avsim_batch *b, int out[6]);
 
 /* diagnostics: per-stage SM cycle counters summed over warps (only in a -DAVSIM_PROFILE build; otherwise returns
  * AVSIM_ERR_ARG).  Stages: load, kinematics, inertia, broadphase, primitive narrowphase, convex narrowphase, smooth,

@@ -144,6 +144,7 @@ def test_batches_above_one_sort_block_keep_the_cost_sorted_queue(setup, monkeypa
     queue: the first and last environments of a 9 000-environment batch step exactly like the same environments in a batch of 48."""
     torch, capi, model, om, OracleEnv = setup
     monkeypatch.setenv("AVSIM_GROUPS", "1")          # one queue for the whole batch (default: 3 groups of 3 000)
+    monkeypatch.setenv("AVSIM_SPLIT", "1")           # same launch form for both batch sizes (small batches default to the fused kernel)
     B, K = 9000, 24
     rng = np.random.default_rng(5)
     fp = np.zeros((B, 2, 3))

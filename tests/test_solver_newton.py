@@ -205,8 +205,11 @@ def test_gpu_contact_records_match_oracle_narrowphase(task):
 
 
 @pytest.mark.gpu
-def test_gpu_bench_workload_trajectory_next_to_oracle():
-    """64 environments of the bench workload (scripted reach / grasp / lift, staggered phases) for 60 env.steps = 1200
+@pytest.mark.parametrize("pipeline", ["split", "fused"])
+def test_gpu_bench_workload_trajectory_next_to_oracle(pipeline, monkeypatch):
+    """Both launch forms of env.step -- the split pipeline (substep + solve kernels, what batches above ~2 500 environments run)
+    and the fused step kernel (small batches) -- forced here by AVSIM_SPLIT, same bound for both:
+    64 environments of the bench workload (scripted reach / grasp / lift, staggered phases) for 60 env.steps = 1200
     substeps next to the fp64 oracle: same rewards and contact counts almost everywhere, joint positions within 2e-3 rad
     (median 1e-4) -- contact-rich trajectories separate at the rate the contact-set flips of fp32 vs fp64 allow"""
     import torch
@@ -219,7 +222,9 @@ def test_gpu_bench_workload_trajectory_next_to_oracle():
     obj = workload.sample_object_positions(B, 1234)
     acts = workload.slot_insertion_script(bench.EPISODE_LEN, obj, 1234)
     model = capi.Model(path, 0)
+    monkeypatch.setenv("AVSIM_SPLIT", "1" if pipeline == "split" else "0")
     b = capi.Batch(model, B, seed=1234)
+    assert b.launch_shape["split"] == (pipeline == "split")
     b.reset(free_pos=obj)
     om = OracleModel(path)
     envs = []
@@ -248,7 +253,7 @@ def test_gpu_bench_workload_trajectory_next_to_oracle():
                 dq.append(float(np.abs(qpos[e, :23] - envs[e].qpos[:23]).max()))
     assert int(b.get(capi.STATUS).max().item()) == 0
     dq = np.array(dq)
-    print(f"\n[trajectory] same reward {rew_same}/{B * T}, same contact count {con_same}/{B * T}; |dq|inf after {T} steps: "
+    print(f"\n[trajectory, {pipeline}] same reward {rew_same}/{B * T}, same contact count {con_same}/{B * T}; |dq|inf after {T} steps: "
           f"median {np.median(dq):.1e} p90 {np.quantile(dq, 0.9):.1e} max {dq.max():.1e}")
     assert rew_same >= 0.98 * B * T and con_same >= 0.85 * B * T, (rew_same, con_same)
     assert np.median(dq) <= 2e-4 and np.quantile(dq, 0.9) <= 5e-3, (float(np.median(dq)), float(np.quantile(dq, 0.9)), float(dq.max()))
