@@ -189,12 +189,20 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     int ng = eg ? atoi(eg) : 3;
     ng = std::max(1, std::min(ng, AV_MAX_GROUPS));
     while (ng > 1 && num_envs / ng < AV_DEFAULT_ENVW * sms / 2) ng--;   // a group should still be a good fraction of a wave
-    // Small batches: spread a group over ALL SMs instead of filling 11-slice blocks on a few of them -- the step is bound by the
-    // serial latency of an environment, and an environment alone on an SM (all helper warps on its hull pairs, no lockstep
-    // partners, the whole L1) runs a substep in 0.85 ms instead of 1.25 ms (profiles/r2_sweeps.txt: B = 128: 25.1 -> 17.1 ms,
-    // B = 512: 27.0 -> 20.5 ms).  From 11 x 148 environments per group on, the shapes are the large-batch optimum (11 slices, 8 solve warps).
+    // split pipeline from ~17 environments per SM on; below, the fused kernel (one launch per env.step: no launch gaps, no record
+    // round trips) is faster: B = 128 / 512 / 1024 / 2048: 16.0 / 19.1 / 24.2 / 27.1 ms fused vs 17.1 / 20.5 / 25.8 / 29.2 split;
+    // B = 4096: 47.5 fused vs 40.0 split (profiles/r2_sweeps.txt)
+    const char *esp = getenv("AVSIM_SPLIT");
+    b->split = esp ? atoi(esp) : (num_envs > AV_SPLIT_MIN_ENVS_PER_SM * sms ? 1 : 0);
+    // Block shapes follow the batch size.  The step is bound by the serial latency of an environment, and an environment with
+    // fewer lockstep partners (more helper warps on its hull pairs, more L1, no waiting for a partner's Newton iterations) runs
+    // a substep faster: alone on an SM 0.8 ms instead of 1.25 ms.  Fused kernel: about two rounds of blocks over the SMs --
+    // ceil(B / 2 SMs) slices (measured best at B = 512 / 1024 / 1536 / 2048: 2-3 / 4 / 6 / 7 slices; 11 slices at 1536: 30.8 vs
+    // 23.2 ms).  Split pipeline: one round per group, ceil(B / groups / SMs) slices, 11 from 9 up (9, 10 measured slower at 4096).
     const int per_sm_envs = std::max(1, ((num_envs + ng - 1) / ng + sms - 1) / sms);
-    b->envw = ee ? atoi(ee) : std::min(b->warps, per_sm_envs >= 9 ? AV_DEFAULT_ENVW : per_sm_envs);   // 9, 10 measured slower than 11 at B = 4096
+    const int fused_envs = std::max(1, (num_envs + 2 * sms - 1) / (2 * sms));
+    const int auto_envw = b->split ? (per_sm_envs >= 9 ? AV_DEFAULT_ENVW : per_sm_envs) : std::min(AV_DEFAULT_ENVW, fused_envs);
+    b->envw = ee ? atoi(ee) : std::min(b->warps, auto_envw);
     b->envw = std::max(1, std::min(b->envw, std::min(b->warps, std::min(AV_MAX_ENVW, (smem_blk - 64) / esz))));
     s.env_warps = b->envw;
     const char *ek = getenv("AVSIM_KEY");
@@ -209,7 +217,7 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     CUP(cudaFuncSetAttribute(avsim_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, esz));
     CUP(cudaFuncSetAttribute(avsim_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_slices * esz));
     {   // solver kernel: one block per SM of `solve_warps` phase-locked warps, one environment slice each
-        const char *esw = getenv("AVSIM_SOLVE_WARPS"), *esp = getenv("AVSIM_SPLIT");
+        const char *esw = getenv("AVSIM_SOLVE_WARPS");
         int sw = esw ? atoi(esw) : std::min(8, per_sm_envs);   // 8 slices leave the SM ~170 KB of L1 for the contact blocks; 6..16 measure within 2 % (profiles/r2_sweeps.txt)
         sw = std::max(1, std::min(sw, std::min(AV_MAX_WARPS, (smem_blk - 1024) / (int)AV_SOLVER_SLICE_BYTES)));
         b->solve_warps = sw;
@@ -217,10 +225,6 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
                                  std::min(AV_MAX_WARPS, (smem_blk - 1024) / (int)AV_SOLVER_SLICE_BYTES) * (int)AV_SOLVER_SLICE_BYTES));
         b->solve_grid = std::min((num_envs + sw - 1) / sw, sms);
         b->solve_per_sm = 1;
-        // split pipeline from ~17 environments per SM on; below, the fused kernel (one launch per env.step: no launch gaps, no record
-        // round trips) is faster: B = 128 / 512 / 1024 / 2048: 16.0 / 19.1 / 24.2 / 27.1 ms fused vs 17.1 / 20.5 / 25.8 / 29.2 split;
-        // B = 4096: 47.5 fused vs 40.0 split (profiles/r2_sweeps.txt)
-        b->split = esp ? atoi(esp) : (num_envs > AV_SPLIT_MIN_ENVS_PER_SM * sms ? 1 : 0);
         b->ngroups = ng;
         for (int g = 0; g < ng && ng > 1; g++) {
             CUP(cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking));
