@@ -291,32 +291,47 @@ __global__ void __launch_bounds__(AV_RT_THREADS) avsim_render_kernel(const __gri
     }
     __syncthreads();
     const int ng = min(s_n, AV_RT_MAXG);
-    // each warp shades 8 x 4 pixel blocks; per block the lanes first cull the region's candidates against the block's
-    // footprint (one or two candidates per lane, one ballot each), so the ray loop visits only geoms that overlap these 32 pixels
-    for (int sb = wq; sb < (AV_RT_W / 8) * (AV_RT_H / 4); sb += AV_RT_THREADS / 32) {
-        const int sbx = sb % (AV_RT_W / 8), sby = sb / (AV_RT_W / 8);
-        const int lx = sbx * 8 + (ln & 7), ly = sby * 4 + (ln >> 3);
-        const int px = tx * AV_RT_W + lx, py = ty * AV_RT_H + ly;
+    // each warp shades the 8 x 4 pixel blocks of one 8-pixel column strip of the region.  The lanes keep the screen extents of
+    // "their" one or two candidates in registers (x test once per strip); per block a ballot of the y / diagonal tests gives the
+    // candidates that overlap these 32 pixels, so the ray loop visits only those
+    static_assert(AV_RT_W / 8 == AV_RT_THREADS / 32, "one column strip per warp");
+    const int sbx = wq, lx = sbx * 8 + (ln & 7), px = tx * AV_RT_W + lx;
+    const float bx0 = (float)(tx * AV_RT_W + sbx * 8), bx1 = bx0 + 8.f;
+    float cr[AV_RT_MAXG / 32][8];
+    bool xin[AV_RT_MAXG / 32];
+#pragma unroll
+    for (int h = 0; h < AV_RT_MAXG / 32; h++) {
+        const int k = ln + 32 * h;
+        xin[h] = false;
+        if (k < ng) {
+            const RGeom &G = sg[k];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { cr[h][i] = G.rect[i]; cr[h][4 + i] = G.diag[i]; }
+            xin[h] = !(cr[h][0] >= bx1 || cr[h][2] < bx0);
+        }
+    }
+    // ray direction = normalize(Rc (x, y, -1)): the x part is fixed per lane, only y changes from block to block
+    const float inv_w = 2.f / W, inv_h = 2.f / H;
+    const float rx = ((px + 0.5f) * inv_w - 1.f) * th * aspect;
+    const V3 dx = v3(Rc.m[0] * rx - Rc.m[2], Rc.m[3] * rx - Rc.m[5], Rc.m[6] * rx - Rc.m[8]);
+    for (int sby = 0; sby < AV_RT_H / 4; sby++) {
+        const int ly = sby * 4 + (ln >> 3), py = ty * AV_RT_H + ly;
         unsigned int mask[AV_RT_MAXG / 32];
         {
-            const float bx0 = (float)(tx * AV_RT_W + sbx * 8), by0 = (float)(ty * AV_RT_H + sby * 4), bx1 = bx0 + 8.f, by1 = by0 + 4.f;
+            const float by0 = (float)(ty * AV_RT_H + sby * 4), by1 = by0 + 4.f;
 #pragma unroll
             for (int h = 0; h < AV_RT_MAXG / 32; h++) {
-                const int k = ln + 32 * h;
-                bool in = false;
                 if (32 * h >= ng) { mask[h] = 0u; continue; }   // uniform: most regions keep fewer than 32 candidates
-                if (k < ng) {
-                    const RGeom &G = sg[k];
-                    in = !(G.rect[0] >= bx1 || G.rect[2] < bx0 || G.rect[1] >= by1 || G.rect[3] < by0 || G.diag[0] > bx1 + by1 ||
-                           G.diag[2] < bx0 + by0 || G.diag[1] > bx1 - by0 || G.diag[3] < bx0 - by1);
-                }
+                const bool in = xin[h] && !(cr[h][1] >= by1 || cr[h][3] < by0 || cr[h][4] > bx1 + by1 || cr[h][6] < bx0 + by0 ||
+                                            cr[h][5] > bx1 - by0 || cr[h][7] < bx0 - by1);
                 mask[h] = __ballot_sync(0xffffffffu, in);
             }
         }
         V3 d;
         {
-            float x = (2.f * (px + 0.5f) / W - 1.f) * th * aspect, y = (1.f - 2.f * (py + 0.5f) / H) * th;
-            d = normalized(mul(Rc, v3(x, y, -1.f)));
+            const float ry = (1.f - (py + 0.5f) * inv_h) * th;
+            const V3 du = v3(dx.x + Rc.m[1] * ry, dx.y + Rc.m[4] * ry, dx.z + Rc.m[7] * ry);
+            d = du * rsqrtf(dot(du, du));
         }
         float best = 1e30f;
         V3 bn = v3(0, 0, 1);
