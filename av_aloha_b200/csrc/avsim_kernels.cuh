@@ -43,6 +43,12 @@ __device__ inline void env_load(const DevModel &m, const BatchState &B, EnvS &S,
     if (lane == 0) { S.status = 0; S.ncon = 0; S.nsc = 0; }
     __syncwarp();
 }
+// split pipeline: 0 = the noslip sweeps run at the start of the next substep kernel launch (lockstep blocks: their cost is the same
+// for every environment), 1 = at the end of the solve kernel on the warp that holds the solution.  Measured: 40.1 vs 45.7 ms
+// per env.step at B = 4096 (profiles/r2_sweeps.txt) -- in the solve kernel the sweeps stretch the trip of every phase-locked block.
+#ifndef AV_NOSLIP_IN_SOLVE
+#define AV_NOSLIP_IN_SOLVE 0
+#endif
 // ---- the head record of a slice <-> its image in global memory (split pipeline).  On the device one lane issues ONE bulk
 // asynchronous copy (TMA engine: cp.async.bulk, UBLKCP in SASS) per direction and the warp waits on an mbarrier / bulk group;
 // -DAV_TMA_HEAD=0 falls back to 128-bit loads and stores by all lanes (the A/B is in profiles/).
@@ -376,10 +382,12 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_substep_kernel(con
             pf.mark(PF_LOAD, lane);
             __syncwarp();
         }
-        if (s > 0) {   // the noslip sweeps on the solver's forces (same work for every environment: lockstep), then the integrator
+        if (s > 0) {   // [the noslip sweeps on the solver's forces,] then the integrator
+#if !AV_NOSLIP_IN_SOLVE
             AV_STAGE_SYNC(stage_solve_begin(m, S, scratch, lane, 3));
             for (int it = 0; it < B.noslip_iters; it++) AV_STAGE_SYNC(solve_sweep(m, S, scratch, lane, true, true));
             pf.mark(PF_SOLVE, lane);
+#endif
             AV_STAGE_SYNC(stage_integrate(m, S, lane); pf.mark(PF_INTEGRATE, lane));
         }
         AV_STAGE_SYNC(stage_kinematics(m, S, lane); pf.mark(PF_KIN, lane); if (s < nsub) { stage_inertia(m, S, lane); pf.mark(PF_INERTIA, lane); });
@@ -470,6 +478,11 @@ __global__ void __launch_bounds__(32 * AV_MAX_WARPS, 1) avsim_solve_kernel(const
         if (run && stop) {   // converged (or out of descent in fp32, or at the cap): forces out, record back to the image
             float gr = 0.f;
             nw.publish(S, lane, gr);
+#if AV_NOSLIP_IN_SOLVE
+            // experiment (see the macro): the noslip sweeps on the warp that still holds the solution in shared memory
+            stage_solve_begin(m, S, scratch, lane, 3);
+            for (int it = 0; it < B.noslip_iters; it++) solve_sweep(m, S, scratch, lane, true, true);
+#endif
             if (lane == 0) {
                 float *o = B.nw_stat + 4 * (size_t)env;
                 o[0] += (float)nw.it; o[1] = fmaxf(o[1], gr); o[2] = fmaxf(o[2], (float)nw.it); o[3] += nw.it >= B.newton_iters ? 1.f : 0.f;
