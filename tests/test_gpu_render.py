@@ -1,7 +1,9 @@
 """GPU tests of the camera renderer (K9).  There is no pixel oracle (no GL context, and the reference declares its
 renders non-deterministic, gym_guided_vision/__init__.py:92-94), so these tests pin what CAN be pinned: the camera
 model (a known world point lands on the pixel the MuJoCo pin-hole convention predicts: -Z forward, +Y up, vertical
-fovy), determinism, the output layout, and that body-mounted cameras follow their body."""
+fovy), determinism, the output layout, that body-mounted cameras follow their body, and -- through the id-buffer hook
+avsim_render_ids -- that every mesh geom is drawn inside (and, where nothing occludes it, over) the projection of its convex
+hull: silhouette IoU of the 26-DOP stand-ins against the hulls' projected vertices."""
 import numpy as np
 import pytest
 
