@@ -193,6 +193,20 @@ class GuidedVisionEnv(_EnvBase):
         """225 x 300 frame of the overhead camera (reference env.py:195-200)"""
         return self._batch.render(self._render_cam, 225, 300).cpu().numpy()[0, 0]
 
+    # -- viewer (reference env.py:373-392 opens mujoco.viewer.launch_passive, an interactive GL window, and syncs it).  There is
+    # no window system behind a batched GPU simulator; the two calls keep their names and meaning as far as a headless process
+    # can: create_viewer registers the key callback (never invoked: there is no keyboard), render_viewer refreshes `viewer_frame`,
+    # a 480 x 640 overhead frame a caller may show with whatever it has (cv2.imshow, a notebook), and returns it.
+    def create_viewer(self, key_callback=None) -> None:
+        self._viewer_key_callback = key_callback
+        self.viewer_frame = None
+
+    def render_viewer(self):
+        if not hasattr(self, "viewer_frame"):
+            self.create_viewer()
+        self.viewer_frame = self._batch.render(self._render_cam, 480, 640).cpu().numpy()[0, 0]
+        return self.viewer_frame
+
     # -- stepping (reference env.py:203-226, 255-269)
     def step_action(self, action):
         a = np.asarray(action, np.float32).reshape(1, self.num_joints)

@@ -246,6 +246,17 @@ def test_set_qpos_then_get_reward_reads_the_forward_state():
     e.close()
 
 
+def test_viewer_calls_exist_and_refresh_a_frame():
+    """reference env.py:373-392: create_viewer(key_callback) / render_viewer() -- headless stand-ins (no GL window on a GPU box)"""
+    from av_aloha_b200 import env
+    e = env.SlotInsertionEnv(num_arms=3, cameras=[])
+    e.reset()
+    e.create_viewer(key_callback=lambda key: None)
+    f = e.render_viewer()
+    assert f.shape == (480, 640, 3) and f.dtype == np.uint8 and f is e.viewer_frame and f.std() > 5
+    e.close()
+
+
 def test_hide_and_show_middle_arm():
     """reference env.py:394-398 (used by data_collection_scripts/replay_sim_episode.py:59 on a 3-arm env): the middle arm leaves
     the picture, the joint state stays, stepping still takes 21-dim actions; show_middle_arm restores the view"""
