@@ -196,11 +196,15 @@ extern "C" avsim_batch *avsim_create(const avsim_model *m, int num_envs, uint64_
     b->split = esp ? atoi(esp) : (num_envs > AV_SPLIT_MIN_ENVS_PER_SM * sms ? 1 : 0);
     // Block shapes follow the batch size.  The step is bound by the serial latency of an environment, and an environment with
     // fewer lockstep partners (more helper warps on its hull pairs, more L1, no waiting for a partner's Newton iterations) runs
-    // a substep faster: alone on an SM 0.8 ms instead of 1.25 ms.  Fused kernel: about two rounds of blocks over the SMs --
-    // ceil(B / 2 SMs) slices (measured best at B = 512 / 1024 / 1536 / 2048: 2-3 / 4 / 6 / 7 slices; 11 slices at 1536: 30.8 vs
-    // 23.2 ms).  Split pipeline: one round per group, ceil(B / groups / SMs) slices, 11 from 9 up (9, 10 measured slower at 4096).
+    // a substep faster: alone on an SM 0.8 ms instead of 1.25 ms.  Fused kernel: ONE round of blocks over the SMs while that
+    // needs at most 7 slices per block (ceil(B / SMs)), above that about two rounds (ceil(B / 2 SMs) slices).  Two rounds of small
+    // blocks win when environments differ in cost (heaviest first, the second round is the cheap ones: bench workload, B = 1024:
+    // 4 slices 21.1 ms vs 7 slices 24.2; B = 1536: 6 slices 23.2 vs 11 slices 30.8) and lose badly when they do not (policy
+    // rollout around the home pose, B = 1024: 11.8 vs 7.8 ms; B = 512: 2 slices 10.5 vs 4 slices 6.2) -- profiles/r2_sweeps.txt.
+    // Split pipeline: one round per group, ceil(B / groups / SMs) slices, 11 from 9 up (9, 10 measured slower at 4096).
     const int per_sm_envs = std::max(1, ((num_envs + ng - 1) / ng + sms - 1) / sms);
-    const int fused_envs = std::max(1, (num_envs + 2 * sms - 1) / (2 * sms));
+    const int one_round = std::max(1, (num_envs + sms - 1) / sms), two_rounds = std::max(1, (num_envs + 2 * sms - 1) / (2 * sms));
+    const int fused_envs = one_round <= 7 ? one_round : two_rounds;
     const int auto_envw = b->split ? (per_sm_envs >= 9 ? AV_DEFAULT_ENVW : per_sm_envs) : std::min(AV_DEFAULT_ENVW, fused_envs);
     b->envw = ee ? atoi(ee) : std::min(b->warps, auto_envw);
     b->envw = std::max(1, std::min(b->envw, std::min(b->warps, std::min(AV_MAX_ENVW, (smem_blk - 64) / esz))));

@@ -472,8 +472,24 @@ def run_gpu(args):
             cores = os.cpu_count() or 1
             n_envs, n_steps = 2 * max(cores, 4), 100
             _, line["cpu_baseline"] = cpu_baseline(args, n_envs, n_steps, cores)
-        print(json.dumps(line))
     venv.close()
+    del venv, batch
+    # ---- BASELINE.json configs[4] as an extra object of the same line (all ranks take part): one policy rollout of 1024
+    # environments in total, sharded over the ranks, 4 cameras at 480 x 640 rendered lazily, device-resident observations, one
+    # all_gather of the episode results -- so the driver's 1..8-GPU runs carry the strong-scaling curve of the evaluation loop too
+    c5 = None
+    if not args.no_config5:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import eval_rollout
+            c5 = eval_rollout.run(world, rank, dev, batch_total=1024, n_cameras=4, steps=EPISODE_LEN, rollouts=1, lazy=True,
+                                  warm_rollout_steps=None)
+        except Exception as e:   # the headline line must survive a failure of the extra leg
+            c5 = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0:
+        if c5 is not None:
+            line["config5"] = c5
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -495,6 +511,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch environments per GPU; strong: --batch environments in total, sharded over the ranks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config5", action="store_true", dest="no_config5", help="skip the extra config-5 rollout leg")
     ap.add_argument("--no-clocks", action="store_true", dest="no_clocks", help="diagnostic: do not poll nvidia-smi during the run")
     ap.add_argument("--no-flush", action="store_true", dest="no_flush", help="diagnostic: do not flush L2 between timed steps")
     ap.add_argument("--preroll", type=int, default=EPISODE_LEN, help="untimed steps that bring the staggered batch to steady state")

@@ -61,6 +61,55 @@ class ChunkPolicy(nn.Module):
         return self._action_queue.popleft()
 
 
+def run(world, rank, dev, batch_total=1024, task="SlotInsertion", n_cameras=4, steps=300, rollouts=1, lazy=True, height=480, width=640,
+        warm_rollout_steps=None):
+    """One config-5 measurement on an already initialised process group (or a single process): `rollouts` rollouts of
+    `batch_total` environments sharded over the ranks, device-timed (CUDA events, max over ranks).  Returns the result line on
+    rank 0, None elsewhere.  warm_rollout_steps: length of the untimed warm-up rollout (default: a full one)."""
+    lo, hi = sharding.shard_range(batch_total, rank, world)
+    cams = CAMS[:n_cameras]
+    env = GuidedVisionVectorEnv(task, hi - lo, cameras=cams, max_episode_steps=steps, device=dev.index, seed=1000 + rank,
+                                observation_height=height, observation_width=width)
+    torch.manual_seed(0)
+    policy = ChunkPolicy(cams).to(dev)
+    results = []
+    if warm_rollout_steps:                                                  # short warm-up: allocations, queue order
+        env._max_episode_steps = int(warm_rollout_steps)
+    observation.rollout(env, policy, lazy_render=lazy)
+    env._max_episode_steps = steps
+    warm_calls = policy.forward_calls
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(rollouts):
+        out = observation.rollout(env, policy, lazy_render=lazy)
+        done_before = torch.cat([torch.zeros_like(out["done"][:, :1]), out["done"][:, :-1]], dim=1)
+        rew = out["reward"].masked_fill(done_before, 0.0)                   # eval.py:283-290: mask steps after the first done
+        results.append(sharding.gather_episode_stats(out["success"].any(dim=1), rew.max(dim=1).values.to(torch.int32),
+                                                     rew.sum(dim=1).float(), batch_total))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    wall = time.perf_counter() - t0
+    dt = float(ms.item()) * 1e-3
+    line = None
+    if rank == 0:
+        succ, mx, sm = (torch.cat([r[k] for r in results]) for k in range(3))
+        line = {"tool": "eval_rollout", "task": task, "n_gpus": world, "batch": batch_total, "rollouts": rollouts,
+                "episode_steps": steps, "cameras": cams, "frame": [height, width], "lazy_render": lazy,
+                "episodes_per_s": batch_total * rollouts / dt, "env_steps_per_s": batch_total * rollouts * steps / dt,
+                "policy_forward_calls_per_rollout": (policy.forward_calls - warm_calls) / rollouts, "device_s": dt, "wall_s": wall,
+                "timing": "CUDA events around the rollouts, max over ranks",
+                "aggregated": sharding.aggregate(succ, mx, sm), "policy": "random-init ACT-shaped stand-in (chunks of 50)"}
+    env.close()
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--task", default="SlotInsertion")
@@ -77,37 +126,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lo, hi = sharding.shard_range(args.batch, rank, world)
-    cams = CAMS[: args.cameras]
-    env = GuidedVisionVectorEnv(args.task, hi - lo, cameras=cams, max_episode_steps=args.steps, device=local, seed=1000 + rank,
-                                observation_height=args.height, observation_width=args.width)
-    torch.manual_seed(0)
-    policy = ChunkPolicy(cams).to(dev)
-    results = []
-    observation.rollout(env, policy, lazy_render=not args.no_lazy)         # warm-up rollout (allocations, queue order)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.rollouts):
-        out = observation.rollout(env, policy, lazy_render=not args.no_lazy)
-        done_before = torch.cat([torch.zeros_like(out["done"][:, :1]), out["done"][:, :-1]], dim=1)
-        rew = out["reward"].masked_fill(done_before, 0.0)                   # eval.py:283-290: mask steps after the first done
-        results.append(sharding.gather_episode_stats(out["success"].any(dim=1), rew.max(dim=1).values.to(torch.int32),
-                                                     rew.sum(dim=1).float(), args.batch))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    dt = time.perf_counter() - t0
+    line = run(world, rank, dev, args.batch, args.task, args.cameras, args.steps, args.rollouts, not args.no_lazy, args.height, args.width)
     if rank == 0:
-        succ, mx, sm = (torch.cat([r[k] for r in results]) for k in range(3))
-        line = {"tool": "eval_rollout", "task": args.task, "n_gpus": world, "batch": args.batch, "rollouts": args.rollouts,
-                "episode_steps": args.steps, "cameras": cams, "lazy_render": not args.no_lazy,
-                "episodes_per_s": args.batch * args.rollouts / dt, "env_steps_per_s": args.batch * args.rollouts * args.steps / dt,
-                "policy_forward_calls_per_rollout": policy.forward_calls / (args.rollouts + 1), "wall_s": dt,
-                "aggregated": sharding.aggregate(succ, mx, sm), "policy": "random-init ACT-shaped stand-in (chunks of 50)"}
         print(json.dumps(line))
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
