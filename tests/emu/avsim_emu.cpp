@@ -131,6 +131,18 @@ void emu_step(EmuBatch *b, const float *action, int nsub) {
     } else
         emu::run_block(0, 1, [&]() { avsim_step_kernel(b->pk.dm, b->st, action, nsub); });   // one block drains the queue
 }
+// the queue-order kernel on its own: n environments with the given cycle counts, sorted in chunks of `chunk` (one block each)
+void emu_order(EmuBatch *b, const long long *cycles, int n, int chunk, int *order_out) {
+    BatchState st = b->st;
+    int queue = -1;
+    st.num_envs = n;
+    st.env_cycles = const_cast<long long *>(cycles);
+    st.order = order_out;
+    st.queue = &queue;
+    int n2 = 1, nch = (n + chunk - 1) / chunk;
+    while (n2 < (n < chunk ? n : chunk)) n2 <<= 1;
+    for (int c = 0; c < nch; c++) emu::run_block(c, nch, [&]() { avsim_order_kernel(st, n2, chunk); });
+}
 void emu_reset_masked(EmuBatch *b, const uint8_t *mask, const float *free_pos) {
     int nb = (b->st.num_envs + 31) / 32;
     for (int blk = 0; blk < nb; blk++)

@@ -154,3 +154,33 @@ def test_reset_state_follows_the_reference_reset(ctx):
     assert np.abs(eb.qpos[0, 23:26] - fp[0, 0]).max() <= 1e-7 and np.abs(eb.qpos[0, 26:30] - [1, 0, 0, 0]).max() == 0.0
     assert np.abs(eb.qpos[0, 30:33] - fp[0, 1]).max() <= 1e-7 and np.abs(eb.qpos[0, 33:37] - [1, 0, 0, 0]).max() == 0.0
     assert np.abs(eb.agent_pos[0, [6, 13]] - 1.0).max() <= 1e-6 and eb.reward[0] == 0
+
+
+def test_order_kernel_chunked_sort_is_a_heaviest_first_permutation(slot_model_path):
+    """The queue-order kernel (source compiled for the host): one block sorts up to `chunk` environments by last step's cost,
+    larger batches are sorted chunk by chunk and interleaved.  Checked: a permutation for every size, exactly sorted (ties in
+    environment order) within one chunk, heaviest-first to within the interleaving for several chunks, ragged last chunk."""
+    import ctypes as C
+    from tests.emu import emu
+    eb = emu.EmuBatch(slot_model_path, 1)
+    L = emu.lib()
+    L.emu_order.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(0)
+    for n, chunk in ((1, 64), (37, 64), (64, 64), (65, 64), (200, 64), (1000, 256), (513, 256)):
+        cyc = rng.integers(0, 50, n).astype(np.int64) * 1000            # many ties
+        order = np.full(n, -1, np.int32)
+        L.emu_order(eb.ptr, cyc.ctypes.data_as(C.POINTER(C.c_longlong)), n, chunk, order.ctypes.data_as(C.POINTER(C.c_int)))
+        assert sorted(order.tolist()) == list(range(n)), (n, chunk)     # every environment exactly once
+        nch = (n + chunk - 1) // chunk
+        if nch == 1:
+            want = np.lexsort((np.arange(n), -cyc))                      # descending cost, ties in ascending environment order
+            assert np.array_equal(order, want), (n, chunk)
+        else:
+            for c in range(nch):                                         # each chunk's environments appear in sorted order ...
+                mine = [e for e in order if c * chunk <= e < (c + 1) * chunk]
+                lo = c * chunk
+                m = min(chunk, n - lo)
+                want = lo + np.lexsort((np.arange(m), -cyc[lo:lo + m]))
+                assert mine == want.tolist(), (n, chunk, c)
+            first = order[:nch]                                          # ... and the queue starts with every chunk's heaviest
+            assert sorted(first // chunk) == list(range(nch))
