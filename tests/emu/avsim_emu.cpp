@@ -58,6 +58,7 @@ struct EmuBatch {
     std::vector<int> order, queue, fckey, fcn, order_b, queue_b;
     std::vector<float> fcval, heads;
     std::vector<long long> cyc_b;
+    int split = 1;   // Newton: 1 = substep + solve kernels (large batches on the device), 0 = the fused step kernel (small batches)
 };
 
 extern "C" {
@@ -91,6 +92,7 @@ EmuBatch *emu_create(const char *path, int num_envs) {
 }
 void emu_destroy(EmuBatch *b) { delete b; }
 void emu_set_warmstart(EmuBatch *b, int mode) { b->st.warm_mode = mode; }
+void emu_set_split(EmuBatch *b, int split) { b->split = split; }
 void emu_set_solver(EmuBatch *b, int solver, int max_iter, int ls_iter, float tol) {
     b->st.solver = solver; b->st.newton_iters = max_iter; b->st.newton_ls = ls_iter; b->st.newton_tol = tol;
 }
@@ -123,7 +125,7 @@ void emu_step(EmuBatch *b, const float *action, int nsub) {
     int n2 = 1;
     while (n2 < b->st.num_envs) n2 <<= 1;
     emu::run_block(0, 1, [&]() { avsim_order_kernel(b->st, n2, 8192); });   // same queue order as the device
-    if (b->st.solver == 1) {   // split pipeline, as avsim_step launches it
+    if (b->st.solver == 1 && b->split) {   // split pipeline, as avsim_step launches it above ~2 500 environments
         for (int s = 0; s <= nsub; s++) {
             emu::run_block(0, 1, [&]() { avsim_substep_kernel(b->pk.dm, b->st, action, s, nsub); });
             if (s < nsub) emu::run_block(0, 1, [&]() { avsim_solve_kernel(b->pk.dm, b->st); });

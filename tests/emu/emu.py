@@ -79,6 +79,11 @@ class EmuBatch:
     def set_solver(self, solver="newton", max_iter=30, ls_iter=20, tol=1e-6):
         lib().emu_set_solver(self.ptr, {"pgs": 0, "newton": 1}[solver], max_iter, ls_iter, tol)
 
+    def set_split(self, split):
+        """Newton only: True = the split pipeline (substep + solve kernels), False = the fused step kernel"""
+        lib().emu_set_split.argtypes = [C.c_void_p, C.c_int]
+        lib().emu_set_split(self.ptr, int(bool(split)))
+
     def forward(self):
         lib().emu_forward(self.ptr)
 

@@ -103,6 +103,35 @@ def test_emulated_cuda_newton_vs_oracle_same_contacts():
             assert eb.nw_stat[0][3] == 0 and eb.nw_stat[0][0] <= 20     # converged well inside the iteration cap
 
 
+def test_emulated_env_step_fused_and_split_pipelines_next_to_oracle():
+    """One env.step (20 substeps: collision, Newton, noslip, Euler) from a contact-rich state through BOTH launch forms of the
+    CUDA source -- the split pipeline (substep + solve kernels, head records in between) and the fused step kernel -- on the
+    host emulator, next to the fp64 oracle.  The two forms run the same stage code: they agree with each other far inside their
+    distance to the oracle."""
+    from av_aloha_b200 import model_io
+    from oracle.oracle import OracleEnv, OracleModel
+    from tests.emu.emu import EmuBatch
+    path = model_io.model_path("slot_insertion", 3)
+    om, st = OracleModel(path), _states("slot_insertion")
+    for e in (5, 200):
+        o = OracleEnv(om)
+        o.qpos[:], o.qvel[:], o.ctrl[:], o.qacc_warmstart[:] = st["qpos"][e], st["qvel"][e], st["ctrl"][e], st["warm"][e]
+        o.set_options(max_iter=100, tol=1e-12, warmstart=1)
+        act = np.concatenate([st["ctrl"][e][:6], [0.5], st["ctrl"][e][7:13], [0.5], st["ctrl"][e][14:21]])
+        nq_arm = 23
+        r = o.step(act.astype(np.float64))
+        out = {}
+        for form in (True, False):
+            eb = EmuBatch(path, 1)
+            eb.set_split(form)
+            eb.qpos[0], eb.qvel[0], eb.ctrl[0], eb.warm[0] = st["qpos"][e], st["qvel"][e], st["ctrl"][e], st["warm"][e]
+            eb.step(act[None].astype(np.float32))
+            assert eb.status[0] == 0 and int(eb.reward[0]) == r and int(eb.ncon[0]) == o.ncon, (e, form)
+            out[form] = eb.qpos[0].copy()
+            assert np.abs(out[form][:nq_arm] - o.qpos[:nq_arm]).max() <= 2e-4, (e, form)
+        assert np.abs(out[True] - out[False]).max() <= 2e-5, e
+
+
 # ------------------------------------------------------------------------------------------ GPU
 def _mobile_dofs(path):
     """dofs that can move: HookPackage's hook hangs on a free joint with damping 1e9 (reference assets/task_hook_package.xml:10),
