@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(AV_RT_THREADS) avsim_render_kernel(const __gri
                                                                      int ncam_all, int H, int W, unsigned char *__restrict__ dst, int id_mode) {
     __shared__ RGeom sg[AV_RT_MAXG];
     __shared__ int s_n;
-    __shared__ int s_gid[AV_RT_MAXG];
-    __shared__ float s_z[AV_RT_MAXG];
+    __shared__ int s_gid[AV_NG];
+    __shared__ float s_z[AV_NG];
     __shared__ unsigned int s_tile[AV_RT_H][AV_RT_W * 3 / 4];
     const int tiles_x = (W + AV_RT_W - 1) / AV_RT_W;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, ci = blockIdx.y, env = blockIdx.z;
@@ -244,18 +244,20 @@ __global__ void __launch_bounds__(AV_RT_THREADS) avsim_render_kernel(const __gri
             float4 dg = rr[3 * g + 1];   // region extents along x+y: [x0+y0, x1+y1], along x-y: [x0-y1, x1-y0]
             if (dg.x > x1 + y1 || dg.z < x0 + y0 || dg.y > x1 - y0 || dg.w < x0 - y1) continue;
             int k = atomicAdd(&s_n, 1);
-            if (k < AV_RT_MAXG) { s_gid[k] = g; s_z[k] = rr[3 * g + 2].x; }
+            if (k < AV_NG) { s_gid[k] = g; s_z[k] = rr[3 * g + 2].x; }
         }
         __syncthreads();
-        const int nk = min(s_n, AV_RT_MAXG);
-        int my_g = 0, my_rank = 0;
-        if (tid < nk) {   // rank sort (nk <= 64): ties broken by geom id so the order, and the picture, are deterministic
+        const int nall = min(s_n, AV_NG);          // every geom that overlaps the region (a model has at most AV_NG)
+        const int nk = min(nall, AV_RT_MAXG);      // ... of which the AV_RT_MAXG nearest are kept
+        int my_g = 0, my_rank = AV_NG;
+        if (tid < nall) {   // rank sort: ties broken by geom id, so the order, the kept set and the picture do not depend on the atomics
             my_g = s_gid[tid];
+            my_rank = 0;
             float z = s_z[tid];
-            for (int j = 0; j < nk; j++) my_rank += (s_z[j] < z || (s_z[j] == z && s_gid[j] < my_g)) ? 1 : 0;
+            for (int j = 0; j < nall; j++) my_rank += (s_z[j] < z || (s_z[j] == z && s_gid[j] < my_g)) ? 1 : 0;
         }
         __syncthreads();
-        if (tid < nk) s_gid[my_rank] = my_g;
+        if (my_rank < nk) s_gid[my_rank] = my_g;
         __syncthreads();
         for (int idx = tid; idx < nk * 64; idx += blockDim.x) {
             const int k = idx >> 6, f = idx & 63, g = s_gid[k];
