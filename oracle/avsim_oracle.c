@@ -11,8 +11,11 @@
  * restates MuJoCo's *published* pipeline and is validated by closed forms and
  * invariants (tests/test_physics_known_answers.py: free fall + spin, static equilibrium, box inertias, virtual work,
  * kinetic energy, cone feasibility, box-box / sphere-box / MPR narrowphase), not against MuJoCo outputs.  Where the algorithm is a free choice
- * (box-box manifold, MPR penetration after libccd, block PGS on the dual), the choice is stated here
- * and the CUDA path (av_aloha_b200/csrc) follows the same statement in fp32, written independently.
+ * (box-box manifold, MPR penetration after libccd), the choice is stated here and the CUDA path (av_aloha_b200/csrc) follows the
+ * same statement in fp32, written independently.  The constraint solve is MuJoCo's default: Newton on the primal problem with an
+ * exact line search (solve_newton; tolerance-based, + noslip sweeps); the block Gauss-Seidel on the dual of round 1 is kept as a
+ * second, independent algorithm for the same optimum (ora_set_solver) -- the two are checked against each other
+ * (tests/test_solver_newton.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
  */
